@@ -1,0 +1,458 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a.
+//
+//   D[M,N] (+)= epilogue( alpha * sum_k A(m,k) * B(n,k) )        bf16 x bf16 -> fp32 accumulate in TMEM
+//
+// This one kernel serves every dense contraction of the MultimodalSum training step
+// (reference: nn.Linear / F.linear call sites in src/transformer/modeling_multimodalsum.py
+// :272-273,428-429,695-704,2281 and their autograd backward):
+//   fprop   y = x W^T        A = x  [M,K]  K-major      B = W  [N,K]  K-major
+//   dgrad   dx = dy W        A = dy [M,N'] K-major      B = W  [N',K'] read as MN-major (no transposed copy)
+//   wgrad   dW = dy^T x      A = dy [T,N'] MN-major     B = x  [T,K'] MN-major, split-K + TMA reduce-add (fp32)
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0     TMA producer   global -> 128B-swizzled smem ring (kStages deep), mbarrier expect_tx
+//   warp 1     MMA issuer     one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM; tcgen05.commit
+//                             releases smem stages and publishes finished accumulators
+//   warps 2-5  epilogue       tcgen05.ld TMEM -> registers, alpha/bias/GELU/ReLU/d-activation, bf16 or fp32,
+//                             swizzled smem staging, TMA store (or TMA reduce-add for split-K / grad accumulation)
+// TMEM holds two accumulator stages (2 x BN fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Ragged M/N/K edges rely on TMA: out-of-bounds loads are zero-filled, out-of-bounds stores are clipped.
+#include "common.cuh"
+#include "../../include/mmsum_b200.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <unordered_map>
+#include <string.h>
+
+namespace mmsum {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;       // 64 bf16 = 128 B = one swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int kGemmThreads = 192;
+static constexpr int kEpiWarps = 4;
+static constexpr int kEpiBufBytes = 32 * 128;  // 32 rows x 128 B per staging buffer
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes + kEpiBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+};
+
+struct GemmKernelArgs {
+  int M, N, K;
+  int m_tiles, n_tiles, splits, k_per_split;
+  int raster_m_fast;
+  float alpha;
+  const float* bias;
+  int act;        // 0 none, 1 gelu(erf), 2 relu
+  int aux_mode;   // 0 none, 1 store pre-activation to aux, 2 multiply by act'(aux)
+  bf16* aux;
+  long long ld_aux;
+  int out_f32;
+  int accumulate;
+};
+
+__device__ __forceinline__ void decode_tile(const GemmKernelArgs& g, int t, int& mt, int& nt, int& sp) {
+  const int mn = g.m_tiles * g.n_tiles;
+  sp = t / mn;
+  const int r = t - sp * mn;
+  if (g.raster_m_fast) { mt = r % g.m_tiles; nt = r / g.m_tiles; }
+  else                 { nt = r % g.n_tiles; mt = r / g.n_tiles; }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmD, const GemmKernelArgs g) {
+  using L = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + L::kStages;
+  uint64_t* tfull_bar = empty_bar + L::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = g.m_tiles * g.n_tiles * g.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < L::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * 32); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int mt, nt, sp; decode_tile(g, t, mt, nt, sp);
+        const int m0 = mt * BM, n0 = nt * BN;
+        const int k_begin = sp * g.k_per_split;
+        const int k_end = min(g.K, k_begin + g.k_per_split);
+        for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * L::kStageBytes;
+          uint8_t* sB = sA + L::kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+          }
+          if (++stage == L::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int mt, nt, sp; decode_tile(g, t, mt, nt, sp);
+        const int k_begin = sp * g.k_per_split;
+        const int k_end = min(g.K, k_begin + g.k_per_split);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        uint32_t accum = 0;
+        for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t aaddr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t baddr = aaddr + L::kABytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            // K-major: 8-row groups are 1024 B apart (SBO); a K step of 16 elements is +32 B inside the swizzle row.
+            // MN-major: 64-wide MN blocks are 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO); K step = 16 rows = 2048 B.
+            const uint64_t ad = A_MN ? umma_smem_desc_sw128(aaddr + kk * 2048, 8192, 1024)
+                                     : umma_smem_desc_sw128(aaddr + kk * 32, 16, 1024);
+            const uint64_t bd = B_MN ? umma_smem_desc_sw128(baddr + kk * 2048, 8192, 1024)
+                                     : umma_smem_desc_sw128(baddr + kk * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, accum);
+            accum = 1;
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == L::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);       // accumulator complete
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int ew = warp - 2;
+    uint8_t* stg = smem + L::kStages * L::kStageBytes + ew * 2 * kEpiBufBytes;
+    int as = 0; uint32_t aphase = 0;
+    int buf = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int mt, nt, sp; decode_tile(g, t, mt, nt, sp);
+      const int m0 = mt * BM, n0 = nt * BN;
+      const int row = m0 + q * 32 + lane;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int ncol0 = n0 + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(tbase + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * g.alpha;
+        if (g.bias != nullptr && sp == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { const int n = ncol0 + i; v[i] += (n < g.N) ? __ldg(g.bias + n) : 0.f; }
+        }
+        if (g.aux_mode == 1) {
+          if (row < g.M) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = ncol0 + j * 8;
+              if (n + 8 <= g.N) {
+                uint4 pk;
+                pk.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]); pk.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+                pk.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]); pk.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+                *reinterpret_cast<uint4*>(g.aux + (size_t)row * g.ld_aux + n) = pk;
+              }
+            }
+          }
+        }
+        if (g.aux_mode != 2) {
+          if (g.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          } else if (g.act == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+        } else {
+          // v *= act'(aux): backward through the activation fused into the dgrad epilogue
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = ncol0 + j * 8;
+            uint4 pk = make_uint4(0, 0, 0, 0);
+            if (row < g.M && n + 8 <= g.N) pk = *reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.ld_aux + n);
+            const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 h = unpack_bf16(w[e]);
+              if (g.act == 1) { v[j * 8 + 2 * e] *= gelu_erf_grad(h.x); v[j * 8 + 2 * e + 1] *= gelu_erf_grad(h.y); }
+              else            { v[j * 8 + 2 * e] *= (h.x > 0.f) ? 1.f : 0.f; v[j * 8 + 2 * e + 1] *= (h.y > 0.f) ? 1.f : 0.f; }
+            }
+          }
+        }
+        // ---- stage to swizzled smem and TMA-store ----
+        if (g.out_f32) {
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* b = stg + buf * kEpiBufBytes + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 f = make_float4(v[j * 4 + 0], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+            *reinterpret_cast<float4*>(b + ((j ^ (lane & 7)) << 4)) = f;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (ncol0 < g.N && m0 + q * 32 < g.M) {
+              if (g.accumulate) tma_reduce_add_2d(&tmD, stg + buf * kEpiBufBytes, ncol0, m0 + q * 32);
+              else              tma_store_2d(&tmD, stg + buf * kEpiBufBytes, ncol0, m0 + q * 32);
+            }
+            tma_store_commit();
+          }
+          buf ^= 1;
+        } else {
+          const int half = c & 1;
+          if (half == 0) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
+          uint8_t* b = stg + buf * kEpiBufBytes + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            pk.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]); pk.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+            pk.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]); pk.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+            *reinterpret_cast<uint4*>(b + (((half * 4 + j) ^ (lane & 7)) << 4)) = pk;
+          }
+          if (half == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int x = n0 + (c >> 1) * 64;
+              if (x < g.N && m0 + q * 32 < g.M) tma_store_2d(&tmD, stg + buf * kEpiBufBytes, x, m0 + q * 32);
+              tma_store_commit();
+            }
+            buf ^= 1;
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// host side: tensor-map cache + launch
+// ----------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+static std::mutex g_mu;
+
+static int get_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) return MMSUM_ERR_DRIVER;
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  return 0;
+}
+
+struct TmKey {
+  const void* ptr; uint64_t inner, outer, ld_bytes; uint32_t box_inner, box_outer; int dtype;
+  bool operator==(const TmKey& o) const { return memcmp(this, &o, sizeof(TmKey)) == 0; }
+};
+struct TmKeyHash {
+  size_t operator()(const TmKey& k) const {
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ULL;
+    for (size_t i = 0; i < sizeof(TmKey) / 8; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
+    return (size_t)h;
+  }
+};
+static std::unordered_map<TmKey, CUtensorMap, TmKeyHash> g_tm_cache;
+
+// 2D row-major tensor [outer, inner] with row pitch ld_bytes; box = [box_outer, box_inner]; 128B swizzle.
+static int make_tmap(CUtensorMap* out, const void* ptr, int dtype /*0 bf16, 1 f32*/, uint64_t inner, uint64_t outer,
+                     uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer) {
+  TmKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.inner = inner; key.outer = outer; key.ld_bytes = ld_bytes;
+  key.box_inner = box_inner; key.box_outer = box_outer; key.dtype = dtype;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_tm_cache.find(key);
+  if (it != g_tm_cache.end()) { *out = it->second; return 0; }
+  if (int rc = get_encode()) return rc;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld_bytes & 15)) return MMSUM_ERR_INVALID;
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {ld_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return MMSUM_ERR_DRIVER;
+  if (g_tm_cache.size() > 65536) g_tm_cache.clear();
+  g_tm_cache.emplace(key, *out);
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else n = kNumSMs;
+  }
+  return n;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmKernelArgs& ka,
+                       int grid, cudaStream_t stream) {
+  using L = GemmSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  gemm_tcgen05_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, td, ka);
+  MMSUM_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace mmsum
+
+using namespace mmsum;
+
+extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!a || !a->A || !a->B || !a->D) return MMSUM_ERR_INVALID;
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return MMSUM_ERR_INVALID;
+  if (!a->out_f32 && a->accumulate) return MMSUM_ERR_INVALID;
+  if (a->aux_mode != 0 && (!a->aux || (a->N % 8) != 0 || (a->ld_aux % 8) != 0)) return MMSUM_ERR_INVALID;
+  int bn = a->block_n;
+  if (bn == 0) bn = (a->N > 128) ? 256 : 128;
+  if (bn != 128 && bn != 256) return MMSUM_ERR_INVALID;
+
+  GemmKernelArgs ka;
+  ka.M = a->M; ka.N = a->N; ka.K = a->K;
+  ka.m_tiles = (a->M + BM - 1) / BM;
+  ka.n_tiles = (a->N + bn - 1) / bn;
+  const int kblocks = (a->K + BK - 1) / BK;
+  int splits = a->splits;
+  if (splits <= 0) {
+    // auto split-K: only when accumulating fp32 output and the MN grid cannot fill the machine
+    splits = 1;
+    const int mn = ka.m_tiles * ka.n_tiles;
+    if (a->out_f32 && a->accumulate && mn < kNumSMs) {
+      splits = (2 * kNumSMs + mn - 1) / mn;
+      if (splits > kblocks / 4) splits = kblocks / 4;
+      if (splits < 1) splits = 1;
+    }
+  }
+  if (splits > 1 && !(a->out_f32 && a->accumulate)) return MMSUM_ERR_INVALID;
+  int kb_per_split = (kblocks + splits - 1) / splits;
+  splits = (kblocks + kb_per_split - 1) / kb_per_split;  // no empty split
+  ka.splits = splits;
+  ka.k_per_split = kb_per_split * BK;
+  ka.raster_m_fast = a->raster_m_fast;
+  ka.alpha = a->alpha;
+  ka.bias = a->bias;
+  ka.act = a->act;
+  ka.aux_mode = a->aux_mode;
+  ka.aux = reinterpret_cast<bf16*>(a->aux);
+  ka.ld_aux = a->ld_aux;
+  ka.out_f32 = a->out_f32;
+  ka.accumulate = a->accumulate;
+
+  CUtensorMap ta, tb, td;
+  int rc;
+  // A: K-major = [M rows, K cols], box {64(k), 128(m)};  MN-major = [K rows, M cols], box {64(m), 64(k)}
+  if (a->a_mn_major) rc = make_tmap(&ta, a->A, 0, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda * 2, 64, 64);
+  else               rc = make_tmap(&ta, a->A, 0, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, 64, BM);
+  if (rc) return rc;
+  if (a->b_mn_major) rc = make_tmap(&tb, a->B, 0, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, 64);
+  else               rc = make_tmap(&tb, a->B, 0, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, 64, (uint32_t)bn);
+  if (rc) return rc;
+  if (a->out_f32) rc = make_tmap(&td, a->D, 1, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 4, 32, 32);
+  else            rc = make_tmap(&td, a->D, 0, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 64, 32);
+  if (rc) return rc;
+
+  if (ka.splits > 1 && (a->act != 0 || a->aux_mode != 0)) return MMSUM_ERR_INVALID;
+  const int total = ka.m_tiles * ka.n_tiles * ka.splits;
+  const int nsm = num_sms();
+  const int grid = total < nsm ? total : nsm;
+  const int am = a->a_mn_major ? 1 : 0, bm = a->b_mn_major ? 1 : 0;
+#define MMSUM_GEMM_CASE(BN_, AM_, BM_) \
+  if (bn == BN_ && am == AM_ && bm == BM_) return launch_gemm<BN_, (AM_ != 0), (BM_ != 0)>(ta, tb, td, ka, grid, stream);
+  MMSUM_GEMM_CASE(256, 0, 0)
+  MMSUM_GEMM_CASE(256, 0, 1)
+  MMSUM_GEMM_CASE(256, 1, 1)
+  MMSUM_GEMM_CASE(256, 1, 0)
+  MMSUM_GEMM_CASE(128, 0, 0)
+  MMSUM_GEMM_CASE(128, 0, 1)
+  MMSUM_GEMM_CASE(128, 1, 1)
+  MMSUM_GEMM_CASE(128, 1, 0)
+#undef MMSUM_GEMM_CASE
+  return MMSUM_ERR_INVALID;
+}
