@@ -51,7 +51,8 @@ def _import_reference():
         import transformer  # vendored HF 3.0.2
         import transformers
         if not hasattr(transformers, "AdamW"):
-            transformers.AdamW = transformer.optimization.AdamW
+            from transformer.optimization import AdamW as _RefAdamW  # vendored copy of transformers 3.0.2 AdamW
+            transformers.AdamW = _RefAdamW
         import multimodal_train as MT
         import table_encoder as TE
         import utils as U
@@ -116,6 +117,34 @@ def reference_step(cfg, state_dict, batch, dtype=torch.float64, label_smoothing=
     img = batch.img.to(dtype)
     loss = model(batch.reviews, batch.reviews_mask, batch.reviews_rating.to(dtype), batch.field, batch.field_value,
                  img, batch.img_mask)[0]
+    model.zero_grad()
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    return loss.detach(), grads, model
+
+
+def reference_text_step(cfg, state_dict, batch, dtype=torch.float32, label_smoothing=None):
+    """BASELINE config 1: the reference's text-only step — text_pretrain.TextSupervised.forward
+    (src/text_pretrain.py:71-113) around BartForEncConditionalGeneration, plain CrossEntropyLoss by default."""
+    m = _import_reference()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import text_pretrain as TP
+    TP.args = argparse.Namespace(label_smoothing=label_smoothing)
+    if label_smoothing is not None:
+        TP.LabelSmoothingLoss = m["U"].LabelSmoothingLoss  # quirk Q6: text_pretrain.py never imports it
+    bcfg = m["BartConfig"].from_json_file(os.path.join(REF_ROOT, "cfg", "bart-large.json"))
+    for k, v in cfg.to_reference_dict().items():
+        setattr(bcfg, k, v)
+    bcfg.dropout = 0.0
+    model = TP.TextSupervised.__new__(TP.TextSupervised)
+    nn.Module.__init__(model)
+    model.bart_model = m["Enc"](bcfg)
+    missing, unexpected = model.load_state_dict(state_dict, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    model = model.to(dtype).train()
+    loss = model(batch.reviews, batch.reviews_mask, batch.reviews_rating.to(dtype))[0]
     model.zero_grad()
     loss.backward()
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
