@@ -41,8 +41,121 @@ typedef struct MmsumGemmArgs {
   int32_t aux_mode;   /* 0 none, 1 store pre-activation (bf16) to aux, 2 multiply result by act'(aux) */
   void* aux;          /* bf16 [M,N] */
   int64_t ld_aux;
+  const void* A2;     /* optional: A = [A | A2] concatenated along K at k_split (K-major A only), else NULL */
+  int64_t lda2;
+  int32_t k_split;    /* multiple of 64 */
 } MmsumGemmArgs;
 int mmsum_gemm_bf16(const MmsumGemmArgs* args, void* stream);
+
+
+/* ---- multi-entity attention ----------------------------------------------------------------------
+ * Replaces SelfAttention.forward / get_head_output (src/transformer/modeling_multimodalsum.py:722-886) for the
+ * encoder self-attention, the decoder causal self-attention and the multi-modal multi-entity cross-attention
+ * (per-entity softmax, mean over valid entities, leave-one-out target exclusion of src/multimodal_train.py:150-163),
+ * and the backward autograd derives from them.  128 query positions per sequence, head_dim 64.
+ * Query sequence `qseq` belongs to business `qseq / R` and is leave-one-out target `qseq % R`. */
+typedef struct MmsumAttnMod {
+  int64_t kv_row_base; /* first KV row of this modality; entity (biz,e) starts at kv_row_base + (biz*E+e)*Sk */
+  int64_t o_off;       /* element offset of this modality's [n_qseq*128, ldo] output (fwd) / upstream grad (bwd) */
+  int32_t E;           /* entities per business */
+  int32_t Sk;          /* keys per entity */
+  int32_t loo;         /* 1: entity e is skipped for target e */
+  int32_t ent_base;    /* index of entity 0 of this modality in the [.., E_total] arrays */
+} MmsumAttnMod;
+
+typedef struct MmsumAttnArgs {
+  const void* Q;  int64_t ldq;  int32_t q_col;               /* bf16 [n_qseq*128, ldq], head h at q_col + 64h */
+  const void* KV; int64_t ldkv; int32_t k_col; int32_t v_col; /* bf16 memory rows; K head h at k_col+64h, V at v_col+64h */
+  void* O; int64_t ldo;            /* fwd: out (bf16); bwd: upstream gradient of the per-modality outputs */
+  float* LSE;                      /* [n_qseq, H, E_total, 128] log2-domain log-sum-exp (fwd out, bwd in) */
+  float* DELTA;                    /* [n_qseq, H, E_total, 128] bwd scratch */
+  const uint8_t* key_valid;        /* per KV row, 1 = attend; NULL = all valid */
+  const uint8_t* ent_valid;        /* [n_biz, E_total]; NULL = all valid */
+  const float* inv_n;              /* [n_qseq, n_mod] 1/#valid entities (0 when none); NULL = 1 */
+  void* dQ;  int64_t lddq;  int32_t dq_col;                   /* bwd out, bf16 */
+  void* dKV; int64_t lddkv; int32_t dk_col; int32_t dv_col;    /* bwd out, bf16, same row indexing as KV */
+  int32_t n_qseq, H, R, causal, n_mod, E_total;
+  float scale;
+  MmsumAttnMod mods[3];
+} MmsumAttnArgs;
+int mmsum_attn_fwd(const MmsumAttnArgs* args, void* stream);
+int mmsum_attn_bwd(const MmsumAttnArgs* args, void* stream); /* dQ/DELTA pass, then dK/dV pass */
+
+/* ---- HBM-bound row kernels (d_model = 1024) ----------------------------------------------------- */
+/* fp32 -> bf16 (weight arena cast, feature cast) */
+int mmsum_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* out = dropout(LN(E[ids] + P[t+2] + rating_diff[seq]*remb)): BartEncoder.forward modeling_multimodalsum.py:368-372,
+ * BartDecoder.forward :588-597, LearnedPositionalEmbedding :961-969.  rating_diff/remb NULL for the encoder. */
+int mmsum_embed_ln_fwd(const int32_t* ids, const float* E, const float* P, const float* rating_diff, const float* remb,
+                       const float* gamma, const float* beta, void* out, float* mean, float* rstd, int32_t rows,
+                       int32_t S, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+/* backward: scatter-add into dE (pad id skipped, nn.Embedding(padding_idx=1) :1001), dP, dremb, dgamma, dbeta (all +=) */
+int mmsum_embed_ln_bwd(const void* dout, const void* dout2 /* optional addend */, const int32_t* ids, const float* E, const float* P, const float* rating_diff,
+                       const float* remb, const float* gamma, const float* mean, const float* rstd, float* dE, float* dP,
+                       float* dremb, float* dgamma, float* dbeta, float* dz_scratch, int32_t rows, int32_t S,
+                       int32_t d_model, int32_t pad_id, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+
+/* out = LN(res + dropout(y)): the post-LN residual blocks of EncoderLayer.forward :288-308 / DecoderLayer.forward :442-489
+ * (LayerNorm factory :972-980, eps 1e-5).  Dropout masks are a pure function of (seed, stream_id, element). */
+int mmsum_add_ln_fwd(const void* res, const void* y, const float* gamma, const float* beta, void* out, float* mean,
+                     float* rstd, int32_t rows, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+/* backward: upstream = d1 (+ d2 if not NULL); dres = dz, dy = dz * mask (may alias dres when p_drop == 0); dgamma/dbeta += */
+int mmsum_add_ln_bwd(const void* d1, const void* d2, const void* res, const void* y, const float* gamma, const float* mean,
+                     const float* rstd, void* dres, void* dy, float* dgamma, float* dbeta, int32_t rows, int32_t d_model,
+                     float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+
+/* out[n] += sum_r x[r,n]  (bias gradients) */
+int mmsum_colsum(const void* x, int64_t ld, int32_t rows, int32_t N, float* out, void* stream);
+
+/* gate fusion of the three modalities, SelfAttention.forward :732-744.  o3 = [3][rows,D] (text, table, img out_proj
+ * outputs), u = [2][rows,D] (alpha/beta pre-activations), pres = [n_biz][2] modality presence, ab = [2][rows,D] gates out */
+int mmsum_gate_fwd(const void* o3, const void* u, const uint8_t* pres, void* y, void* ab, int32_t rows,
+                   int32_t rows_per_biz, int32_t d_model, void* stream);
+int mmsum_gate_bwd_u(const void* dy, const void* o3, const void* ab, void* du, int32_t rows, int32_t d_model, void* stream);
+int mmsum_gate_bwd_o(const void* dy, const void* ab, const void* dca, const void* dcb, void* do3, int32_t rows,
+                     int32_t d_model, void* stream);
+
+/* label-smoothed CE over bf16 logits [rows, ld] (src/utils.py:32-38; eps < 0: plain CE, src/text_pretrain.py:97);
+ * loss_rows[r] per-row loss (computed before the row is overwritten); loss_out (optional) = loss_scale * sum(loss_rows); write_grad: logits := dlogits * gscale */
+int mmsum_ce_fwd_bwd(void* logits, int64_t ld, int32_t rows, int32_t V, const int32_t* target, float eps, float gscale,
+                     const float* gscale_dev /* optional device scalar multiplied into gscale */, float* loss_rows, float* loss_out, float loss_scale, int32_t write_grad, void* stream);
+
+/* integer bookkeeping of one step: decoder inputs (shift_tokens_right :225-246), pad masks (:249-254), rating_diff
+ * (src/multimodal_train.py:154-156), memory key/entity validity, 1/#valid entities, modality presence */
+typedef struct MmsumPrepArgs {
+  int32_t B, R, S, F, n_img, img_keys, n_mod, pad_id, bos_id, eos_id;
+  int32_t* enc_ids;    /* [B*R*S] */
+  int32_t* dec_ids;    /* [B*R*S] */
+  int32_t* labels;     /* [B*R*S] */
+  uint8_t* enc_valid;  /* [B*R*S] */
+  uint8_t* dec_valid;  /* [B*R*S] */
+  uint8_t* mem_valid;  /* [B*R*S + B*F + B*n_img*img_keys] */
+  uint8_t* ent_valid;  /* [B, R + (F>0) + n_img] */
+  uint8_t* pres;       /* [B, 2] or NULL */
+  float* rating_diff;  /* [B*R] */
+  float* inv_n;        /* [B*R, n_mod] */
+} MmsumPrepArgs;
+int mmsum_prep_step(const int64_t* reviews, const int64_t* reviews_mask, const float* rating, const uint8_t* table_valid,
+                    const uint8_t* img_mask, const MmsumPrepArgs* args, void* stream);
+
+/* table-encoder front end: src/table_encoder.py:27-82 (yelp, dataset 0: v0..v5 = name, category, str_categorical,
+ * str_boolean, rating, hours; W0 = rating_embedding.weight, W1 = hours_embedding.weight) and :108-166 (amazon, dataset 1:
+ * v0..v5 = price, rating, brand, name, category, description; W0 = price_embedding.weight, W1 = rating_embedding.weight).
+ * X = [B, F, 2*1024] bf16 (names | values), valid = [B, F]. */
+typedef struct MmsumTableArgs {
+  int32_t dataset, B;
+  const float* E;
+  const int64_t* field;
+  const int64_t* v0; const int64_t* v1; const int64_t* v2; const int64_t* v3; const int64_t* v4; const int64_t* v5;
+  const float* W0; const float* W1;
+  void* X;
+  uint8_t* valid;
+} MmsumTableArgs;
+int mmsum_table_fwd(const MmsumTableArgs* args, void* stream);
+/* dW[c,j] += sum bits[b,row,j] * dX[b, f0+row, 1024 + c]   (rating / hours / price embedding gradients) */
+int mmsum_table_bits_bwd(const void* dX, const int64_t* bits, float* dW, int32_t B, int32_t F, int32_t f0, int32_t nrows,
+                         int32_t nb, void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,40 @@ class GemmArgs(C.Structure):
         ("block_n", C.c_int32), ("raster_m_fast", C.c_int32),
         ("alpha", C.c_float), ("bias", C.c_void_p),
         ("act", C.c_int32), ("aux_mode", C.c_int32), ("aux", C.c_void_p), ("ld_aux", C.c_int64),
+        ("A2", C.c_void_p), ("lda2", C.c_int64), ("k_split", C.c_int32),
     ]
+
+
+class AttnMod(C.Structure):
+    _fields_ = [("kv_row_base", C.c_int64), ("o_off", C.c_int64), ("E", C.c_int32), ("Sk", C.c_int32),
+                ("loo", C.c_int32), ("ent_base", C.c_int32)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("Q", C.c_void_p), ("ldq", C.c_int64), ("q_col", C.c_int32),
+        ("KV", C.c_void_p), ("ldkv", C.c_int64), ("k_col", C.c_int32), ("v_col", C.c_int32),
+        ("O", C.c_void_p), ("ldo", C.c_int64),
+        ("LSE", C.c_void_p), ("DELTA", C.c_void_p),
+        ("key_valid", C.c_void_p), ("ent_valid", C.c_void_p), ("inv_n", C.c_void_p),
+        ("dQ", C.c_void_p), ("lddq", C.c_int64), ("dq_col", C.c_int32),
+        ("dKV", C.c_void_p), ("lddkv", C.c_int64), ("dk_col", C.c_int32), ("dv_col", C.c_int32),
+        ("n_qseq", C.c_int32), ("H", C.c_int32), ("R", C.c_int32), ("causal", C.c_int32),
+        ("n_mod", C.c_int32), ("E_total", C.c_int32), ("scale", C.c_float),
+        ("mods", AttnMod * 3),
+    ]
+
+
+class PrepArgs(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "R", "S", "F", "n_img", "img_keys", "n_mod", "pad_id", "bos_id", "eos_id")] + \
+               [(n, C.c_void_p) for n in ("enc_ids", "dec_ids", "labels", "enc_valid", "dec_valid", "mem_valid",
+                                          "ent_valid", "pres", "rating_diff", "inv_n")]
+
+
+class TableArgs(C.Structure):
+    _fields_ = [("dataset", C.c_int32), ("B", C.c_int32), ("E", C.c_void_p), ("field", C.c_void_p)] + \
+               [("v%d" % i, C.c_void_p) for i in range(6)] + \
+               [("W0", C.c_void_p), ("W1", C.c_void_p), ("X", C.c_void_p), ("valid", C.c_void_p)]
 
 
 def lib():
@@ -45,7 +78,10 @@ def lib():
 
 # every symbol include/mmsum_b200.h declares (tests/test_abi.py cross-checks this list against the header)
 EXPORTS = [
-    "mmsum_gemm_bf16",
+    "mmsum_gemm_bf16", "mmsum_attn_fwd", "mmsum_attn_bwd", "mmsum_cast_f32_bf16",
+    "mmsum_embed_ln_fwd", "mmsum_embed_ln_bwd", "mmsum_add_ln_fwd", "mmsum_add_ln_bwd", "mmsum_colsum",
+    "mmsum_gate_fwd", "mmsum_gate_bwd_u", "mmsum_gate_bwd_o", "mmsum_ce_fwd_bwd", "mmsum_prep_step",
+    "mmsum_table_fwd", "mmsum_table_bits_bwd",
 ]
 
 

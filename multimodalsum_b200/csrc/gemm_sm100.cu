@@ -57,6 +57,7 @@ struct GemmKernelArgs {
   long long ld_aux;
   int out_f32;
   int accumulate;
+  int k_split;    // > 0: A columns [k_split, K) come from the second A tensor map (concat along K)
 };
 
 __device__ __forceinline__ void decode_tile(const GemmKernelArgs& g, int t, int& mt, int& nt, int& sp) {
@@ -69,8 +70,9 @@ __device__ __forceinline__ void decode_tile(const GemmKernelArgs& g, int t, int&
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmD, const GemmKernelArgs g) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                    const GemmKernelArgs g) {
   using L = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -119,6 +121,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, k0);
+          } else if (g.k_split > 0 && k0 >= g.k_split) {
+            tma_load_2d(sA, &tmA2, &full_bar[stage], k0 - g.k_split, m0);
           } else {
             tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
           }
@@ -365,8 +369,8 @@ static int num_sms() {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmKernelArgs& ka,
-                       int grid, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& td,
+                       const GemmKernelArgs& ka, int grid, cudaStream_t stream) {
   using L = GemmSmem<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -375,7 +379,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  gemm_tcgen05_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, td, ka);
+  gemm_tcgen05_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, L::kTotal, stream>>>(ta, ta2, tb, td, ka);
   MMSUM_CHECK_LAUNCH();
   return 0;
 }
@@ -410,7 +414,7 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
       if (splits < 1) splits = 1;
     }
   }
-  if (splits > 1 && !(a->out_f32 && a->accumulate)) return MMSUM_ERR_INVALID;
+  if (splits > 1 && (!(a->out_f32 && a->accumulate) || a->A2 != nullptr)) return MMSUM_ERR_INVALID;
   int kb_per_split = (kblocks + splits - 1) / splits;
   splits = (kblocks + kb_per_split - 1) / kb_per_split;  // no empty split
   ka.splits = splits;
@@ -425,11 +429,22 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
   ka.out_f32 = a->out_f32;
   ka.accumulate = a->accumulate;
 
-  CUtensorMap ta, tb, td;
+  CUtensorMap ta, ta2, tb, td;
   int rc;
+  ka.k_split = 0;
   // A: K-major = [M rows, K cols], box {64(k), 128(m)};  MN-major = [K rows, M cols], box {64(m), 64(k)}
-  if (a->a_mn_major) rc = make_tmap(&ta, a->A, 0, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda * 2, 64, 64);
-  else               rc = make_tmap(&ta, a->A, 0, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, 64, BM);
+  if (a->A2 != nullptr) {
+    // A = [A | A2] concatenated along K at k_split (K-major only; split on a k-block boundary)
+    if (a->a_mn_major || a->k_split <= 0 || a->k_split >= a->K || (a->k_split % BK) != 0) return MMSUM_ERR_INVALID;
+    ka.k_split = a->k_split;
+    rc = make_tmap(&ta, a->A, 0, (uint64_t)a->k_split, (uint64_t)a->M, (uint64_t)a->lda * 2, 64, BM);
+    if (rc) return rc;
+    rc = make_tmap(&ta2, a->A2, 0, (uint64_t)(a->K - a->k_split), (uint64_t)a->M, (uint64_t)a->lda2 * 2, 64, BM);
+  } else {
+    if (a->a_mn_major) rc = make_tmap(&ta, a->A, 0, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda * 2, 64, 64);
+    else               rc = make_tmap(&ta, a->A, 0, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda * 2, 64, BM);
+    ta2 = ta;
+  }
   if (rc) return rc;
   if (a->b_mn_major) rc = make_tmap(&tb, a->B, 0, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, 64);
   else               rc = make_tmap(&tb, a->B, 0, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, 64, (uint32_t)bn);
@@ -444,7 +459,7 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
   const int grid = total < nsm ? total : nsm;
   const int am = a->a_mn_major ? 1 : 0, bm = a->b_mn_major ? 1 : 0;
 #define MMSUM_GEMM_CASE(BN_, AM_, BM_) \
-  if (bn == BN_ && am == AM_ && bm == BM_) return launch_gemm<BN_, (AM_ != 0), (BM_ != 0)>(ta, tb, td, ka, grid, stream);
+  if (bn == BN_ && am == AM_ && bm == BM_) return launch_gemm<BN_, (AM_ != 0), (BM_ != 0)>(ta, ta2, tb, td, ka, grid, stream);
   MMSUM_GEMM_CASE(256, 0, 0)
   MMSUM_GEMM_CASE(256, 0, 1)
   MMSUM_GEMM_CASE(256, 1, 1)

@@ -1,0 +1,568 @@
+"""Step engine: orchestrates the hand-written CUDA kernels (through the C-ABI) into the forward and backward of
+MultimodalSum.forward (reference: src/multimodal_train.py:124-163).
+
+B200-first design decisions:
+  * batched leave-one-out: the reference's 9 sequential decoder passes are ONE decoder pass over 9·B sequences in
+    which target i simply does not see review i — decoder GEMMs get M = 9·B·128 rows and the
+    cross-attention K/V of every memory token is projected once per layer instead of 9 times;
+  * one K|V GEMM per layer over the concatenated text+table+image memory (k/v projections are shared by the modalities);
+  * parameters live in three flat arenas (fp32 master, bf16 compute copy, fp32 gradient) ordered by the time their
+    gradients become final in backward, so data-parallel buckets are contiguous slices that can be all-reduced while
+    backward is still running; fused weights (q|k|v, k|v) are adjacent in the arena so one GEMM serves them;
+  * activations are token-major [rows, 1024] bf16, saved per layer (≈1.2 GB / decoder layer at 16 businesses) — no
+    recomputation; all workspaces are allocated once per shape.
+torch is used for memory (arenas, workspaces), streams and torch.distributed only.
+"""
+import math
+
+import torch
+
+from . import ops
+from .synth import ModelConfig
+
+ALIGN = 64
+
+
+def _arena_order(cfg: ModelConfig):
+    """Parameter names (reference state_dict keys) in backward-completion order."""
+    names = []
+    bm = "bart_model.model."
+
+    def self_attn(lp):
+        a = lp + "self_attn."
+        return [a + "out_proj.weight", a + "out_proj.bias",
+                a + "q_proj.weight", a + "k_proj.weight", a + "v_proj.weight",
+                a + "q_proj.bias", a + "k_proj.bias", a + "v_proj.bias",
+                lp + "self_attn_layer_norm.weight", lp + "self_attn_layer_norm.bias"]
+
+    def ffn(lp):
+        return [lp + "fc2.weight", lp + "fc2.bias", lp + "fc1.weight", lp + "fc1.bias",
+                lp + "final_layer_norm.weight", lp + "final_layer_norm.bias"]
+
+    for i in reversed(range(cfg.decoder_layers)):
+        lp = bm + "decoder.layers.%d." % i
+        names += ffn(lp)
+        c = lp + "encoder_attn."
+        if cfg.dataset != "text":
+            names += [c + "alpha_proj.weight", c + "alpha_proj.bias", c + "beta_proj.weight", c + "beta_proj.bias"]
+        names += [c + "out_proj.weight", c + "out_proj.bias", c + "q_proj.weight", c + "q_proj.bias",
+                  c + "k_proj.weight", c + "v_proj.weight", c + "k_proj.bias", c + "v_proj.bias",
+                  lp + "encoder_attn_layer_norm.weight", lp + "encoder_attn_layer_norm.bias"]
+        names += self_attn(lp)
+    names += [bm + "decoder.layernorm_embedding.weight", bm + "decoder.layernorm_embedding.bias",
+              bm + "decoder.rating_embeddings", bm + "decoder.embed_positions.weight"]
+    if cfg.dataset != "text":
+        t = "table_encoder."
+        names += [t + "linear.weight", t + "fc.weight", t + "fc.bias"]
+        names += [t + "rating_embedding.weight", t + ("hours_embedding.weight" if cfg.dataset == "yelp" else "price_embedding.weight")]
+        names += ["img_encoder.linear.weight"]
+    for i in reversed(range(cfg.encoder_layers)):
+        lp = bm + "encoder.layers.%d." % i
+        names += ffn(lp)
+        names += self_attn(lp)
+    names += [bm + "encoder.layernorm_embedding.weight", bm + "encoder.layernorm_embedding.bias",
+              bm + "encoder.embed_positions.weight", bm + "shared.weight"]
+    return names
+
+
+class _Pool:
+    """Free-list of equally shaped scratch tensors.  Everything runs on one stream, so a buffer may be handed out
+    again as soon as its last consumer has been enqueued."""
+
+    def __init__(self, n, shape, device):
+        self.free = [torch.empty(shape, device=device, dtype=torch.bfloat16) for _ in range(n)]
+
+    def get(self):
+        return self.free.pop()
+
+    def put(self, *ts):
+        for t in ts:
+            if t is not None and all(t is not f for f in self.free):
+                self.free.append(t)
+
+
+class StepEngine:
+    def __init__(self, cfg: ModelConfig, device="cuda"):
+        if cfg.d_model != 1024 or cfg.head_dim != 64:
+            raise ValueError("kernels are specialised to d_model 1024 / head_dim 64 (bart-large)")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.names = _arena_order(cfg)
+        self.shapes = {}
+        self.offsets = {}
+        self.numel = 0
+        self.bound = False
+        self.ws = None
+        self.ws_key = None
+        self.seed = 0x5EED
+        self.step_count = 0
+        self.dropout = cfg.dropout
+        self.grad_ready_hook = None      # callable(lo, hi): gradient arena range [lo, hi) is final (data-parallel buckets)
+        self._w16_version = -1
+        self.anchor = None
+
+    # ------------------------------------------------------------------ parameters
+    def bind(self, named_params):
+        """Move the parameters into the flat arenas and re-point `.data` at the arena views."""
+        named = dict(named_params)
+        off = 0
+        for n in self.names:
+            if n not in named:
+                raise KeyError("parameter %s missing" % n)
+            self.shapes[n] = tuple(named[n].shape)
+            self.offsets[n] = off
+            off += (named[n].numel() + ALIGN - 1) // ALIGN * ALIGN
+        extra = set(named) - set(self.names)
+        if extra:
+            raise KeyError("unexpected parameters: %s" % sorted(extra)[:4])
+        self.numel = off
+        dev = self.device
+        self.W32 = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.W16 = torch.empty(off, device=dev, dtype=torch.bfloat16)
+        self.G32 = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.params = {}
+        with torch.no_grad():
+            for n in self.names:
+                p = named[n]
+                v = self.w32(n)
+                v.copy_(p.data.to(device=dev, dtype=torch.float32))
+                p.data = v
+                self.params[n] = p
+        self.anchor = torch.zeros(1, device=dev, requires_grad=True)
+        self.bound = True
+        self._w16_version = -1
+
+    def _view(self, arena, n, n2=None):
+        o = self.offsets[n]
+        if n2 is None:
+            return arena[o:o + math.prod(self.shapes[n])].view(self.shapes[n])
+        # fused view over adjacent tensors n..n2 (same trailing dims, no padding in between)
+        o2 = self.offsets[n2] + math.prod(self.shapes[n2])
+        tail = self.shapes[n][1:]
+        return arena[o:o2].view((-1,) + tail)
+
+    def w32(self, n, n2=None):
+        return self._view(self.W32, n, n2)
+
+    def w16(self, n, n2=None):
+        return self._view(self.W16, n, n2)
+
+    def g32(self, n, n2=None):
+        return self._view(self.G32, n, n2)
+
+    def refresh_bf16_weights(self, force=False):
+        if force or self.W32._version != self._w16_version:
+            ops.cast_bf16(self.W32, self.W16)
+            self._w16_version = self.W32._version
+
+    # ------------------------------------------------------------------ workspaces
+    def _alloc(self, B, R, S, F, n_img, img_keys):
+        key = (B, R, S, F, n_img, img_keys)
+        if self.ws_key == key:
+            return self.ws
+        cfg, dev = self.cfg, self.device
+        D, FF, H = cfg.d_model, cfg.ffn_dim, cfg.heads
+        T = B * R * S
+        Tm = T + B * F + B * n_img * img_keys
+        N = B * R
+        Et = R + (1 if F > 0 else 0) + n_img
+        bf = lambda *s: torch.empty(s, device=dev, dtype=torch.bfloat16)
+        f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        u8 = lambda *s: torch.zeros(s, device=dev, dtype=torch.uint8)
+        i32 = lambda *s: torch.zeros(s, device=dev, dtype=torch.int32)
+        w = dict(B=B, R=R, S=S, F=F, n_img=n_img, img_keys=img_keys, T=T, Tm=Tm, N=N, Et=Et)
+        w.update(enc_ids=i32(T), dec_ids=i32(T), labels=i32(T), enc_valid=u8(T), dec_valid=u8(T), mem_valid=u8(Tm),
+                 ent_valid=u8(B, Et), pres=u8(B, 2), rating_diff=f32(N), inv_n=f32(N, 3 if F > 0 else 1))
+        w["MEM"] = bf(Tm, D)
+        if F > 0:
+            w.update(tabX=bf(B * F, 2 * D), tab_valid=u8(B, F), tab_h=bf(B * F, D), img16=bf(B * n_img * img_keys, 1024))
+        L_e, L_d = cfg.encoder_layers, cfg.decoder_layers
+        enc = []
+        for l in range(L_e):
+            enc.append(dict(x=bf(T, D) if l > 0 else None, qkv=bf(T, 3 * D), ctx=bf(T, D), o=bf(T, D), x1=bf(T, D), h=bf(T, FF),
+                            a=bf(T, FF), f=bf(T, D), lse=f32(N, H, 1, S), m1=f32(T), r1=f32(T), m2=f32(T), r2=f32(T)))
+        w["enc"] = enc
+        w["enc_x0"] = bf(T, D)
+        w["enc_m0"], w["enc_r0"] = f32(T), f32(T)
+        dec = []
+        nm = 3 if F > 0 else 1
+        for l in range(L_d):
+            d = dict(x=bf(T, D), qkv=bf(T, 3 * D), ctx=bf(T, D), o=bf(T, D), x1=bf(T, D), qc=bf(T, D), kv=bf(Tm, 2 * D),
+                     A3=bf(nm, T, D), O3=bf(nm, T, D), x2=bf(T, D), h=bf(T, FF), a=bf(T, FF), f=bf(T, D),
+                     lse=f32(N, H, 1, S), lse_c=f32(N, H, Et, S),
+                     m1=f32(T), r1=f32(T), m2=f32(T), r2=f32(T), m3=f32(T), r3=f32(T))
+            if nm == 3:
+                d.update(AB=bf(2, T, D), yc=bf(T, D))
+            dec.append(d)
+        w["dec"] = dec
+        w["dec_m0"], w["dec_r0"] = f32(T), f32(T)
+        w["x_out"] = bf(T, D)
+        self.ldv = (cfg.vocab_size + 7) // 8 * 8
+        w["logits"] = bf(T, self.ldv)
+        w["loss_rows"] = f32(T)
+        w["loss"] = f32(1)
+        # backward scratch
+        w["pool"] = _Pool(5, (T, D), dev)
+        w["dH"] = bf(T, FF)
+        w["dqkv"] = bf(T, 3 * D)
+        w["dkv"] = bf(Tm, 2 * D)
+        w["delta"] = f32(N, H, Et, S)
+        w["dMEM32"] = f32(Tm, D)
+        w["dMEM16"] = bf(Tm, D)
+        w["dz32"] = f32(T, D)
+        w["dA3"] = bf(nm, T, D)
+        w["dO3"] = bf(nm, T, D)
+        if nm == 3:
+            w.update(U=bf(2, T, D), dU=bf(2, T, D), dca=bf(T, 2 * D), dcb=bf(T, 2 * D))
+        if F > 0:
+            w.update(dtab_h=bf(B * F, D), dtabX=bf(B * F, 2 * D))
+        self.ws, self.ws_key = w, key
+        return w
+
+    # ------------------------------------------------------------------ helpers
+    def _sid(self, kind, layer):
+        return (self.step_count * 4096 + kind * 64 + layer) & 0xFFFFFFFF
+
+    def _self_attn_args(self, w, qkv, out, lse, key_valid, causal, bwd=None):
+        D, H, S = self.cfg.d_model, self.cfg.heads, w["S"]
+        kw = dict(Q=qkv, ldq=3 * D, q_col=0, KV=qkv, ldkv=3 * D, k_col=D, v_col=2 * D, O=out, ldo=D, LSE=lse,
+                  key_valid=key_valid, ent_valid=None, inv_n=None, n_qseq=w["N"], H=H, R=1, causal=int(causal), E_total=1,
+                  scale=self.cfg.head_dim ** -0.5, mods=[(0, 0, 1, S, 0, 0)])
+        if bwd is not None:
+            dqkv = bwd
+            kw.update(DELTA=w["delta"], dQ=dqkv, lddq=3 * D, dq_col=0, dKV=dqkv, lddkv=3 * D, dk_col=D, dv_col=2 * D)
+        return ops.attn_args(**kw)
+
+    def _cross_attn_args(self, w, qc, kv, out3, lse, bwd=None):
+        D, H, S, T = self.cfg.d_model, self.cfg.heads, w["S"], w["T"]
+        B, R, F, n_img, ik = w["B"], w["R"], w["F"], w["n_img"], w["img_keys"]
+        mods = [(0, 0, R, S, 1, 0)]
+        if F > 0:
+            mods.append((T, T * D, 1, F, 0, R))
+            mods.append((T + B * F, 2 * T * D, n_img, ik, 0, R + 1))
+        kw = dict(Q=qc, ldq=D, q_col=0, KV=kv, ldkv=2 * D, k_col=0, v_col=D, O=out3, ldo=D, LSE=lse,
+                  key_valid=w["mem_valid"], ent_valid=w["ent_valid"], inv_n=w["inv_n"], n_qseq=w["N"], H=H, R=R, causal=0,
+                  E_total=w["Et"], scale=self.cfg.head_dim ** -0.5, mods=mods)
+        if bwd is not None:
+            dqc, dkv = bwd
+            kw.update(DELTA=w["delta"], dQ=dqc, lddq=D, dq_col=0, dKV=dkv, lddkv=2 * D, dk_col=0, dv_col=D)
+        return ops.attn_args(**kw)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, batch, label_smoothing=0.1, training=True):
+        """batch: synth.Batch on the device.  Returns the scalar loss tensor (fp32, device)."""
+        if not self.bound:
+            raise RuntimeError("engine.bind(named_parameters) first")
+        cfg = self.cfg
+        D, FF, V = cfg.d_model, cfg.ffn_dim, cfg.vocab_size
+        B, R, S = batch.reviews.shape
+        multimodal = cfg.dataset != "text"
+        if multimodal:
+            F = 47 if cfg.dataset == "yelp" else 133
+            n_img, img_keys = batch.img.shape[1], batch.img.shape[2]
+        else:
+            F, n_img, img_keys = 0, 0, 0
+        if S != 128:
+            raise ValueError("the attention kernels are specialised to 128-token frames")
+        w = self._alloc(B, R, S, F, n_img, img_keys)
+        T, Tm = w["T"], w["Tm"]
+        self.step_count += 1
+        self.training = training
+        pd = self.dropout if training else 0.0
+        self.pd = pd
+        self.label_smoothing = label_smoothing
+        seed = self.seed
+        self.refresh_bf16_weights()
+        bm = "bart_model.model."
+        g = ops.gemm
+
+        # ---- table front end + step bookkeeping (integer work, bit-exact)
+        if multimodal:
+            t = "table_encoder."
+            W1name = t + ("hours_embedding.weight" if cfg.dataset == "yelp" else "price_embedding.weight")
+            if cfg.dataset == "yelp":
+                W0, W1 = self.w32(t + "rating_embedding.weight"), self.w32(W1name)
+            else:
+                W0, W1 = self.w32(W1name), self.w32(t + "rating_embedding.weight")
+            ops.table_fwd(cfg.dataset, B, self.w32(bm + "shared.weight"), batch.field, batch.field_value, W0, W1,
+                          w["tabX"], w["tab_valid"])
+            img_mask_u8 = batch.img_mask.view(torch.uint8) if batch.img_mask.dtype == torch.bool else batch.img_mask
+        ops.prep_step(batch.reviews, batch.reviews_mask, batch.reviews_rating,
+                      w["tab_valid"] if multimodal else None, img_mask_u8 if multimodal else None,
+                      B=B, R=R, S=S, F=F, n_img=n_img, img_keys=img_keys, n_mod=3 if multimodal else 1,
+                      pad_id=cfg.pad_token_id, bos_id=cfg.bos_token_id, eos_id=cfg.eos_token_id,
+                      enc_ids=w["enc_ids"], dec_ids=w["dec_ids"], labels=w["labels"], enc_valid=w["enc_valid"],
+                      dec_valid=w["dec_valid"], mem_valid=w["mem_valid"], ent_valid=w["ent_valid"],
+                      pres=w["pres"] if multimodal else None, rating_diff=w["rating_diff"], inv_n=w["inv_n"])
+        MEM = w["MEM"]
+        if multimodal:
+            t = "table_encoder."
+            g(w["tabX"], self.w16(t + "fc.weight"), w["tab_h"], bias=self.w32(t + "fc.bias"), act=ops.ACT_RELU)
+            g(w["tab_h"], self.w16(t + "linear.weight"), MEM[T:T + B * F])
+            img = batch.img.reshape(B * n_img * img_keys, 1024)
+            if img.dtype == torch.float32:
+                ops.cast_bf16(img.contiguous(), w["img16"])
+                img = w["img16"]
+            w["img_in"] = img
+            g(img, self.w16("img_encoder.linear.weight"), MEM[T + B * F:])
+
+        # ---- encoder (BartEncoder.forward :346-404)
+        pre = bm + "encoder."
+        x = w["enc_x0"]
+        ops.embed_ln_fwd(w["enc_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"), None, None,
+                         self.w32(pre + "layernorm_embedding.weight"), self.w32(pre + "layernorm_embedding.bias"),
+                         x, w["enc_m0"], w["enc_r0"], T, S, pd, seed, self._sid(0, 0))
+        L_e = cfg.encoder_layers
+        for l in range(L_e):
+            a = w["enc"][l]
+            a["x"] = x
+            lp = pre + "layers.%d." % l
+            out = MEM[:T] if l == L_e - 1 else w["enc"][l + 1]["x"]
+            self._self_block_fwd(w, a, lp, x, w["enc_valid"], False, l, 1)
+            self._ffn_block_fwd(a, lp, a["x1"], out, "m2", "r2", l, 2)
+            x = out
+
+        # ---- decoder, batched leave-one-out (BartDecoder.forward :530-660 over 9·B sequences)
+        pre = bm + "decoder."
+        L_d = cfg.decoder_layers
+        x = w["dec"][0]["x"]
+        ops.embed_ln_fwd(w["dec_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"),
+                         w["rating_diff"], self.w32(pre + "rating_embeddings"),
+                         self.w32(pre + "layernorm_embedding.weight"), self.w32(pre + "layernorm_embedding.bias"),
+                         x, w["dec_m0"], w["dec_r0"], T, S, pd, seed, self._sid(3, 0))
+        for l in range(L_d):
+            a = w["dec"][l]
+            lp = pre + "layers.%d." % l
+            c = lp + "encoder_attn."
+            out = w["x_out"] if l == L_d - 1 else w["dec"][l + 1]["x"]
+            self._self_block_fwd(w, a, lp, a["x"], w["dec_valid"], True, l, 4)
+            # cross-attention block (SelfAttention.forward multimodal branch :722-745)
+            g(a["x1"], self.w16(c + "q_proj.weight"), a["qc"], bias=self.w32(c + "q_proj.bias"))
+            g(MEM, self.w16(c + "k_proj.weight", c + "v_proj.weight"), a["kv"], bias=self.w32(c + "k_proj.bias", c + "v_proj.bias"))
+            ops.attn_fwd(self._cross_attn_args(w, a["qc"], a["kv"], a["A3"], a["lse_c"]))
+            nm = a["A3"].shape[0]
+            g(a["A3"].view(nm * T, D), self.w16(c + "out_proj.weight"), a["O3"].view(nm * T, D), bias=self.w32(c + "out_proj.bias"))
+            if multimodal:
+                U = w["U"]
+                ops.gemm_cat(a["O3"][0], a["O3"][1], self.w16(c + "alpha_proj.weight"), U[0], bias=self.w32(c + "alpha_proj.bias"))
+                ops.gemm_cat(a["O3"][0], a["O3"][2], self.w16(c + "beta_proj.weight"), U[1], bias=self.w32(c + "beta_proj.bias"))
+                ops.gate_fwd(a["O3"], U, w["pres"], a["yc"], a["AB"], T, R * S, D)
+                yc = a["yc"]
+            else:
+                yc = a["O3"][0]
+            ops.add_ln_fwd(a["x1"], yc, self.w32(lp + "encoder_attn_layer_norm.weight"), self.w32(lp + "encoder_attn_layer_norm.bias"),
+                           a["x2"], a["m2"], a["r2"], pd, seed, self._sid(5, l))
+            self._ffn_block_fwd(a, lp, a["x2"], out, "m3", "r3", l, 6)
+            x = out
+
+        # ---- LM head + loss (:2281, src/utils.py:32-38); mean over all 9·B·128 rows == mean of the 9 pass means
+        logits = w["logits"]
+        g(x, self.w16(bm + "shared.weight"), logits[:, :V], bias=self.w32_flb(), raster_m_fast=True)
+        ops.ce_fwd_bwd(logits, V, w["labels"], label_smoothing, 0.0, None, w["loss_rows"], w["loss"], 1.0 / T, False)
+        return w["loss"]
+
+    def w32_flb(self):
+        return self.final_logits_bias.view(-1) if getattr(self, "final_logits_bias", None) is not None else None
+
+    def _self_block_fwd(self, w, a, lp, x, key_valid, causal, l, kind):
+        g = ops.gemm
+        s = lp + "self_attn."
+        g(x, self.w16(s + "q_proj.weight", s + "v_proj.weight"), a["qkv"], bias=self.w32(s + "q_proj.bias", s + "v_proj.bias"))
+        ops.attn_fwd(self._self_attn_args(w, a["qkv"], a["ctx"], a["lse"], key_valid, causal))
+        g(a["ctx"], self.w16(s + "out_proj.weight"), a["o"], bias=self.w32(s + "out_proj.bias"))
+        ops.add_ln_fwd(x, a["o"], self.w32(lp + "self_attn_layer_norm.weight"), self.w32(lp + "self_attn_layer_norm.bias"),
+                       a["x1"], a["m1"], a["r1"], self.pd, self.seed, self._sid(kind, l))
+
+    def _ffn_block_fwd(self, a, lp, xin, out, mk, rk, l, kind):
+        g = ops.gemm
+        g(xin, self.w16(lp + "fc1.weight"), a["a"], bias=self.w32(lp + "fc1.bias"), act=ops.ACT_GELU, aux=a["h"],
+          aux_mode=ops.AUX_STORE_PREACT)
+        g(a["a"], self.w16(lp + "fc2.weight"), a["f"], bias=self.w32(lp + "fc2.bias"))
+        ops.add_ln_fwd(xin, a["f"], self.w32(lp + "final_layer_norm.weight"), self.w32(lp + "final_layer_norm.bias"),
+                       out, a[mk], a[rk], self.pd, self.seed, self._sid(kind, l))
+
+    # ------------------------------------------------------------------ backward
+    def _wgrad(self, dy, x, gname, gname2=None, col_slice=None):
+        """G[name] += dyᵀ·x   (dy [T, N_out], x [T, K_in]) — MN-major operands, split-K, TMA reduce-add."""
+        out = self.g32(gname, gname2)
+        if col_slice is not None:
+            out = out[:, col_slice[0]:col_slice[1]]
+        ops.gemm(dy, x, out, a_t=True, b_t=True, accumulate=True)
+
+    def _ready(self, name_last):
+        if self.grad_ready_hook is not None:
+            hi = self.offsets[name_last] + (math.prod(self.shapes[name_last]) + ALIGN - 1) // ALIGN * ALIGN
+            self.grad_ready_hook(hi)
+
+    def _ffn_block_bwd(self, w, a, lp, d1, d2, xin, mk, rk, l, kind):
+        """Backward of x_out = LN(xin + drop(fc2(gelu(fc1(xin))))).  Returns the two addends of d xin."""
+        pool, pd = w["pool"], self.pd
+        dres = pool.get()
+        df = pool.get() if pd > 0 else dres
+        ops.add_ln_bwd(d1, d2, xin, a["f"], self.w32(lp + "final_layer_norm.weight"), a[mk], a[rk], dres, df,
+                       self.g32(lp + "final_layer_norm.weight"), self.g32(lp + "final_layer_norm.bias"), pd, self.seed,
+                       self._sid(kind, l))
+        pool.put(d1, d2)
+        ops.colsum(df, self.g32(lp + "fc2.bias"))
+        self._wgrad(df, a["a"], lp + "fc2.weight")
+        dH = w["dH"]
+        ops.gemm(df, self.w16(lp + "fc2.weight"), dH, b_t=True, act=ops.ACT_GELU, aux=a["h"], aux_mode=ops.AUX_MUL_DACT)
+        if df is not dres:
+            pool.put(df)
+        ops.colsum(dH, self.g32(lp + "fc1.bias"))
+        self._wgrad(dH, xin, lp + "fc1.weight")
+        dx = pool.get()
+        ops.gemm(dH, self.w16(lp + "fc1.weight"), dx, b_t=True)
+        return dres, dx
+
+    def _self_block_bwd(self, w, a, lp, d1, d2, key_valid, causal, l, kind):
+        """Backward of x1 = LN(x + drop(out_proj(attn(qkv(x))))).  Returns the two addends of d x."""
+        pool, pd, D = w["pool"], self.pd, self.cfg.d_model
+        s = lp + "self_attn."
+        dres = pool.get()
+        do = pool.get() if pd > 0 else dres
+        ops.add_ln_bwd(d1, d2, a["x"], a["o"], self.w32(lp + "self_attn_layer_norm.weight"), a["m1"], a["r1"], dres, do,
+                       self.g32(lp + "self_attn_layer_norm.weight"), self.g32(lp + "self_attn_layer_norm.bias"), pd, self.seed,
+                       self._sid(kind, l))
+        pool.put(d1, d2)
+        ops.colsum(do, self.g32(s + "out_proj.bias"))
+        self._wgrad(do, a["ctx"], s + "out_proj.weight")
+        dctx = pool.get()
+        ops.gemm(do, self.w16(s + "out_proj.weight"), dctx, b_t=True)
+        if do is not dres:
+            pool.put(do)
+        dqkv = w["dqkv"]
+        ops.attn_bwd(self._self_attn_args(w, a["qkv"], dctx, a["lse"], key_valid, causal, bwd=dqkv))
+        pool.put(dctx)
+        ops.colsum(dqkv, self.g32(s + "q_proj.bias", s + "v_proj.bias"))
+        self._wgrad(dqkv, a["x"], s + "q_proj.weight", s + "v_proj.weight")
+        dx = pool.get()
+        ops.gemm(dqkv, self.w16(s + "q_proj.weight", s + "v_proj.weight"), dx, b_t=True)
+        return dres, dx
+
+    def backward(self, grad_out=None):
+        """Writes every parameter gradient into the fp32 gradient arena (+=) and points `.grad` at it."""
+        cfg, w = self.cfg, self.ws
+        D, V = cfg.d_model, cfg.vocab_size
+        T, Tm, B, R, S, F = w["T"], w["Tm"], w["B"], w["R"], w["S"], w["F"]
+        n_img, img_keys = w["n_img"], w["img_keys"]
+        multimodal = cfg.dataset != "text"
+        pool, pd, seed = w["pool"], self.pd, self.seed
+        bm = "bart_model.model."
+        g = ops.gemm
+        first = next(iter(self.params.values()))
+        if first.grad is None:
+            self.G32.zero_()
+        w["dMEM32"].zero_()
+
+        # ---- loss + LM head
+        logits = w["logits"]
+        ops.ce_fwd_bwd(logits, V, w["labels"], self.label_smoothing, 1.0 / T, grad_out, w["loss_rows"], None, 0.0, True)
+        dl = logits[:, :V]
+        d1 = pool.get()
+        g(dl, self.w16(bm + "shared.weight"), d1, b_t=True)
+        xfin = w["x_out"]
+        ops.gemm(dl, xfin, self.g32(bm + "shared.weight"), a_t=True, b_t=True, accumulate=True)
+        d2 = None
+
+        # ---- decoder layers, last to first
+        pre = bm + "decoder."
+        for l in reversed(range(cfg.decoder_layers)):
+            a = w["dec"][l]
+            lp = pre + "layers.%d." % l
+            c = lp + "encoder_attn."
+            d1, d2 = self._ffn_block_bwd(w, a, lp, d1, d2, a["x2"], "m3", "r3", l, 6)
+            # cross block
+            dres = pool.get()
+            yc = a["yc"] if multimodal else a["O3"][0]
+            dyc = pool.get() if pd > 0 else dres
+            ops.add_ln_bwd(d1, d2, a["x1"], yc, self.w32(lp + "encoder_attn_layer_norm.weight"), a["m2"], a["r2"], dres, dyc,
+                           self.g32(lp + "encoder_attn_layer_norm.weight"), self.g32(lp + "encoder_attn_layer_norm.bias"),
+                           pd, seed, self._sid(5, l))
+            pool.put(d1, d2)
+            nm = a["A3"].shape[0]
+            if multimodal:
+                dU, dO3 = w["dU"], w["dO3"]
+                ops.gate_bwd_u(dyc, a["O3"], a["AB"], dU, T, D)
+                ops.colsum(dU[0], self.g32(c + "alpha_proj.bias"))
+                ops.colsum(dU[1], self.g32(c + "beta_proj.bias"))
+                self._wgrad(dU[0], a["O3"][0], c + "alpha_proj.weight", col_slice=(0, D))
+                self._wgrad(dU[0], a["O3"][1], c + "alpha_proj.weight", col_slice=(D, 2 * D))
+                self._wgrad(dU[1], a["O3"][0], c + "beta_proj.weight", col_slice=(0, D))
+                self._wgrad(dU[1], a["O3"][2], c + "beta_proj.weight", col_slice=(D, 2 * D))
+                g(dU[0], self.w16(c + "alpha_proj.weight"), w["dca"], b_t=True)
+                g(dU[1], self.w16(c + "beta_proj.weight"), w["dcb"], b_t=True)
+                ops.gate_bwd_o(dyc, a["AB"], w["dca"], w["dcb"], dO3, T, D)
+                dO3f = dO3.view(nm * T, D)
+            else:
+                dO3f = dyc
+            ops.colsum(dO3f, self.g32(c + "out_proj.bias"))
+            self._wgrad(dO3f, a["A3"].view(nm * T, D), c + "out_proj.weight")
+            dA3 = w["dA3"]
+            g(dO3f, self.w16(c + "out_proj.weight"), dA3.view(nm * T, D), b_t=True)
+            if dyc is not dres:
+                pool.put(dyc)
+            dqc = pool.get()
+            dkv = w["dkv"]
+            ops.attn_bwd(self._cross_attn_args(w, a["qc"], a["kv"], dA3, a["lse_c"], bwd=(dqc, dkv)))
+            ops.colsum(dqc, self.g32(c + "q_proj.bias"))
+            self._wgrad(dqc, a["x1"], c + "q_proj.weight")
+            dx1 = pool.get()
+            g(dqc, self.w16(c + "q_proj.weight"), dx1, b_t=True)
+            pool.put(dqc)
+            ops.colsum(dkv, self.g32(c + "k_proj.bias", c + "v_proj.bias"))
+            self._wgrad(dkv, w["MEM"], c + "k_proj.weight", c + "v_proj.weight")
+            g(dkv, self.w16(c + "k_proj.weight", c + "v_proj.weight"), w["dMEM32"], b_t=True, accumulate=True)
+            # self block
+            d1, d2 = self._self_block_bwd(w, a, lp, dres, dx1, w["dec_valid"], True, l, 4)
+            self._ready(lp + "self_attn_layer_norm.bias")
+        # decoder embedding
+        ops.embed_ln_bwd(d1, d2, w["dec_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"),
+                         w["rating_diff"], self.w32(pre + "rating_embeddings"), self.w32(pre + "layernorm_embedding.weight"),
+                         w["dec_m0"], w["dec_r0"], self.g32(bm + "shared.weight"), self.g32(pre + "embed_positions.weight"),
+                         self.g32(pre + "rating_embeddings"), self.g32(pre + "layernorm_embedding.weight"),
+                         self.g32(pre + "layernorm_embedding.bias"), w["dz32"], T, S, cfg.pad_token_id, pd, seed, self._sid(3, 0))
+        pool.put(d1, d2)
+        self._ready(pre + "embed_positions.weight")
+
+        # ---- memory gradients: table, image, text
+        ops.cast_bf16(w["dMEM32"], w["dMEM16"])
+        dMEM = w["dMEM16"]
+        if multimodal:
+            t = "table_encoder."
+            dtab = dMEM[T:T + B * F]
+            self._wgrad(dtab, w["tab_h"], t + "linear.weight")
+            g(dtab, self.w16(t + "linear.weight"), w["dtab_h"], b_t=True, act=ops.ACT_RELU, aux=w["tab_h"], aux_mode=ops.AUX_MUL_DACT)
+            ops.colsum(w["dtab_h"], self.g32(t + "fc.bias"))
+            self._wgrad(w["dtab_h"], w["tabX"], t + "fc.weight")
+            g(w["dtab_h"], self.w16(t + "fc.weight"), w["dtabX"], b_t=True)
+            batch = self._batch
+            if cfg.dataset == "yelp":
+                ops.table_bits_bwd(w["dtabX"], batch.field_value[4], self.g32(t + "rating_embedding.weight"), B, F, 39, 1, 4)
+                ops.table_bits_bwd(w["dtabX"], batch.field_value[5], self.g32(t + "hours_embedding.weight"), B, F, 40, 7, 4)
+            else:
+                ops.table_bits_bwd(w["dtabX"], batch.field_value[0], self.g32(t + "price_embedding.weight"), B, F, 0, 1, 11)
+                ops.table_bits_bwd(w["dtabX"], batch.field_value[1], self.g32(t + "rating_embedding.weight"), B, F, 1, 1, 4)
+            self._wgrad(dMEM[T + B * F:], w["img_in"], "img_encoder.linear.weight")
+            self._ready("img_encoder.linear.weight")
+
+        # ---- encoder layers, last to first
+        pre = bm + "encoder."
+        d1 = pool.get()
+        d1.copy_(dMEM[:T])
+        d2 = None
+        for l in reversed(range(cfg.encoder_layers)):
+            a = w["enc"][l]
+            lp = pre + "layers.%d." % l
+            d1, d2 = self._ffn_block_bwd(w, a, lp, d1, d2, a["x1"], "m2", "r2", l, 2)
+            d1, d2 = self._self_block_bwd(w, a, lp, d1, d2, w["enc_valid"], False, l, 1)
+            self._ready(lp + "self_attn_layer_norm.bias")
+        ops.embed_ln_bwd(d1, d2, w["enc_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"), None, None,
+                         self.w32(pre + "layernorm_embedding.weight"), w["enc_m0"], w["enc_r0"], self.g32(bm + "shared.weight"),
+                         self.g32(pre + "embed_positions.weight"), None, self.g32(pre + "layernorm_embedding.weight"),
+                         self.g32(pre + "layernorm_embedding.bias"), w["dz32"], T, S, cfg.pad_token_id, pd, seed, self._sid(0, 0))
+        pool.put(d1, d2)
+        self._ready(bm + "shared.weight")
+        for n, p in self.params.items():
+            if p.grad is None:
+                p.grad = self.g32(n)

@@ -73,3 +73,128 @@ def gemm(A, B, out=None, *, a_t=False, b_t=False, out_dtype=torch.bfloat16, bias
     a.ld_aux = aux.stride(0) if aux is not None else 0
     check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16")
     return out
+
+
+def gemm_cat(A, A2, B, out=None, *, bias=None, out_dtype=torch.bfloat16):
+    """out = [A | A2]·Bᵀ + bias with the concatenation along K done by the TMA producer (no cat buffer)."""
+    _check2d(A, "A", torch.bfloat16)
+    _check2d(A2, "A2", torch.bfloat16)
+    _check2d(B, "B", torch.bfloat16)
+    M, K1 = A.shape
+    K = K1 + A2.shape[1]
+    N = B.shape[0]
+    if A2.shape[0] != M or B.shape[1] != K:
+        raise ValueError("gemm_cat shape mismatch")
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=out_dtype)
+    a = GemmArgs()
+    a.A, a.B, a.D = A.data_ptr(), B.data_ptr(), out.data_ptr()
+    a.lda, a.ldb, a.ldd = A.stride(0), B.stride(0), out.stride(0)
+    a.M, a.N, a.K = M, N, K
+    a.out_f32 = int(out.dtype == torch.float32)
+    a.alpha = 1.0
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.A2, a.lda2, a.k_split = A2.data_ptr(), A2.stride(0), K1
+    check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16(cat)")
+    return out
+
+
+def cast_bf16(src, dst):
+    check(_lib.lib().mmsum_cast_f32_bf16(_ptr(src), _ptr(dst), C.c_int64(src.numel()), _stream()), "mmsum_cast_f32_bf16")
+    return dst
+
+
+def embed_ln_fwd(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, rows, S, p_drop, seed, sid):
+    check(_lib.lib().mmsum_embed_ln_fwd(_ptr(ids), _ptr(E), _ptr(P), _ptr(rating_diff), _ptr(remb), _ptr(gamma), _ptr(beta),
+                                        _ptr(out), _ptr(mean), _ptr(rstd), rows, S, E.shape[1], C.c_float(p_drop),
+                                        C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_embed_ln_fwd")
+
+
+def embed_ln_bwd(dout, dout2, ids, E, P, rating_diff, remb, gamma, mean, rstd, dE, dP, dremb, dgamma, dbeta, dz, rows, S,
+                 pad_id, p_drop, seed, sid):
+    check(_lib.lib().mmsum_embed_ln_bwd(_ptr(dout), _ptr(dout2), _ptr(ids), _ptr(E), _ptr(P), _ptr(rating_diff), _ptr(remb),
+                                        _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dE), _ptr(dP), _ptr(dremb), _ptr(dgamma),
+                                        _ptr(dbeta), _ptr(dz), rows, S, E.shape[1], pad_id, C.c_float(p_drop),
+                                        C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_embed_ln_bwd")
+
+
+def add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid):
+    rows, d = res.shape
+    check(_lib.lib().mmsum_add_ln_fwd(_ptr(res), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(mean), _ptr(rstd), rows, d,
+                                      C.c_float(p_drop), C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_add_ln_fwd")
+
+
+def add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid):
+    rows, d = res.shape
+    check(_lib.lib().mmsum_add_ln_bwd(_ptr(d1), _ptr(d2), _ptr(res), _ptr(y), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres),
+                                      _ptr(dy), _ptr(dgamma), _ptr(dbeta), rows, d, C.c_float(p_drop), C.c_uint64(seed),
+                                      C.c_uint32(sid), _stream()), "mmsum_add_ln_bwd")
+
+
+def colsum(x, out):
+    """out[n] += Σ_r x[r, n]  (x bf16 2-D, possibly a column-slice view)."""
+    _check2d(x, "x", torch.bfloat16)
+    check(_lib.lib().mmsum_colsum(_ptr(x), C.c_int64(x.stride(0)), x.shape[0], x.shape[1], _ptr(out), _stream()), "mmsum_colsum")
+
+
+def gate_fwd(o3, u, pres, y, ab, rows, rows_per_biz, d):
+    check(_lib.lib().mmsum_gate_fwd(_ptr(o3), _ptr(u), _ptr(pres), _ptr(y), _ptr(ab), rows, rows_per_biz, d, _stream()), "mmsum_gate_fwd")
+
+
+def gate_bwd_u(dy, o3, ab, du, rows, d):
+    check(_lib.lib().mmsum_gate_bwd_u(_ptr(dy), _ptr(o3), _ptr(ab), _ptr(du), rows, d, _stream()), "mmsum_gate_bwd_u")
+
+
+def gate_bwd_o(dy, ab, dca, dcb, do3, rows, d):
+    check(_lib.lib().mmsum_gate_bwd_o(_ptr(dy), _ptr(ab), _ptr(dca), _ptr(dcb), _ptr(do3), rows, d, _stream()), "mmsum_gate_bwd_o")
+
+
+def ce_fwd_bwd(logits, V, target, eps, gscale, gscale_dev, loss_rows, loss_out, loss_scale, write_grad):
+    rows = logits.shape[0]
+    check(_lib.lib().mmsum_ce_fwd_bwd(_ptr(logits), C.c_int64(logits.stride(0)), rows, V, _ptr(target),
+                                      C.c_float(-1.0 if eps is None else eps), C.c_float(gscale), _ptr(gscale_dev),
+                                      _ptr(loss_rows), _ptr(loss_out), C.c_float(loss_scale), int(write_grad), _stream()),
+          "mmsum_ce_fwd_bwd")
+
+
+def attn_args(**kw):
+    a = _lib.AttnArgs()
+    mods = kw.pop("mods")
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            v = v.data_ptr()
+        setattr(a, k, v)
+    a.n_mod = len(mods)
+    for i, m in enumerate(mods):
+        a.mods[i].kv_row_base, a.mods[i].o_off, a.mods[i].E, a.mods[i].Sk, a.mods[i].loo, a.mods[i].ent_base = m
+    return a
+
+
+def attn_fwd(a):
+    check(_lib.lib().mmsum_attn_fwd(C.byref(a), _stream()), "mmsum_attn_fwd")
+
+
+def attn_bwd(a):
+    check(_lib.lib().mmsum_attn_bwd(C.byref(a), _stream()), "mmsum_attn_bwd")
+
+
+def prep_step(reviews, reviews_mask, rating, table_valid, img_mask, **kw):
+    a = _lib.PrepArgs()
+    for k, v in kw.items():
+        setattr(a, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+    check(_lib.lib().mmsum_prep_step(_ptr(reviews), _ptr(reviews_mask), _ptr(rating), _ptr(table_valid), _ptr(img_mask),
+                                     C.byref(a), _stream()), "mmsum_prep_step")
+
+
+def table_fwd(dataset, B, E, field, values, W0, W1, X, valid):
+    a = _lib.TableArgs()
+    a.dataset, a.B = (0 if dataset == "yelp" else 1), B
+    a.E, a.field = E.data_ptr(), field.data_ptr()
+    for i, v in enumerate(values):
+        setattr(a, "v%d" % i, v.data_ptr())
+    a.W0, a.W1, a.X, a.valid = W0.data_ptr(), W1.data_ptr(), X.data_ptr(), valid.data_ptr()
+    check(_lib.lib().mmsum_table_fwd(C.byref(a), _stream()), "mmsum_table_fwd")
+
+
+def table_bits_bwd(dX, bits, dW, B, F, f0, nrows, nb):
+    check(_lib.lib().mmsum_table_bits_bwd(_ptr(dX), _ptr(bits), _ptr(dW), B, F, f0, nrows, nb, _stream()), "mmsum_table_bits_bwd")

@@ -1,0 +1,107 @@
+"""CPU-side checks: C-ABI library loads and exports every symbol the header declares; arena layout, module
+state_dict keys and synthetic generators are consistent with the reference's parameter inventory."""
+import os
+import re
+
+import pytest
+import torch
+
+from multimodalsum_b200 import _lib
+from multimodalsum_b200.engine import ALIGN, StepEngine, _arena_order
+from multimodalsum_b200.synth import ModelConfig, make_batch, make_state_dict, param_shapes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SMALL = dict(encoder_layers=2, decoder_layers=2, ffn_dim=256, vocab_size=512, max_position_embeddings=128)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mmsum_b200.h")).read()
+    declared = sorted(set(re.findall(r"\bint\s+(mmsum_\w+)\s*\(", header)))
+    assert declared, "no declarations found"
+    lib = _lib.lib()           # raises if the .so is missing: there is no fallback
+    for name in declared:
+        assert hasattr(lib, name), "libmmsum_b200.so does not export %s" % name
+    assert sorted(_lib.EXPORTS) == declared
+
+
+def test_ops_refuse_cpu_tensors():
+    from multimodalsum_b200 import ops
+    a = torch.zeros(128, 64, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.gemm(a, a)
+
+
+@pytest.mark.parametrize("dataset", ["yelp", "amazon", "text"])
+def test_arena_order_covers_reference_parameters(dataset):
+    cfg = ModelConfig(dataset=dataset, **SMALL)
+    names = _arena_order(cfg)
+    assert len(names) == len(set(names))
+    shapes = param_shapes(cfg)
+    aliases = ("encoder.embed_tokens.weight", "decoder.embed_tokens.weight", "table_encoder.bart_embedding.weight")
+    expected = {n for n in shapes if not n.endswith(aliases) and not n.endswith("final_logits_bias")}
+    assert set(names) == expected
+    # fused groups must be adjacent in the arena (one GEMM serves q|k|v and k|v)
+    idx = {n: i for i, n in enumerate(names)}
+    for n in names:
+        if n.endswith("self_attn.q_proj.weight"):
+            b = n[:-len("q_proj.weight")]
+            assert idx[b + "k_proj.weight"] == idx[n] + 1 and idx[b + "v_proj.weight"] == idx[n] + 2
+            assert idx[b + "k_proj.bias"] == idx[b + "q_proj.bias"] + 1 and idx[b + "v_proj.bias"] == idx[b + "q_proj.bias"] + 2
+        if n.endswith("encoder_attn.k_proj.weight"):
+            b = n[:-len("k_proj.weight")]
+            assert idx[b + "v_proj.weight"] == idx[n] + 1 and idx[b + "v_proj.bias"] == idx[b + "k_proj.bias"] + 1
+    # shared embedding is last: its gradient is final only after the encoder's gather backward
+    assert names[-1] == "bart_model.model.shared.weight"
+
+
+@pytest.mark.parametrize("dataset", ["yelp", "amazon", "text"])
+def test_module_state_dict_matches_reference_keys(dataset):
+    from multimodalsum_b200.modules import AmazonTableEncoder, MultimodalSum, TextSupervised, YelpTableEncoder
+    cfg = ModelConfig(dataset=dataset, **SMALL)
+    if dataset == "text":
+        m = TextSupervised(config=cfg)
+    else:
+        m = MultimodalSum(TableEncoder=YelpTableEncoder if dataset == "yelp" else AmazonTableEncoder, config=cfg)
+    sd = m.state_dict()
+    shapes = param_shapes(cfg)
+    assert set(sd.keys()) == set(shapes.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+    # aliasing contract: shared == encoder.embed_tokens == decoder.embed_tokens == table_encoder.bart_embedding
+    shared = m.bart_model.model.shared.weight
+    assert m.bart_model.model.encoder.embed_tokens.weight is shared
+    assert m.bart_model.model.decoder.embed_tokens.weight is shared
+    if dataset != "text":
+        assert m.table_encoder.bart_embedding.weight is shared
+    # loads the synthetic reference-keyed state_dict without missing / unexpected keys
+    missing, unexpected = m.load_state_dict(make_state_dict(cfg, seed=0), strict=False)
+    assert not missing and not unexpected
+    # parameter names seen by the engine == arena order set
+    assert {n for n, _ in m.named_parameters()} == set(_arena_order(cfg))
+    # reference init recipe (:188-199): pad row of the shared embedding is zero
+    m2 = MultimodalSum(config=ModelConfig(dataset="yelp", **SMALL)) if dataset == "yelp" else None
+    if m2 is not None:
+        assert m2.bart_model.model.shared.weight[1].abs().sum().item() == 0.0
+
+
+def test_no_cpu_fallback():
+    from multimodalsum_b200.modules import MultimodalSum
+    cfg = ModelConfig(dataset="yelp", **SMALL)
+    m = MultimodalSum(config=cfg)
+    b = make_batch(cfg, 1, seed=0, n_reviews=3, max_imgs=1)
+    with pytest.raises(RuntimeError):
+        m(b.reviews, b.reviews_mask, b.reviews_rating, b.field, b.field_value, b.img, b.img_mask)
+
+
+def test_synthetic_batch_shapes_and_invariants():
+    cfg = ModelConfig(dataset="yelp")
+    b = make_batch(cfg, 2, seed=3)
+    assert b.reviews.shape == (2, 9, 128) and b.img.shape == (2, 10, 196, 1024) and b.field.shape == (47, 6)
+    lens = b.reviews_mask.sum(-1)
+    assert lens.min() >= 60 and lens.max() <= 100
+    idx = (lens - 1).unsqueeze(-1)
+    assert (b.reviews.gather(-1, idx) == 2).all()            # EOS closes every review
+    assert (b.reviews[:, :, 0] != 0).all()                   # never BOS at position 0
+    assert ((b.reviews == 1) == (b.reviews_mask == 0)).all()
+    b2 = make_batch(ModelConfig(dataset="amazon"), 2, seed=3)
+    assert b2.img.shape == (2, 1, 196, 1024) and b2.field.shape == (6, 1) and b2.field_value[4].shape == (2, 3, 8, 12)
