@@ -298,7 +298,8 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const MmsumAttnArgs p)
 // ----------------------------------------------------------------------------------------------
 // backward, part 1 (per query sequence): dQ and DELTA
 //   P = exp2(sc*QK^T - LSE),  dP' = dA V^T,  delta' = rowsum(P o dP'),
-//   dQ += scale * inv_n * ( (P o dP') K - delta' * (P K) )        summed over entities and modalities
+//   dQ += scale * inv_n * ( (P o (dP' - dref)) K + (dref - delta') * (P K) )   summed over entities and modalities
+//   (dref = estimate of delta' from the entity's first key block, so no cancellation happens after bf16 rounding)
 // DELTA stores delta' (un-normalised by inv_n) for part 2.
 // ----------------------------------------------------------------------------------------------
 struct BwdQSmem {
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_dq_kernel(const MmsumAttnArgs
   const float sc = p.scale * kLog2e;
   float dq[8][4], X[8][4], Y[8][4];
   zero_acc(dq);
-  float dl[2] = {0.f, 0.f};
+  float dl[2] = {0.f, 0.f}, dref[2] = {0.f, 0.f};
   uint32_t daf[4][4];
   int cur_mod = -1;
   const bf16* dO = reinterpret_cast<const bf16*>(p.O);
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_dq_kernel(const MmsumAttnArgs
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-    if (it.first) { zero_acc(X); zero_acc(Y); dl[0] = dl[1] = 0.f; }
+    if (it.first) { zero_acc(X); zero_acc(Y); dl[0] = dl[1] = 0.f; dref[0] = dref[1] = 0.f; }
 
     const float* lse = p.LSE + (((long long)qseq * p.H + h) * p.E_total + it.ent) * SQ + r0;
     const float lse_r[2] = {lse[g], lse[g + 8]};
@@ -382,9 +383,27 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_dq_kernel(const MmsumAttnArgs
         if (p.causal) ok = ok && (it.key0 + j <= qr);
         const float pr = ok ? exp2f(s[nt][c] * sc - lse_r[c >> 1]) : 0.f;
         s[nt][c] = pr;
-        dp[nt][c] *= pr;
-        dl[c >> 1] += dp[nt][c];
+        dl[c >> 1] += dp[nt][c] * pr;
       }
+    }
+    if (it.first) {
+      // delta_ref: the softmax-weighted mean of dP' over the FIRST key block.  dS is formed as P o (dP' - delta_ref)
+      // before the bf16 rounding (no cancellation after rounding); the exact delta is restored through Y at the end.
+      float pa[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) { pa[0] += s[nt][0] + s[nt][1]; pa[1] += s[nt][2] + s[nt][3]; }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float a = dl[r], b = pa[r];
+        a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+        b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
+        dref[r] = (b > 0.f) ? a / b : 0.f;
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dp[nt][c] = s[nt][c] * (dp[nt][c] - dref[c >> 1]);
     }
     uint32_t pf[4][4], pdf[4][4];
     pack_p(pf, s);
@@ -403,8 +422,8 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_dq_kernel(const MmsumAttnArgs
         const float w = p.scale * inv_n;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-          dq[nt][2 * r] += w * (X[nt][2 * r] - d * Y[nt][2 * r]);
-          dq[nt][2 * r + 1] += w * (X[nt][2 * r + 1] - d * Y[nt][2 * r + 1]);
+          dq[nt][2 * r] += w * (X[nt][2 * r] + (dref[r] - d) * Y[nt][2 * r]);
+          dq[nt][2 * r + 1] += w * (X[nt][2 * r + 1] + (dref[r] - d) * Y[nt][2 * r + 1]);
         }
       }
     }

@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(bf16* __restrict__ logi
   }
   // block reduce (m, s) and sz
   float wm = warp_max(m);
-  s *= __expf(m - wm);
+  s = (m == -INFINITY) ? 0.f : s * __expf(m - wm);   // lanes / warps without data (V < 8*256) hold m = -inf
   s = warp_sum(s); sz = warp_sum(sz);
   if (lane == 0) { red[0][warp] = wm; red[1][warp] = s; red[2][warp] = sz; }
   __syncthreads();
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(bf16* __restrict__ logi
   for (int w = 1; w < 8; ++w) M = fmaxf(M, red[0][w]);
   float S = 0.f, SZ = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) { S += red[1][w] * __expf(red[0][w] - M); SZ += red[2][w]; }
+  for (int w = 0; w < 8; ++w) { S += (red[0][w] == -INFINITY) ? 0.f : red[1][w] * __expf(red[0][w] - M); SZ += red[2][w]; }
   const float lse = M + logf(S);
   if (tid == 0) {
     const float logp_y = zy - lse;

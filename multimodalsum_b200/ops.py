@@ -4,10 +4,20 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, check
+from ._lib import GemmArgs
+from ._lib import check as _check_rc
+
+LAUNCHES = 0      # kernels launched through the C-ABI since import (bench.py: gpu_launches)
+GEMM_TIMER = None  # optional callable(flops) -> context manager bracketing each GEMM launch (bench.py roofline)
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 AUX_NONE, AUX_STORE_PREACT, AUX_MUL_DACT = 0, 1, 2
+
+
+def check(rc, what, n_kernels=1):
+    global LAUNCHES
+    _check_rc(rc, what)
+    LAUNCHES += n_kernels
 
 
 def _stream():
@@ -71,7 +81,11 @@ def gemm(A, B, out=None, *, a_t=False, b_t=False, out_dtype=torch.bfloat16, bias
     a.act, a.aux_mode = act, aux_mode
     a.aux = aux.data_ptr() if aux is not None else None
     a.ld_aux = aux.stride(0) if aux is not None else 0
-    check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16")
+    if GEMM_TIMER is not None:
+        with GEMM_TIMER(2.0 * M * N * K):
+            check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16")
+    else:
+        check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16")
     return out
 
 
@@ -95,7 +109,11 @@ def gemm_cat(A, A2, B, out=None, *, bias=None, out_dtype=torch.bfloat16):
     a.alpha = 1.0
     a.bias = bias.data_ptr() if bias is not None else None
     a.A2, a.lda2, a.k_split = A2.data_ptr(), A2.stride(0), K1
-    check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16(cat)")
+    if GEMM_TIMER is not None:
+        with GEMM_TIMER(2.0 * M * N * K):
+            check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16(cat)")
+    else:
+        check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16(cat)")
     return out
 
 
@@ -115,7 +133,7 @@ def embed_ln_bwd(dout, dout2, ids, E, P, rating_diff, remb, gamma, mean, rstd, d
     check(_lib.lib().mmsum_embed_ln_bwd(_ptr(dout), _ptr(dout2), _ptr(ids), _ptr(E), _ptr(P), _ptr(rating_diff), _ptr(remb),
                                         _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dE), _ptr(dP), _ptr(dremb), _ptr(dgamma),
                                         _ptr(dbeta), _ptr(dz), rows, S, E.shape[1], pad_id, C.c_float(p_drop),
-                                        C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_embed_ln_bwd")
+                                        C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_embed_ln_bwd", 2)
 
 
 def add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid):
@@ -154,7 +172,7 @@ def ce_fwd_bwd(logits, V, target, eps, gscale, gscale_dev, loss_rows, loss_out, 
     check(_lib.lib().mmsum_ce_fwd_bwd(_ptr(logits), C.c_int64(logits.stride(0)), rows, V, _ptr(target),
                                       C.c_float(-1.0 if eps is None else eps), C.c_float(gscale), _ptr(gscale_dev),
                                       _ptr(loss_rows), _ptr(loss_out), C.c_float(loss_scale), int(write_grad), _stream()),
-          "mmsum_ce_fwd_bwd")
+          "mmsum_ce_fwd_bwd", 2 if loss_out is not None else 1)
 
 
 def attn_args(**kw):
@@ -175,7 +193,7 @@ def attn_fwd(a):
 
 
 def attn_bwd(a):
-    check(_lib.lib().mmsum_attn_bwd(C.byref(a), _stream()), "mmsum_attn_bwd")
+    check(_lib.lib().mmsum_attn_bwd(C.byref(a), _stream()), "mmsum_attn_bwd", 2)
 
 
 def prep_step(reviews, reviews_mask, rating, table_valid, img_mask, **kw):
