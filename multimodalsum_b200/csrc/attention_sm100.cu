@@ -1,0 +1,825 @@
+// tcgen05 / TMEM / TMA multi-entity attention for sm_100a — forward, dQ backward, dK/dV backward.
+//
+// One family of kernels covers
+//   * encoder self-attention        (modeling_multimodalsum.py:746-749, 783-853; key-pad mask)
+//   * decoder causal self-attention (same call path + causal triu mask)
+//   * the multi-entity, multi-modal cross-attention (:722-745, :768-869): per modality an independent softmax PER
+//     ENTITY (review / table / image) and the mean over the entities that have a valid key; the leave-one-out target of
+//     multimodal_train.py:150-163 is "entity i is excluded for target i".
+// Self-attention is the special case "one modality, one entity, memory = own sequence".
+//
+// Masking semantics: pad keys of a valid entity get probability exactly 0 (the reference fills -2^16 / -inf, both
+// underflow to 0 in fp32 next to any valid key); entities without a valid key are skipped (the reference zeroes them and
+// removes them from the divisor); a modality without any valid entity yields 0.
+//
+// Shapes are the model's: 128 query positions per sequence (one UMMA M=128 tile), head_dim 64, <= 208 keys per entity,
+// so a whole entity's score tile lives in TMEM (128 lanes x <=208 fp32 columns) and no online-softmax rescaling is needed.
+//
+// forward, one CTA per (sequence, head), 192 threads:
+//   warp 0    TMA producer: Q once, then K_e / V_e per entity into a 2-stage smem ring (128B swizzle)
+//   warp 1    MMA issuer:   S_e = Q K_e^T -> TMEM (double buffered);  O_e = P_e V_e -> TMEM
+//   warps 2-5 softmax:      thread = query row; tcgen05.ld S, max, exp2, bf16 P -> swizzled smem (A operand of P V);
+//                           reads O_e back and accumulates (1/n)(1/l_e) O_e in registers; writes the modality outputs
+#include "common.cuh"
+#include "../../include/mmsum_b200.h"
+
+namespace mmsum {
+
+static constexpr int SQ = 128;
+static constexpr int HD = 64;
+static constexpr int kMaxKeys = 208;            // per entity, multiple of 16
+static constexpr int kMaxEnt = 24;
+static constexpr float kLog2e = 1.4426950408889634f;
+static constexpr int kKVStageBytes = kMaxKeys * 128;   // 26624 = 26 * 1024
+static constexpr int kPBytes = 4 * SQ * 128;           // four 64-key atoms of [128 rows x 128 B]
+static constexpr uint32_t kColS0 = 0, kColS1 = 224, kColO = 448;
+
+struct EntItem {
+  int kv_row0;     // first KV row of the entity
+  int nkeys;       // keys of the entity (Sk of its modality)
+  int n16;         // nkeys rounded up to 16
+  short mod, ent;  // modality, global entity index
+};
+
+struct AttnMaps {
+  CUtensorMap q;       // Q rows, box {64, 128}
+  CUtensorMap kv[3];   // per modality: KV rows, box {64, Sk}
+  CUtensorMap d_o;     // bwd: upstream gradient rows (all modalities stacked), box {64, 128}
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ int build_ent_items(const MmsumAttnArgs& p, int qseq, EntItem* items) {
+  const int biz = qseq / p.R;
+  const int tgt = qseq - biz * p.R;
+  int n = 0;
+  for (int m = 0; m < p.n_mod; ++m) {
+    const MmsumAttnMod& md = p.mods[m];
+    for (int e = 0; e < md.E; ++e) {
+      if (md.loo && e == tgt) continue;
+      const int ge = md.ent_base + e;
+      if (p.ent_valid != nullptr && p.ent_valid[(long long)biz * p.E_total + ge] == 0) continue;
+      EntItem it;
+      it.kv_row0 = (int)(md.kv_row_base + ((long long)biz * md.E + e) * md.Sk);
+      it.nkeys = md.Sk;
+      it.n16 = (md.Sk + 15) & ~15;
+      it.mod = (short)m; it.ent = (short)ge;
+      if (n < kMaxEnt) items[n++] = it;
+    }
+  }
+  return n;
+}
+
+// validity bitmask of the entity's keys: bit j of word w = key 32w + j may be attended
+__device__ __forceinline__ void key_bitmask(const MmsumAttnArgs& p, const EntItem& it, int lane, uint32_t (&words)[7]) {
+#pragma unroll
+  for (int w = 0; w < 7; ++w) {
+    const int j = w * 32 + lane;
+    bool ok = j < it.nkeys;
+    if (ok && p.key_valid != nullptr) ok = p.key_valid[(long long)it.kv_row0 + j] != 0;
+    words[w] = __ballot_sync(0xffffffffu, ok);
+  }
+}
+
+struct FwdSmem {
+  uint8_t q[SQ * 128];
+  uint8_t k[2][kKVStageBytes];
+  uint8_t v[2][kKVStageBytes];
+  uint8_t p[kPBytes];
+  EntItem items[kMaxEnt];
+  uint64_t q_full, kv_full[2], kv_empty[2], s_full[2], s_empty[2], p_full, mma2_done;
+  uint32_t tmem_slot;
+  int n_items;
+};
+
+__global__ void __launch_bounds__(192, 1)
+attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tgt = blockIdx.x % p.R;
+  const int h = (blockIdx.x / p.R) % p.H;
+  const int biz = blockIdx.x / (p.R * p.H);
+  const int qseq = biz * p.R + tgt;
+  const int qrow0 = qseq * SQ;
+
+  if (threadIdx.x == 0) {
+    sm.n_items = build_ent_items(p, qseq, sm.items);
+    mbar_init(&sm.q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.kv_full[s], 1); mbar_init(&sm.kv_empty[s], 1);
+      mbar_init(&sm.s_full[s], 1); mbar_init(&sm.s_empty[s], 128);
+    }
+    mbar_init(&sm.p_full, 128);
+    mbar_init(&sm.mma2_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.q);
+  }
+  // V rows beyond an entity's key count are multiplied by P = 0: they must hold finite values, never stale NaN bits
+  for (int i = threadIdx.x; i < 2 * kKVStageBytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sm.v[0])[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 1) { tmem_alloc(&sm.tmem_slot, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_slot;
+  const int n_items = sm.n_items;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&sm.q_full, SQ * 128);
+      tma_load_2d(sm.q, &maps.q, &sm.q_full, p.q_col + h * HD, qrow0);
+      for (int i = 0; i < n_items; ++i) {
+        const int st = i & 1;
+        mbar_wait(&sm.kv_empty[st], ((i >> 1) & 1) ^ 1);
+        const EntItem it = sm.items[i];
+        mbar_expect_tx(&sm.kv_full[st], 2 * it.nkeys * 128);
+        tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.kv_full[st], p.k_col + h * HD, it.kv_row0);
+        tma_load_2d(sm.v[st], &maps.kv[it.mod], &sm.kv_full[st], p.v_col + h * HD, it.kv_row0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_items > 0) {
+      const uint32_t qaddr = smem_u32(sm.q), paddr = smem_u32(sm.p);
+      mbar_wait(&sm.q_full, 0);
+      auto issue_s = [&](int i) {
+        const int st = i & 1;
+        const EntItem it = sm.items[i];
+        mbar_wait(&sm.kv_full[st], (i >> 1) & 1);
+        mbar_wait(&sm.s_empty[st], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, it.n16, 0, 0);
+        const uint32_t kaddr = smem_u32(sm.k[st]);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem + (st ? kColS1 : kColS0), umma_smem_desc_sw128(qaddr + kk * 32, 16, 1024),
+                    umma_smem_desc_sw128(kaddr + kk * 32, 16, 1024), idesc, kk > 0);
+        umma_commit(&sm.s_full[st]);
+      };
+      issue_s(0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+      for (int i = 0; i < n_items; ++i) {
+        if (i + 1 < n_items) issue_s(i + 1);
+        const int st = i & 1;
+        const EntItem it = sm.items[i];
+        mbar_wait(&sm.p_full, i & 1);
+        tc_fence_after();
+        const uint32_t vaddr = smem_u32(sm.v[st]);
+        for (int kk = 0; kk < it.n16 / 16; ++kk)
+          umma_bf16(tmem + kColO, umma_smem_desc_sw128(paddr + (kk >> 2) * (SQ * 128) + (kk & 3) * 32, 16, 1024),
+                    umma_smem_desc_sw128(vaddr + kk * 2048, 8192, 1024), idesc_o, kk > 0);
+        umma_commit(&sm.kv_empty[st]);
+        umma_commit(&sm.mma2_done);
+      }
+    }
+  } else {
+    // ===================== softmax / accumulate warps: thread = query row =====================
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const float sc = p.scale * kLog2e;
+    float acc[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    bf16* Og = reinterpret_cast<bf16*>(p.O);
+    auto flush = [&](int m) {
+      bf16* dst = Og + p.mods[m].o_off + (long long)(qrow0 + row) * p.ldo + h * HD;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 u;
+        u.x = pack_bf16(acc[j * 8 + 0], acc[j * 8 + 1]); u.y = pack_bf16(acc[j * 8 + 2], acc[j * 8 + 3]);
+        u.z = pack_bf16(acc[j * 8 + 4], acc[j * 8 + 5]); u.w = pack_bf16(acc[j * 8 + 6], acc[j * 8 + 7]);
+        *reinterpret_cast<uint4*>(dst + j * 8) = u;
+      }
+#pragma unroll
+      for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    };
+    auto add_o = [&](float wgt) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + lane_off + kColO + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[half * 32 + i] += wgt * __uint_as_float(r[i]);
+      }
+    };
+    int cur_mod = 0;
+    float w_prev = 0.f;
+    uint8_t* prow = sm.p + row * 128;
+    for (int i = 0; i < n_items; ++i) {
+      const EntItem it = sm.items[i];
+      const int st = i & 1;
+      uint32_t words[7];
+      key_bitmask(p, it, lane, words);
+      const uint32_t scol = tmem + lane_off + (st ? kColS1 : kColS0);
+      const int nchunk = (it.n16 + 31) >> 5;
+      mbar_wait(&sm.s_full[st], (i >> 1) & 1);
+      tc_fence_after();
+      // pass 1: row max over the valid keys
+      float mx = -INFINITY;
+      for (int c = 0; c < nchunk; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(scol + c * 32, r);
+        tmem_ld_wait();
+        uint32_t wd = words[c];
+        if (p.causal) { const int lim = row - c * 32; wd &= (lim >= 31) ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u)); }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = ((wd >> j) & 1u) ? fmaxf(mx, __uint_as_float(r[j])) : mx;
+      }
+      const float msc = (mx == -INFINITY) ? 0.f : mx * sc;
+      // the previous entity's P V has finished: fold its output in, and its P buffer / O accumulator are free again
+      if (i > 0) {
+        mbar_wait(&sm.mma2_done, (i - 1) & 1);
+        tc_fence_after();
+        add_o(w_prev);
+        if (it.mod != cur_mod) { while (cur_mod < it.mod) { flush(cur_mod); ++cur_mod; } }
+      } else {
+        while (cur_mod < it.mod) { flush(cur_mod); ++cur_mod; }
+      }
+      // pass 2: P = exp2(s*sc - m) -> bf16 into the swizzled A-operand tile; l = row sum
+      float l = 0.f;
+      for (int c = 0; c < nchunk; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(scol + c * 32, r);
+        tmem_ld_wait();
+        uint32_t wd = words[c];
+        if (p.causal) { const int lim = row - c * 32; wd &= (lim >= 31) ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u)); }
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          pv[j] = ((wd >> j) & 1u) ? ex2(fmaf(__uint_as_float(r[j]), sc, -msc)) : 0.f;
+          l += pv[j];
+        }
+        uint8_t* atom = prow + (c >> 1) * (SQ * 128);
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          uint4 u;
+          u.x = pack_bf16(pv[g8 * 8 + 0], pv[g8 * 8 + 1]); u.y = pack_bf16(pv[g8 * 8 + 2], pv[g8 * 8 + 3]);
+          u.z = pack_bf16(pv[g8 * 8 + 4], pv[g8 * 8 + 5]); u.w = pack_bf16(pv[g8 * 8 + 6], pv[g8 * 8 + 7]);
+          const int chunk = (c & 1) * 4 + g8;
+          *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = u;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sm.s_empty[st]);
+      fence_proxy_async_smem();
+      mbar_arrive(&sm.p_full);
+      const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
+      w_prev = (l > 0.f) ? inv_n / l : 0.f;
+      p.LSE[(((long long)qseq * p.H + h) * p.E_total + it.ent) * SQ + row] = (l > 0.f) ? (msc + log2f(l)) : INFINITY;
+    }
+    if (n_items > 0) {
+      mbar_wait(&sm.mma2_done, (n_items - 1) & 1);
+      tc_fence_after();
+      add_o(w_prev);
+    }
+    while (cur_mod < p.n_mod) { flush(cur_mod); ++cur_mod; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ----------------------------------------------------------------------------------------------
+// backward, part 1 — one CTA per (sequence, head): dQ and DELTA
+//   per entity:  S = Q K^T and dP' = dA V^T into TMEM;  P = exp2(sc*S - LSE) (kept in registers as bf16),
+//   delta' = rowsum(P o dP');  dS = scale*inv_n * P o (dP' - delta') -> bf16 smem;  dQ += dS K  (TMEM, all entities)
+// ----------------------------------------------------------------------------------------------
+static constexpr uint32_t kColDP = 224, kColDQ = 448;
+
+struct BwdQSmem {
+  uint8_t q[SQ * 128];
+  uint8_t da[SQ * 128];
+  uint8_t k[2][kKVStageBytes];
+  uint8_t v[2][kKVStageBytes];
+  uint8_t ds[kPBytes];
+  EntItem items[kMaxEnt];
+  uint64_t q_full, da_full, da_free, kv_full[2], kv_empty[2], sdp_full, sdp_empty, ds_full, ds_free;
+  uint32_t tmem_slot;
+  int n_items;
+};
+
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  BwdQSmem& sm = *reinterpret_cast<BwdQSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tgt = blockIdx.x % p.R;
+  const int h = (blockIdx.x / p.R) % p.H;
+  const int biz = blockIdx.x / (p.R * p.H);
+  const int qseq = biz * p.R + tgt;
+  const int qrow0 = qseq * SQ;
+
+  if (threadIdx.x == 0) {
+    sm.n_items = build_ent_items(p, qseq, sm.items);
+    mbar_init(&sm.q_full, 1); mbar_init(&sm.da_full, 1); mbar_init(&sm.da_free, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&sm.kv_full[s], 1); mbar_init(&sm.kv_empty[s], 1); }
+    mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, 128);
+    mbar_init(&sm.ds_full, 128); mbar_init(&sm.ds_free, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 4 * kKVStageBytes / 16; i += blockDim.x)   // K and V stages: finite contents only
+    reinterpret_cast<uint4*>(sm.k[0])[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 1) { tmem_alloc(&sm.tmem_slot, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_slot;
+  const int n_items = sm.n_items;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&sm.q_full, SQ * 128);
+      tma_load_2d(sm.q, &maps.q, &sm.q_full, p.q_col + h * HD, qrow0);
+      int cur_mod = -1, n_da = 0;
+      for (int i = 0; i < n_items; ++i) {
+        const int st = i & 1;
+        const EntItem it = sm.items[i];
+        if (it.mod != cur_mod) {
+          mbar_wait(&sm.da_free, (n_da & 1) ^ 1);      // previous modality's dP MMAs have retired
+          mbar_expect_tx(&sm.da_full, SQ * 128);
+          tma_load_2d(sm.da, &maps.d_o, &sm.da_full, h * HD, (int)(p.mods[it.mod].o_off / p.ldo) + qrow0);
+          cur_mod = it.mod; ++n_da;
+        }
+        mbar_wait(&sm.kv_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&sm.kv_full[st], 2 * it.nkeys * 128);
+        tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.kv_full[st], p.k_col + h * HD, it.kv_row0);
+        tma_load_2d(sm.v[st], &maps.kv[it.mod], &sm.kv_full[st], p.v_col + h * HD, it.kv_row0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_items > 0) {
+      const uint32_t qaddr = smem_u32(sm.q), daaddr = smem_u32(sm.da), dsaddr = smem_u32(sm.ds);
+      mbar_wait(&sm.q_full, 0);
+      int cur_mod = -1, n_da = 0;
+      auto issue_sdp = [&](int i) {
+        const int st = i & 1;
+        const EntItem it = sm.items[i];
+        if (it.mod != cur_mod) { mbar_wait(&sm.da_full, n_da & 1); cur_mod = it.mod; ++n_da; }
+        mbar_wait(&sm.kv_full[st], (i >> 1) & 1);
+        mbar_wait(&sm.sdp_empty, (i & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, it.n16, 0, 0);
+        const uint32_t kaddr = smem_u32(sm.k[st]), vaddr = smem_u32(sm.v[st]);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem + kColS0, umma_smem_desc_sw128(qaddr + kk * 32, 16, 1024),
+                    umma_smem_desc_sw128(kaddr + kk * 32, 16, 1024), idesc, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem + kColDP, umma_smem_desc_sw128(daaddr + kk * 32, 16, 1024),
+                    umma_smem_desc_sw128(vaddr + kk * 32, 16, 1024), idesc, kk > 0);
+        umma_commit(&sm.sdp_full);
+        // last item of its modality: the dA tile may be replaced once these MMAs retire
+        if (i + 1 >= n_items || sm.items[i + 1].mod != it.mod) umma_commit(&sm.da_free);
+      };
+      issue_sdp(0);
+      const uint32_t idesc_q = umma_idesc_bf16(128, HD, 0, 1);
+      for (int i = 0; i < n_items; ++i) {
+        if (i + 1 < n_items) issue_sdp(i + 1);
+        const int st = i & 1;
+        const EntItem it = sm.items[i];
+        mbar_wait(&sm.ds_full, i & 1);
+        tc_fence_after();
+        const uint32_t kaddr = smem_u32(sm.k[st]);
+        for (int kk = 0; kk < it.n16 / 16; ++kk)
+          umma_bf16(tmem + kColDQ, umma_smem_desc_sw128(dsaddr + (kk >> 2) * (SQ * 128) + (kk & 3) * 32, 16, 1024),
+                    umma_smem_desc_sw128(kaddr + kk * 2048, 8192, 1024), idesc_q, (i > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&sm.kv_empty[st]);
+        umma_commit(&sm.ds_free);
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const float sc = p.scale * kLog2e;
+    uint8_t* dsrow = sm.ds + row * 128;
+    for (int i = 0; i < n_items; ++i) {
+      const EntItem it = sm.items[i];
+      uint32_t words[7];
+      key_bitmask(p, it, lane, words);
+      const int nchunk = (it.n16 + 31) >> 5;
+      const long long li = (((long long)qseq * p.H + h) * p.E_total + it.ent) * SQ + row;
+      const float lse = p.LSE[li];
+      const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
+      mbar_wait(&sm.sdp_full, i & 1);
+      tc_fence_after();
+      uint32_t pp[7][16];
+      float delta = 0.f;
+#pragma unroll
+      for (int c = 0; c < 7; ++c) {
+        if (c < nchunk) {
+          uint32_t rs[32], rd[32];
+          tmem_ld_32x32(tmem + lane_off + kColS0 + c * 32, rs);
+          tmem_ld_32x32(tmem + lane_off + kColDP + c * 32, rd);
+          tmem_ld_wait();
+          uint32_t wd = words[c];
+          if (p.causal) { const int lim = row - c * 32; wd &= (lim >= 31) ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u)); }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ((wd >> j) & 1u) ? ex2(fmaf(__uint_as_float(rs[j]), sc, -lse)) : 0.f;
+            const float p1 = ((wd >> (j + 1)) & 1u) ? ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse)) : 0.f;
+            delta = fmaf(p0, __uint_as_float(rd[j]), delta);
+            delta = fmaf(p1, __uint_as_float(rd[j + 1]), delta);
+            pp[c][j >> 1] = pack_bf16(p0, p1);
+          }
+        }
+      }
+      p.DELTA[li] = delta;
+      if (i > 0) mbar_wait(&sm.ds_free, (i - 1) & 1);   // dQ MMA of the previous entity has consumed the dS tile
+      const float wgt = p.scale * inv_n;
+#pragma unroll
+      for (int c = 0; c < 7; ++c) {
+        if (c < nchunk) {
+          uint32_t rd[32];
+          tmem_ld_32x32(tmem + lane_off + kColDP + c * 32, rd);
+          tmem_ld_wait();
+          uint8_t* atom = dsrow + (c >> 1) * (SQ * 128);
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 pr = unpack_bf16(pp[c][g8 * 4 + e]);
+              const int j = g8 * 8 + 2 * e;
+              o[e] = pack_bf16(wgt * pr.x * (__uint_as_float(rd[j]) - delta), wgt * pr.y * (__uint_as_float(rd[j + 1]) - delta));
+            }
+            const int chunk = (c & 1) * 4 + g8;
+            *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sm.sdp_empty);
+      fence_proxy_async_smem();
+      mbar_arrive(&sm.ds_full);
+    }
+    // dQ: read the accumulator once every entity has been folded in
+    bf16* dQg = reinterpret_cast<bf16*>(p.dQ) + (long long)(qrow0 + row) * p.lddq + p.dq_col + h * HD;
+    if (n_items > 0) {
+      mbar_wait(&sm.ds_free, (n_items - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + lane_off + kColDQ + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
+          u.y = pack_bf16(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
+          u.z = pack_bf16(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
+          u.w = pack_bf16(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
+          *reinterpret_cast<uint4*>(dQg + half * 32 + j * 8) = u;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(dQg + j * 8) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ----------------------------------------------------------------------------------------------
+// backward, part 2 — one CTA per (business, head, entity tile of <=128 keys): dK, dV summed over the consumer targets
+//   per target:  S^T = K Q^T and dP'^T = V dA^T into TMEM (keys on the lanes);
+//   Pn^T = inv_n * exp2(sc*S^T - LSE[q]);  dS^T = scale * Pn^T o (dP'^T - delta'[q]);  both -> bf16 smem;
+//   dV += Pn^T dA,  dK += dS^T Q  (TMEM accumulators over all targets)
+// ----------------------------------------------------------------------------------------------
+struct BwdKVSmem {
+  uint8_t k[SQ * 128];
+  uint8_t v[SQ * 128];
+  uint8_t q[2][SQ * 128];
+  uint8_t da[2][SQ * 128];
+  uint8_t pt[2 * SQ * 128];
+  uint8_t dst[2 * SQ * 128];
+  float lse[2][SQ];
+  float dlt[2][SQ];
+  uint64_t kv_full, qd_full[2], qd_empty[2], sdp_full, sdp_empty, pds_full, pds_free;
+  uint32_t tmem_slot;
+};
+static constexpr uint32_t kColST = 0, kColDPT = 128, kColDK = 256, kColDV = 320;
+
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ CUtensorMap kv128,
+                       const MmsumAttnArgs p, int tiles_per_bh) {
+  extern __shared__ uint8_t smem_raw[];
+  BwdKVSmem& sm = *reinterpret_cast<BwdKVSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int rem = blockIdx.x % tiles_per_bh;
+  const int bh = blockIdx.x / tiles_per_bh;
+  const int h = bh % p.H, biz = bh / p.H;
+  int m = 0, e = 0, tile = 0;
+  for (m = 0; m < p.n_mod; ++m) {
+    const int nt = (p.mods[m].Sk + SQ - 1) / SQ;
+    const int cnt = p.mods[m].E * nt;
+    if (rem < cnt) { e = rem / nt; tile = rem % nt; break; }
+    rem -= cnt;
+  }
+  const MmsumAttnMod& md = p.mods[m];
+  const int ge = md.ent_base + e;
+  const int key0 = tile * SQ;
+  const int nkeys = min(SQ, md.Sk - key0);
+  const int kvrow0 = (int)(md.kv_row_base + ((long long)biz * md.E + e) * md.Sk) + key0;
+  const bool ent_ok = (p.ent_valid == nullptr) || (p.ent_valid[(long long)biz * p.E_total + ge] != 0);
+  bf16* dKV = reinterpret_cast<bf16*>(p.dKV);
+
+  // consumer targets of this entity (leave-one-out excludes target e)
+  int n_steps = 0;
+  for (int tg = 0; tg < p.R; ++tg) n_steps += (md.loo && tg == e) ? 0 : 1;
+  if (!ent_ok || n_steps == 0) {
+    // null entity: its gradient is exactly zero (the buffer is never memset)
+    if (warp >= 2) {
+      const int row = (warp & 3) * 32 + lane;
+      if (row < nkeys) {
+        bf16* dk = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dk_col + h * HD;
+        bf16* dv = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dv_col + h * HD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          *reinterpret_cast<uint4*>(dk + j * 8) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(dv + j * 8) = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&sm.qd_full[s], 1); mbar_init(&sm.qd_empty[s], 1); }
+    mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, 128);
+    mbar_init(&sm.pds_full, 128); mbar_init(&sm.pds_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&sm.tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_slot;
+  auto step_target = [&](int s) {   // s-th consumer target -> target index
+    int tg = s;
+    if (md.loo && tg >= e) ++tg;
+    return tg;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&sm.kv_full, 2 * SQ * 128);
+      tma_load_2d(sm.k, &kv128, &sm.kv_full, p.k_col + h * HD, kvrow0);
+      tma_load_2d(sm.v, &kv128, &sm.kv_full, p.v_col + h * HD, kvrow0);
+      for (int s = 0; s < n_steps; ++s) {
+        const int st = s & 1;
+        const int qrow0 = (biz * p.R + step_target(s)) * SQ;
+        mbar_wait(&sm.qd_empty[st], ((s >> 1) & 1) ^ 1);
+        mbar_expect_tx(&sm.qd_full[st], 2 * SQ * 128);
+        tma_load_2d(sm.q[st], &maps.q, &sm.qd_full[st], p.q_col + h * HD, qrow0);
+        tma_load_2d(sm.da[st], &maps.d_o, &sm.qd_full[st], h * HD, (int)(md.o_off / p.ldo) + qrow0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t kaddr = smem_u32(sm.k), vaddr = smem_u32(sm.v), ptaddr = smem_u32(sm.pt), dsaddr = smem_u32(sm.dst);
+      const uint32_t idesc_s = umma_idesc_bf16(128, SQ, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+      mbar_wait(&sm.kv_full, 0);
+      auto issue_sdp = [&](int s) {
+        const int st = s & 1;
+        mbar_wait(&sm.qd_full[st], (s >> 1) & 1);
+        mbar_wait(&sm.sdp_empty, (s & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t qaddr = smem_u32(sm.q[st]), daaddr = smem_u32(sm.da[st]);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem + kColST, umma_smem_desc_sw128(kaddr + kk * 32, 16, 1024),
+                    umma_smem_desc_sw128(qaddr + kk * 32, 16, 1024), idesc_s, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem + kColDPT, umma_smem_desc_sw128(vaddr + kk * 32, 16, 1024),
+                    umma_smem_desc_sw128(daaddr + kk * 32, 16, 1024), idesc_s, kk > 0);
+        umma_commit(&sm.sdp_full);
+      };
+      issue_sdp(0);
+      for (int s = 0; s < n_steps; ++s) {
+        if (s + 1 < n_steps) issue_sdp(s + 1);
+        const int st = s & 1;
+        mbar_wait(&sm.pds_full, s & 1);
+        tc_fence_after();
+        const uint32_t qaddr = smem_u32(sm.q[st]), daaddr = smem_u32(sm.da[st]);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // contraction over the 128 queries
+          umma_bf16(tmem + kColDV, umma_smem_desc_sw128(ptaddr + (kk >> 2) * (SQ * 128) + (kk & 3) * 32, 16, 1024),
+                    umma_smem_desc_sw128(daaddr + kk * 2048, 8192, 1024), idesc_o, (s > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16(tmem + kColDK, umma_smem_desc_sw128(dsaddr + (kk >> 2) * (SQ * 128) + (kk & 3) * 32, 16, 1024),
+                    umma_smem_desc_sw128(qaddr + kk * 2048, 8192, 1024), idesc_o, (s > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&sm.qd_empty[st]);
+        umma_commit(&sm.pds_free);
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;            // key within the tile
+    const int et = warp - 2;                   // 0..3: index among the softmax warps
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const float sc = p.scale * kLog2e;
+    const bool kvalid = (row < nkeys) && (p.key_valid == nullptr || p.key_valid[(long long)kvrow0 + row] != 0);
+    uint8_t* ptrow = sm.pt + row * 128;
+    uint8_t* dsrow = sm.dst + row * 128;
+    for (int s = 0; s < n_steps; ++s) {
+      const int st = s & 1;
+      const int qseq = biz * p.R + step_target(s);
+      const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + m] : 1.f;
+      {  // stage LSE / DELTA of this target's 128 query rows (one value per softmax thread)
+        const long long li = (((long long)qseq * p.H + h) * p.E_total + ge) * SQ + (et * 32 + lane);
+        sm.lse[st][et * 32 + lane] = p.LSE[li];
+        sm.dlt[st][et * 32 + lane] = p.DELTA[li];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&sm.sdp_full, s & 1);
+      tc_fence_after();
+      if (s > 0) mbar_wait(&sm.pds_free, (s - 1) & 1);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rd[32];
+        tmem_ld_32x32(tmem + lane_off + kColST + c * 32, rs);
+        tmem_ld_32x32(tmem + lane_off + kColDPT + c * 32, rd);
+        tmem_ld_wait();
+        uint32_t wd = kvalid ? 0xffffffffu : 0u;
+        if (p.causal) {  // key (key0 + row) <= query (c*32 + j)  <=>  j >= key0 + row - c*32
+          const int lo = key0 + row - c * 32;
+          wd &= (lo <= 0) ? 0xffffffffu : (lo >= 32 ? 0u : ~((1u << lo) - 1u));
+        }
+        uint8_t* patom = ptrow + (c >> 1) * (SQ * 128);
+        uint8_t* datom = dsrow + (c >> 1) * (SQ * 128);
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          uint32_t po[4], dso[4];
+          const float4 l0 = *reinterpret_cast<const float4*>(&sm.lse[st][c * 32 + g8 * 8]);
+          const float4 l1 = *reinterpret_cast<const float4*>(&sm.lse[st][c * 32 + g8 * 8 + 4]);
+          const float4 d0 = *reinterpret_cast<const float4*>(&sm.dlt[st][c * 32 + g8 * 8]);
+          const float4 d1 = *reinterpret_cast<const float4*>(&sm.dlt[st][c * 32 + g8 * 8 + 4]);
+          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const int j = g8 * 8 + 2 * e2;
+            const float p0 = ((wd >> j) & 1u) ? inv_n * ex2(fmaf(__uint_as_float(rs[j]), sc, -ls[2 * e2])) : 0.f;
+            const float p1 = ((wd >> (j + 1)) & 1u) ? inv_n * ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -ls[2 * e2 + 1])) : 0.f;
+            po[e2] = pack_bf16(p0, p1);
+            dso[e2] = pack_bf16(p.scale * p0 * (__uint_as_float(rd[j]) - dl[2 * e2]),
+                                p.scale * p1 * (__uint_as_float(rd[j + 1]) - dl[2 * e2 + 1]));
+          }
+          const int chunk = (c & 1) * 4 + g8;
+          *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[0], po[1], po[2], po[3]);
+          *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sm.sdp_empty);
+      fence_proxy_async_smem();
+      mbar_arrive(&sm.pds_full);
+    }
+    mbar_wait(&sm.pds_free, (n_steps - 1) & 1);
+    tc_fence_after();
+    {
+      // every lane issues the (.sync.aligned) TMEM loads; only lanes that own a key store
+      const int srow = row < nkeys ? row : 0;
+      bf16* dk = dKV + (long long)(kvrow0 + srow) * p.lddkv + p.dk_col + h * HD;
+      bf16* dv = dKV + (long long)(kvrow0 + srow) * p.lddkv + p.dv_col + h * HD;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        bf16* dst = which == 0 ? dk : dv;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem + lane_off + (which == 0 ? kColDK : kColDV) + half * 32, r);
+          tmem_ld_wait();
+          if (row < nkeys) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
+              u.y = pack_bf16(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
+              u.z = pack_bf16(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
+              u.w = pack_bf16(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
+              *reinterpret_cast<uint4*>(dst + half * 32 + j * 8) = u;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+static int validate_tc(const MmsumAttnArgs* a, bool bwd) {
+  if (!a || !a->Q || !a->KV || !a->O || !a->LSE) return MMSUM_ERR_INVALID;
+  if (a->n_qseq <= 0 || a->H <= 0 || a->R <= 0 || a->n_mod < 1 || a->n_mod > 3) return MMSUM_ERR_INVALID;
+  if (a->n_qseq % a->R) return MMSUM_ERR_INVALID;
+  if ((a->ldq % 8) || (a->ldkv % 8) || (a->ldo % 8) || (a->q_col % 8) || (a->k_col % 8) || (a->v_col % 8)) return MMSUM_ERR_INVALID;
+  int ents = 0;
+  for (int m = 0; m < a->n_mod; ++m) {
+    if (a->mods[m].E <= 0 || a->mods[m].Sk <= 0 || a->mods[m].Sk > kMaxKeys) return MMSUM_ERR_INVALID;
+    ents += a->mods[m].E;
+    if (a->mods[m].o_off % a->ldo) return MMSUM_ERR_INVALID;
+  }
+  if (ents > kMaxEnt || ents > a->E_total) return MMSUM_ERR_INVALID;
+  if (a->causal && (a->n_mod != 1 || a->mods[0].Sk != SQ)) return MMSUM_ERR_INVALID;
+  if (bwd) {
+    if (!a->DELTA || !a->dQ || !a->dKV) return MMSUM_ERR_INVALID;
+    if ((a->lddq % 8) || (a->lddkv % 8) || (a->dq_col % 8) || (a->dk_col % 8) || (a->dv_col % 8)) return MMSUM_ERR_INVALID;
+  }
+  return 0;
+}
+
+static int build_maps(const MmsumAttnArgs* a, AttnMaps* mp, bool bwd) {
+  const int n_biz = a->n_qseq / a->R;
+  const uint64_t qrows = (uint64_t)a->n_qseq * SQ;
+  int rc = make_tmap(&mp->q, a->Q, 0, (uint64_t)a->ldq, qrows, (uint64_t)a->ldq * 2, 64, SQ);
+  if (rc) return rc;
+  for (int m = 0; m < 3; ++m) {
+    const MmsumAttnMod& md = a->mods[m < a->n_mod ? m : 0];
+    const uint64_t rows = (uint64_t)md.kv_row_base + (uint64_t)n_biz * md.E * md.Sk;
+    rc = make_tmap(&mp->kv[m], a->KV, 0, (uint64_t)a->ldkv, rows, (uint64_t)a->ldkv * 2, 64, (uint32_t)md.Sk);
+    if (rc) return rc;
+  }
+  if (bwd) {
+    uint64_t orows = 0;
+    for (int m = 0; m < a->n_mod; ++m) {
+      const uint64_t r = (uint64_t)(a->mods[m].o_off / a->ldo) + qrows;
+      if (r > orows) orows = r;
+    }
+    rc = make_tmap(&mp->d_o, a->O, 0, (uint64_t)a->ldo, orows, (uint64_t)a->ldo * 2, 64, SQ);
+    if (rc) return rc;
+  } else {
+    mp->d_o = mp->q;
+  }
+  return 0;
+}
+
+}  // namespace mmsum
+
+using namespace mmsum;
+
+extern "C" int mmsum_attn_fwd(const MmsumAttnArgs* a, void* stream_v) {
+  if (int rc = validate_tc(a, false)) return rc;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  AttnMaps mp;
+  if (int rc = build_maps(a, &mp, false)) return rc;
+  const int smem = (int)sizeof(FwdSmem) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  attn_fwd_tc_kernel<<<a->n_qseq * a->H, 192, smem, stream>>>(mp, *a);
+  MMSUM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
+  if (int rc = validate_tc(a, true)) return rc;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  AttnMaps mp;
+  if (int rc = build_maps(a, &mp, true)) return rc;
+  const int n_biz = a->n_qseq / a->R;
+  uint64_t kvrows = 0;
+  int tiles = 0;
+  for (int m = 0; m < a->n_mod; ++m) {
+    const uint64_t r = (uint64_t)a->mods[m].kv_row_base + (uint64_t)n_biz * a->mods[m].E * a->mods[m].Sk;
+    if (r > kvrows) kvrows = r;
+    tiles += a->mods[m].E * ((a->mods[m].Sk + SQ - 1) / SQ);
+  }
+  CUtensorMap kv128;
+  if (int rc = make_tmap(&kv128, a->KV, 0, (uint64_t)a->ldkv, kvrows, (uint64_t)a->ldkv * 2, 64, SQ)) return rc;
+  const int smem_q = (int)sizeof(BwdQSmem) + 1024, smem_kv = (int)sizeof(BwdKVSmem) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  attn_bwd_dq_tc_kernel<<<a->n_qseq * a->H, 192, smem_q, stream>>>(mp, *a);
+  MMSUM_CHECK_LAUNCH();
+  attn_bwd_dkv_tc_kernel<<<n_biz * a->H * tiles, 192, smem_kv, stream>>>(mp, kv128, *a, tiles);
+  MMSUM_CHECK_LAUNCH();
+  return 0;
+}

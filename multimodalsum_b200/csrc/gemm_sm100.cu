@@ -332,7 +332,7 @@ struct TmKeyHash {
 static std::unordered_map<TmKey, CUtensorMap, TmKeyHash> g_tm_cache;
 
 // 2D row-major tensor [outer, inner] with row pitch ld_bytes; box = [box_outer, box_inner]; 128B swizzle.
-static int make_tmap(CUtensorMap* out, const void* ptr, int dtype /*0 bf16, 1 f32*/, uint64_t inner, uint64_t outer,
+int make_tmap(CUtensorMap* out, const void* ptr, int dtype /*0 bf16, 1 f32*/, uint64_t inner, uint64_t outer,
                      uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer) {
   TmKey key;
   memset(&key, 0, sizeof(key));
