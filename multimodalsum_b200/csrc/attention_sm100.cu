@@ -200,14 +200,12 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       for (int i = 0; i < HD; ++i) acc[i] = 0.f;
     };
     auto add_o = [&](float wgt) {
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(tmem + lane_off + kColO, r0);
+      tmem_ld_32x32(tmem + lane_off + kColO + 32, r1);
+      tmem_ld_wait();
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem + lane_off + kColO + half * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[half * 32 + i] += wgt * __uint_as_float(r[i]);
-      }
+      for (int i = 0; i < 32; ++i) { acc[i] += wgt * __uint_as_float(r0[i]); acc[32 + i] += wgt * __uint_as_float(r1[i]); }
     };
     int cur_mod = 0;
     float w_prev = 0.f;
@@ -221,17 +219,33 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       const int nchunk = (it.n16 + 31) >> 5;
       mbar_wait(&sm.s_full[st], (i >> 1) & 1);
       tc_fence_after();
-      // pass 1: row max over the valid keys
-      float mx = -INFINITY;
-      for (int c = 0; c < nchunk; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(scol + c * 32, r);
-        tmem_ld_wait();
+      // pass 1: row max over the valid keys (4 independent chains; the next chunk's TMEM load is in flight meanwhile)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      auto chunk_mask = [&](int c) {
         uint32_t wd = words[c];
         if (p.causal) { const int lim = row - c * 32; wd &= (lim >= 31) ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u)); }
+        return wd;
+      };
+      auto max_chunk = [&](const uint32_t (&r)[32], int c) {
+        const uint32_t wd = chunk_mask(c);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = ((wd >> j) & 1u) ? fmaxf(mx, __uint_as_float(r[j])) : mx;
+        for (int j = 0; j < 32; ++j) mx4[j & 3] = ((wd >> j) & 1u) ? fmaxf(mx4[j & 3], __uint_as_float(r[j])) : mx4[j & 3];
+      };
+      {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(scol, ra);
+        for (int c = 0; c < nchunk; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nchunk) tmem_ld_32x32(scol + (c + 1) * 32, rb);
+          max_chunk(ra, c);
+          if (c + 1 < nchunk) {
+            tmem_ld_wait();
+            if (c + 2 < nchunk) tmem_ld_32x32(scol + (c + 2) * 32, ra);
+            max_chunk(rb, c + 1);
+          }
+        }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float msc = (mx == -INFINITY) ? 0.f : mx * sc;
       // the previous entity's P V has finished: fold its output in, and its P buffer / O accumulator are free again
       if (i > 0) {
@@ -243,18 +257,14 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
         while (cur_mod < it.mod) { flush(cur_mod); ++cur_mod; }
       }
       // pass 2: P = exp2(s*sc - m) -> bf16 into the swizzled A-operand tile; l = row sum
-      float l = 0.f;
-      for (int c = 0; c < nchunk; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(scol + c * 32, r);
-        tmem_ld_wait();
-        uint32_t wd = words[c];
-        if (p.causal) { const int lim = row - c * 32; wd &= (lim >= 31) ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u)); }
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      auto exp_chunk = [&](const uint32_t (&r)[32], int c) {
+        const uint32_t wd = chunk_mask(c);
         float pv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           pv[j] = ((wd >> j) & 1u) ? ex2(fmaf(__uint_as_float(r[j]), sc, -msc)) : 0.f;
-          l += pv[j];
+          l4[j & 3] += pv[j];
         }
         uint8_t* atom = prow + (c >> 1) * (SQ * 128);
 #pragma unroll
@@ -265,7 +275,22 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
           const int chunk = (c & 1) * 4 + g8;
           *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = u;
         }
+      };
+      {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(scol, ra);
+        for (int c = 0; c < nchunk; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nchunk) tmem_ld_32x32(scol + (c + 1) * 32, rb);
+          exp_chunk(ra, c);
+          if (c + 1 < nchunk) {
+            tmem_ld_wait();
+            if (c + 2 < nchunk) tmem_ld_32x32(scol + (c + 2) * 32, ra);
+            exp_chunk(rb, c + 1);
+          }
+        }
       }
+      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       tc_fence_before();
       mbar_arrive(&sm.s_empty[st]);
       fence_proxy_async_smem();
@@ -413,7 +438,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       mbar_wait(&sm.sdp_full, i & 1);
       tc_fence_after();
       uint32_t pp[7][16];
-      float delta = 0.f;
+      float dl4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 7; ++c) {
         if (c < nchunk) {
@@ -427,12 +452,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           for (int j = 0; j < 32; j += 2) {
             const float p0 = ((wd >> j) & 1u) ? ex2(fmaf(__uint_as_float(rs[j]), sc, -lse)) : 0.f;
             const float p1 = ((wd >> (j + 1)) & 1u) ? ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse)) : 0.f;
-            delta = fmaf(p0, __uint_as_float(rd[j]), delta);
-            delta = fmaf(p1, __uint_as_float(rd[j + 1]), delta);
+            dl4[(j >> 1) & 3] = fmaf(p0, __uint_as_float(rd[j]), dl4[(j >> 1) & 3]);
+            dl4[(j >> 1) & 3] = fmaf(p1, __uint_as_float(rd[j + 1]), dl4[(j >> 1) & 3]);
             pp[c][j >> 1] = pack_bf16(p0, p1);
           }
         }
       }
+      const float delta = (dl4[0] + dl4[1]) + (dl4[2] + dl4[3]);
       p.DELTA[li] = delta;
       if (i > 0) mbar_wait(&sm.ds_free, (i - 1) & 1);   // dQ MMA of the previous entity has consumed the dS tile
       const float wgt = p.scale * inv_n;
@@ -651,12 +677,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
       mbar_wait(&sm.sdp_full, s & 1);
       tc_fence_after();
       if (s > 0) mbar_wait(&sm.pds_free, (s - 1) & 1);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t rs[32], rd[32];
-        tmem_ld_32x32(tmem + lane_off + kColST + c * 32, rs);
-        tmem_ld_32x32(tmem + lane_off + kColDPT + c * 32, rd);
-        tmem_ld_wait();
+      auto proc = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c) {
         uint32_t wd = kvalid ? 0xffffffffu : 0u;
         if (p.causal) {  // key (key0 + row) <= query (c*32 + j)  <=>  j >= key0 + row - c*32
           const int lo = key0 + row - c * 32;
@@ -685,6 +706,24 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
           const int chunk = (c & 1) * 4 + g8;
           *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[0], po[1], po[2], po[3]);
           *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
+        }
+      };
+      {
+        uint32_t sa[32], da_[32], sb[32], db[32];
+        tmem_ld_32x32(tmem + lane_off + kColST, sa);
+        tmem_ld_32x32(tmem + lane_off + kColDPT, da_);
+#pragma unroll 1
+        for (int c = 0; c < 4; c += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32(tmem + lane_off + kColST + (c + 1) * 32, sb);
+          tmem_ld_32x32(tmem + lane_off + kColDPT + (c + 1) * 32, db);
+          proc(sa, da_, c);
+          tmem_ld_wait();
+          if (c + 2 < 4) {
+            tmem_ld_32x32(tmem + lane_off + kColST + (c + 2) * 32, sa);
+            tmem_ld_32x32(tmem + lane_off + kColDPT + (c + 2) * 32, da_);
+          }
+          proc(sb, db, c + 1);
         }
       }
       tc_fence_before();
