@@ -33,13 +33,33 @@ static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr int kKVStageBytes = kMaxKeys * 128;   // 26624 = 26 * 1024
 static constexpr int kPBytes = 4 * SQ * 128;           // four 64-key atoms of [128 rows x 128 B]
 static constexpr uint32_t kColS0 = 0, kColS1 = 224, kColO = 448;
-
 struct EntItem {
   int kv_row0;     // first KV row of the entity
   int nkeys;       // keys of the entity (Sk of its modality)
   int n16;         // nkeys rounded up to 16
   short mod, ent;  // modality, global entity index
 };
+
+// 2 control warps (TMA producer, MMA issuer) + 16 softmax warps: 4 per TMEM lane quarter, each owning every 4th
+// 32-column chunk of the score tile and 16 of the 64 output columns.  One warp per scheduler cannot hide the ALU /
+// MUFU / TMEM latencies of the softmax (measured IPC 0.26); four can.
+static constexpr int kSoftWarps = 16;
+static constexpr int kSoftThreads = kSoftWarps * 32;
+static constexpr int kAttnThreads = 64 + kSoftThreads;
+
+__device__ __forceinline__ void soft_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kSoftThreads) : "memory"); }
+
+// validity word of chunk c (keys 32c .. 32c+31) of an entity, computed by one warp
+__device__ __forceinline__ uint32_t chunk_word(const MmsumAttnArgs& p, const EntItem& it, int c, int lane) {
+  const int j = c * 32 + lane;
+  bool ok = j < it.nkeys;
+  if (ok && p.key_valid != nullptr) ok = p.key_valid[(long long)it.kv_row0 + j] != 0;
+  return __ballot_sync(0xffffffffu, ok);
+}
+__device__ __forceinline__ uint32_t causal_word(uint32_t wd, int row, int c) {
+  const int lim = row - c * 32;   // keys 32c + j <= row
+  return wd & ((lim >= 31) ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u)));
+}
 
 struct AttnMaps {
   CUtensorMap q;       // Q rows, box {64, 128}
@@ -90,13 +110,15 @@ struct FwdSmem {
   uint8_t k[2][kKVStageBytes];
   uint8_t v[2][kKVStageBytes];
   uint8_t p[kPBytes];
+  float red_max[2][4][SQ];
+  float red_sum[2][4][SQ];
   EntItem items[kMaxEnt];
   uint64_t q_full, kv_full[2], kv_empty[2], s_full[2], s_empty[2], p_full, mma2_done;
   uint32_t tmem_slot;
   int n_items;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -112,9 +134,9 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
     mbar_init(&sm.q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sm.kv_full[s], 1); mbar_init(&sm.kv_empty[s], 1);
-      mbar_init(&sm.s_full[s], 1); mbar_init(&sm.s_empty[s], 128);
+      mbar_init(&sm.s_full[s], 1); mbar_init(&sm.s_empty[s], kSoftThreads);
     }
-    mbar_init(&sm.p_full, 128);
+    mbar_init(&sm.p_full, kSoftThreads);
     mbar_init(&sm.mma2_done, 1);
     fence_barrier_init();
     tma_prefetch_desc(&maps.q);
@@ -178,128 +200,135 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       }
     }
   } else {
-    // ===================== softmax / accumulate warps: thread = query row =====================
+    // ===================== softmax / accumulate warps =====================
+    // thread = (query row, column group cg): score chunks cg and cg+4, output columns [16cg, 16cg+16)
     const int q4 = warp & 3;
+    const int cg = (warp - 2) >> 2;
     const int row = q4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float sc = p.scale * kLog2e;
-    float acc[HD];
+    float acc[16];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
     bf16* Og = reinterpret_cast<bf16*>(p.O);
     auto flush = [&](int m) {
-      bf16* dst = Og + p.mods[m].o_off + (long long)(qrow0 + row) * p.ldo + h * HD;
+      bf16* dst = Og + p.mods[m].o_off + (long long)(qrow0 + row) * p.ldo + h * HD + cg * 16;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 2; ++j) {
         uint4 u;
         u.x = pack_bf16(acc[j * 8 + 0], acc[j * 8 + 1]); u.y = pack_bf16(acc[j * 8 + 2], acc[j * 8 + 3]);
         u.z = pack_bf16(acc[j * 8 + 4], acc[j * 8 + 5]); u.w = pack_bf16(acc[j * 8 + 6], acc[j * 8 + 7]);
         *reinterpret_cast<uint4*>(dst + j * 8) = u;
       }
 #pragma unroll
-      for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
     };
     auto add_o = [&](float wgt) {
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(tmem + lane_off + kColO, r0);
-      tmem_ld_32x32(tmem + lane_off + kColO + 32, r1);
+      uint32_t r[16];
+      tmem_ld_32x16(tmem + lane_off + kColO + cg * 16, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { acc[i] += wgt * __uint_as_float(r0[i]); acc[32 + i] += wgt * __uint_as_float(r1[i]); }
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(wgt, __uint_as_float(r[i]), acc[i]);
+    };
+    // finish the bookkeeping of the previous entity once all four column groups have published their partial sums
+    float msc_prev = 0.f, invn_prev = 0.f;
+    int ent_prev = 0;
+    auto close_prev = [&](int par_prev) {
+      const float l = (sm.red_sum[par_prev][0][row] + sm.red_sum[par_prev][1][row]) +
+                      (sm.red_sum[par_prev][2][row] + sm.red_sum[par_prev][3][row]);
+      if (cg == 0)
+        p.LSE[(((long long)qseq * p.H + h) * p.E_total + ent_prev) * SQ + row] = (l > 0.f) ? (msc_prev + log2f(l)) : INFINITY;
+      return (l > 0.f) ? invn_prev / l : 0.f;
     };
     int cur_mod = 0;
-    float w_prev = 0.f;
-    uint8_t* prow = sm.p + row * 128;
     for (int i = 0; i < n_items; ++i) {
       const EntItem it = sm.items[i];
-      const int st = i & 1;
-      uint32_t words[7];
-      key_bitmask(p, it, lane, words);
-      const uint32_t scol = tmem + lane_off + (st ? kColS1 : kColS0);
+      const int st = i & 1, par = i & 1;
       const int nchunk = (it.n16 + 31) >> 5;
+      const bool has0 = cg < nchunk, has1 = cg + 4 < nchunk;
+      uint32_t w0 = has0 ? chunk_word(p, it, cg, lane) : 0u;
+      uint32_t w1 = has1 ? chunk_word(p, it, cg + 4, lane) : 0u;
+      if (p.causal) { w0 = causal_word(w0, row, cg); w1 = causal_word(w1, row, cg + 4); }
+      const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
+      const uint32_t scol = tmem + lane_off + (st ? kColS1 : kColS0);
       mbar_wait(&sm.s_full[st], (i >> 1) & 1);
       tc_fence_after();
-      // pass 1: row max over the valid keys (4 independent chains; the next chunk's TMEM load is in flight meanwhile)
+      // max pass (one 32-column chunk in registers at a time; 4 softmax warps per scheduler hide the TMEM latency)
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      auto chunk_mask = [&](int c) {
-        uint32_t wd = words[c];
-        if (p.causal) { const int lim = row - c * 32; wd &= (lim >= 31) ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u)); }
-        return wd;
-      };
-      auto max_chunk = [&](const uint32_t (&r)[32], int c) {
-        const uint32_t wd = chunk_mask(c);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx4[j & 3] = ((wd >> j) & 1u) ? fmaxf(mx4[j & 3], __uint_as_float(r[j])) : mx4[j & 3];
-      };
-      {
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(scol, ra);
-        for (int c = 0; c < nchunk; c += 2) {
+      for (int t = 0; t < 2; ++t) {
+        const bool has = t == 0 ? has0 : has1;
+        const uint32_t wd = t == 0 ? w0 : w1;
+        if (has) {
+          uint32_t r[32];
+          tmem_ld_32x32(scol + (cg + 4 * t) * 32, r);
           tmem_ld_wait();
-          if (c + 1 < nchunk) tmem_ld_32x32(scol + (c + 1) * 32, rb);
-          max_chunk(ra, c);
-          if (c + 1 < nchunk) {
-            tmem_ld_wait();
-            if (c + 2 < nchunk) tmem_ld_32x32(scol + (c + 2) * 32, ra);
-            max_chunk(rb, c + 1);
+          if (wd == 0xffffffffu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(r[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx4[j & 3] = ((wd >> j) & 1u) ? fmaxf(mx4[j & 3], __uint_as_float(r[j])) : mx4[j & 3];
           }
         }
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      sm.red_max[par][cg][row] = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      soft_bar();
+      const float mx = fmaxf(fmaxf(sm.red_max[par][0][row], sm.red_max[par][1][row]),
+                             fmaxf(sm.red_max[par][2][row], sm.red_max[par][3][row]));
       const float msc = (mx == -INFINITY) ? 0.f : mx * sc;
-      // the previous entity's P V has finished: fold its output in, and its P buffer / O accumulator are free again
+      // the previous entity's P V has finished: fold its output in; its P buffer / O accumulator are free again
       if (i > 0) {
+        const float w_prev = close_prev(par ^ 1);
         mbar_wait(&sm.mma2_done, (i - 1) & 1);
         tc_fence_after();
         add_o(w_prev);
-        if (it.mod != cur_mod) { while (cur_mod < it.mod) { flush(cur_mod); ++cur_mod; } }
-      } else {
-        while (cur_mod < it.mod) { flush(cur_mod); ++cur_mod; }
       }
-      // pass 2: P = exp2(s*sc - m) -> bf16 into the swizzled A-operand tile; l = row sum
+      while (cur_mod < it.mod) { flush(cur_mod); ++cur_mod; }
+      // exp pass: P = exp2(s*sc - m) -> bf16 into the swizzled A-operand tile; partial row sum
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
-      auto exp_chunk = [&](const uint32_t (&r)[32], int c) {
-        const uint32_t wd = chunk_mask(c);
-        float pv[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          pv[j] = ((wd >> j) & 1u) ? ex2(fmaf(__uint_as_float(r[j]), sc, -msc)) : 0.f;
-          l4[j & 3] += pv[j];
-        }
-        uint8_t* atom = prow + (c >> 1) * (SQ * 128);
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          uint4 u;
-          u.x = pack_bf16(pv[g8 * 8 + 0], pv[g8 * 8 + 1]); u.y = pack_bf16(pv[g8 * 8 + 2], pv[g8 * 8 + 3]);
-          u.z = pack_bf16(pv[g8 * 8 + 4], pv[g8 * 8 + 5]); u.w = pack_bf16(pv[g8 * 8 + 6], pv[g8 * 8 + 7]);
-          const int chunk = (c & 1) * 4 + g8;
-          *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = u;
-        }
-      };
-      {
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(scol, ra);
-        for (int c = 0; c < nchunk; c += 2) {
+      for (int t = 0; t < 2; ++t) {
+        const bool has = t == 0 ? has0 : has1;
+        const uint32_t wd = t == 0 ? w0 : w1;
+        if (has) {
+          const int c = cg + 4 * t;
+          uint32_t r[32];
+          tmem_ld_32x32(scol + c * 32, r);
           tmem_ld_wait();
-          if (c + 1 < nchunk) tmem_ld_32x32(scol + (c + 1) * 32, rb);
-          exp_chunk(ra, c);
-          if (c + 1 < nchunk) {
-            tmem_ld_wait();
-            if (c + 2 < nchunk) tmem_ld_32x32(scol + (c + 2) * 32, ra);
-            exp_chunk(rb, c + 1);
+          if (wd == 0xffffffffu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float e = ex2(fmaf(__uint_as_float(r[j]), sc, -msc)); l4[j & 3] += e; r[j] = __float_as_uint(e); }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float e = ((wd >> j) & 1u) ? ex2(fmaf(__uint_as_float(r[j]), sc, -msc)) : 0.f;
+              l4[j & 3] += e; r[j] = __float_as_uint(e);
+            }
+          }
+          uint8_t* atom = sm.p + row * 128 + (c >> 1) * (SQ * 128);
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(r[g8 * 8 + 0]), __uint_as_float(r[g8 * 8 + 1]));
+            u.y = pack_bf16(__uint_as_float(r[g8 * 8 + 2]), __uint_as_float(r[g8 * 8 + 3]));
+            u.z = pack_bf16(__uint_as_float(r[g8 * 8 + 4]), __uint_as_float(r[g8 * 8 + 5]));
+            u.w = pack_bf16(__uint_as_float(r[g8 * 8 + 6]), __uint_as_float(r[g8 * 8 + 7]));
+            const int chunk = (c & 1) * 4 + g8;
+            *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = u;
           }
         }
       }
-      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      sm.red_sum[par][cg][row] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       tc_fence_before();
       mbar_arrive(&sm.s_empty[st]);
       fence_proxy_async_smem();
       mbar_arrive(&sm.p_full);
-      const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
-      w_prev = (l > 0.f) ? inv_n / l : 0.f;
-      p.LSE[(((long long)qseq * p.H + h) * p.E_total + it.ent) * SQ + row] = (l > 0.f) ? (msc + log2f(l)) : INFINITY;
+      msc_prev = msc; invn_prev = inv_n; ent_prev = it.ent;
     }
     if (n_items > 0) {
+      soft_bar();                                   // partial sums of the last entity are visible
+      const float w_prev = close_prev((n_items - 1) & 1);
       mbar_wait(&sm.mma2_done, (n_items - 1) & 1);
       tc_fence_after();
       add_o(w_prev);
@@ -324,13 +353,14 @@ struct BwdQSmem {
   uint8_t k[2][kKVStageBytes];
   uint8_t v[2][kKVStageBytes];
   uint8_t ds[kPBytes];
+  float red_delta[2][4][SQ];
   EntItem items[kMaxEnt];
   uint64_t q_full, da_full, da_free, kv_full[2], kv_empty[2], sdp_full, sdp_empty, ds_full, ds_free;
   uint32_t tmem_slot;
   int n_items;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
   BwdQSmem& sm = *reinterpret_cast<BwdQSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -345,8 +375,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
     sm.n_items = build_ent_items(p, qseq, sm.items);
     mbar_init(&sm.q_full, 1); mbar_init(&sm.da_full, 1); mbar_init(&sm.da_free, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&sm.kv_full[s], 1); mbar_init(&sm.kv_empty[s], 1); }
-    mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, 128);
-    mbar_init(&sm.ds_full, 128); mbar_init(&sm.ds_free, 1);
+    mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, kSoftThreads);
+    mbar_init(&sm.ds_full, kSoftThreads); mbar_init(&sm.ds_free, 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < 4 * kKVStageBytes / 16; i += blockDim.x)   // K and V stages: finite contents only
@@ -422,59 +452,69 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       }
     }
   } else {
+    // thread = (query row, column group cg): score chunks cg and cg+4, dQ columns [16cg, 16cg+16)
     const int q4 = warp & 3;
+    const int cg = (warp - 2) >> 2;
     const int row = q4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float sc = p.scale * kLog2e;
-    uint8_t* dsrow = sm.ds + row * 128;
     for (int i = 0; i < n_items; ++i) {
       const EntItem it = sm.items[i];
-      uint32_t words[7];
-      key_bitmask(p, it, lane, words);
+      const int par = i & 1;
       const int nchunk = (it.n16 + 31) >> 5;
+      const bool has[2] = {cg < nchunk, cg + 4 < nchunk};
+      uint32_t wd[2];
+      wd[0] = has[0] ? chunk_word(p, it, cg, lane) : 0u;
+      wd[1] = has[1] ? chunk_word(p, it, cg + 4, lane) : 0u;
+      if (p.causal) { wd[0] = causal_word(wd[0], row, cg); wd[1] = causal_word(wd[1], row, cg + 4); }
       const long long li = (((long long)qseq * p.H + h) * p.E_total + it.ent) * SQ + row;
       const float lse = p.LSE[li];
       const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
       mbar_wait(&sm.sdp_full, i & 1);
       tc_fence_after();
-      uint32_t pp[7][16];
+      // pass 1: P = exp2(sc*S - LSE) (stashed as packed bf16), partial delta' = sum P o dP'
+      uint32_t pp[2][16];
       float dl4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 7; ++c) {
-        if (c < nchunk) {
+      for (int t = 0; t < 2; ++t) {
+        if (has[t]) {
+          const int c = cg + 4 * t;
           uint32_t rs[32], rd[32];
           tmem_ld_32x32(tmem + lane_off + kColS0 + c * 32, rs);
           tmem_ld_32x32(tmem + lane_off + kColDP + c * 32, rd);
           tmem_ld_wait();
-          uint32_t wd = words[c];
-          if (p.causal) { const int lim = row - c * 32; wd &= (lim >= 31) ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u)); }
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const float p0 = ((wd >> j) & 1u) ? ex2(fmaf(__uint_as_float(rs[j]), sc, -lse)) : 0.f;
-            const float p1 = ((wd >> (j + 1)) & 1u) ? ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse)) : 0.f;
+            const float p0 = ((wd[t] >> j) & 1u) ? ex2(fmaf(__uint_as_float(rs[j]), sc, -lse)) : 0.f;
+            const float p1 = ((wd[t] >> (j + 1)) & 1u) ? ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse)) : 0.f;
             dl4[(j >> 1) & 3] = fmaf(p0, __uint_as_float(rd[j]), dl4[(j >> 1) & 3]);
             dl4[(j >> 1) & 3] = fmaf(p1, __uint_as_float(rd[j + 1]), dl4[(j >> 1) & 3]);
-            pp[c][j >> 1] = pack_bf16(p0, p1);
+            pp[t][j >> 1] = pack_bf16(p0, p1);
           }
         }
       }
-      const float delta = (dl4[0] + dl4[1]) + (dl4[2] + dl4[3]);
-      p.DELTA[li] = delta;
+      sm.red_delta[par][cg][row] = (dl4[0] + dl4[1]) + (dl4[2] + dl4[3]);
+      soft_bar();
+      const float delta = (sm.red_delta[par][0][row] + sm.red_delta[par][1][row]) +
+                          (sm.red_delta[par][2][row] + sm.red_delta[par][3][row]);
+      if (cg == 0) p.DELTA[li] = delta;
       if (i > 0) mbar_wait(&sm.ds_free, (i - 1) & 1);   // dQ MMA of the previous entity has consumed the dS tile
+      // pass 2: dS = scale*inv_n * P o (dP' - delta') -> bf16 A-operand tile
       const float wgt = p.scale * inv_n;
 #pragma unroll
-      for (int c = 0; c < 7; ++c) {
-        if (c < nchunk) {
+      for (int t = 0; t < 2; ++t) {
+        if (has[t]) {
+          const int c = cg + 4 * t;
           uint32_t rd[32];
           tmem_ld_32x32(tmem + lane_off + kColDP + c * 32, rd);
           tmem_ld_wait();
-          uint8_t* atom = dsrow + (c >> 1) * (SQ * 128);
+          uint8_t* atom = sm.ds + row * 128 + (c >> 1) * (SQ * 128);
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 pr = unpack_bf16(pp[c][g8 * 4 + e]);
+              const float2 pr = unpack_bf16(pp[t][g8 * 4 + e]);
               const int j = g8 * 8 + 2 * e;
               o[e] = pack_bf16(wgt * pr.x * (__uint_as_float(rd[j]) - delta), wgt * pr.y * (__uint_as_float(rd[j + 1]) - delta));
             }
@@ -489,28 +529,25 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       mbar_arrive(&sm.ds_full);
     }
     // dQ: read the accumulator once every entity has been folded in
-    bf16* dQg = reinterpret_cast<bf16*>(p.dQ) + (long long)(qrow0 + row) * p.lddq + p.dq_col + h * HD;
+    bf16* dQg = reinterpret_cast<bf16*>(p.dQ) + (long long)(qrow0 + row) * p.lddq + p.dq_col + h * HD + cg * 16;
     if (n_items > 0) {
       mbar_wait(&sm.ds_free, (n_items - 1) & 1);
       tc_fence_after();
+      uint32_t r[16];
+      tmem_ld_32x16(tmem + lane_off + kColDQ + cg * 16, r);
+      tmem_ld_wait();
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem + lane_off + kColDQ + half * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
-          u.y = pack_bf16(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
-          u.z = pack_bf16(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
-          u.w = pack_bf16(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
-          *reinterpret_cast<uint4*>(dQg + half * 32 + j * 8) = u;
-        }
+      for (int j = 0; j < 2; ++j) {
+        uint4 u;
+        u.x = pack_bf16(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
+        u.y = pack_bf16(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
+        u.z = pack_bf16(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
+        u.w = pack_bf16(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
+        *reinterpret_cast<uint4*>(dQg + j * 8) = u;
       }
     } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(dQg + j * 8) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(dQg) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(dQg + 8) = make_uint4(0, 0, 0, 0);
     }
   }
   tc_fence_before();
@@ -538,7 +575,7 @@ struct BwdKVSmem {
 };
 static constexpr uint32_t kColST = 0, kColDPT = 128, kColDK = 256, kColDV = 320;
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ CUtensorMap kv128,
                        const MmsumAttnArgs p, int tiles_per_bh) {
   extern __shared__ uint8_t smem_raw[];
@@ -569,11 +606,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
     // null entity: its gradient is exactly zero (the buffer is never memset)
     if (warp >= 2) {
       const int row = (warp & 3) * 32 + lane;
+      const int cg = (warp - 2) >> 2;
       if (row < nkeys) {
-        bf16* dk = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dk_col + h * HD;
-        bf16* dv = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dv_col + h * HD;
+        bf16* dk = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dk_col + h * HD + cg * 16;
+        bf16* dv = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dv_col + h * HD + cg * 16;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 2; ++j) {
           *reinterpret_cast<uint4*>(dk + j * 8) = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(dv + j * 8) = make_uint4(0, 0, 0, 0);
         }
@@ -585,8 +623,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
   if (threadIdx.x == 0) {
     mbar_init(&sm.kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&sm.qd_full[s], 1); mbar_init(&sm.qd_empty[s], 1); }
-    mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, 128);
-    mbar_init(&sm.pds_full, 128); mbar_init(&sm.pds_free, 1);
+    mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, kSoftThreads);
+    mbar_init(&sm.pds_full, kSoftThreads); mbar_init(&sm.pds_free, 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(&sm.tmem_slot, 512); tmem_relinquish(); }
@@ -656,75 +694,59 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
       }
     }
   } else {
+    // thread = (key row, column group cg): query chunk cg (32 of the 128 queries), dK / dV columns [16cg, 16cg+16)
     const int q4 = warp & 3;
+    const int sw = warp - 2;
+    const int cg = sw >> 2;
     const int row = q4 * 32 + lane;            // key within the tile
-    const int et = warp - 2;                   // 0..3: index among the softmax warps
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float sc = p.scale * kLog2e;
     const bool kvalid = (row < nkeys) && (p.key_valid == nullptr || p.key_valid[(long long)kvrow0 + row] != 0);
-    uint8_t* ptrow = sm.pt + row * 128;
-    uint8_t* dsrow = sm.dst + row * 128;
+    uint32_t wd = kvalid ? 0xffffffffu : 0u;
+    if (p.causal) {  // key (key0 + row) <= query (cg*32 + j)  <=>  j >= key0 + row - cg*32
+      const int lo = key0 + row - cg * 32;
+      wd &= (lo <= 0) ? 0xffffffffu : (lo >= 32 ? 0u : ~((1u << lo) - 1u));
+    }
+    uint8_t* patom = sm.pt + row * 128 + (cg >> 1) * (SQ * 128);
+    uint8_t* datom = sm.dst + row * 128 + (cg >> 1) * (SQ * 128);
     for (int s = 0; s < n_steps; ++s) {
       const int st = s & 1;
       const int qseq = biz * p.R + step_target(s);
       const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + m] : 1.f;
-      {  // stage LSE / DELTA of this target's 128 query rows (one value per softmax thread)
-        const long long li = (((long long)qseq * p.H + h) * p.E_total + ge) * SQ + (et * 32 + lane);
-        sm.lse[st][et * 32 + lane] = p.LSE[li];
-        sm.dlt[st][et * 32 + lane] = p.DELTA[li];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (sw < 4) {  // stage LSE / DELTA of this target's 128 query rows
+        const long long li = (((long long)qseq * p.H + h) * p.E_total + ge) * SQ + (sw * 32 + lane);
+        sm.lse[st][sw * 32 + lane] = p.LSE[li];
+        sm.dlt[st][sw * 32 + lane] = p.DELTA[li];
       }
+      soft_bar();
       mbar_wait(&sm.sdp_full, s & 1);
       tc_fence_after();
+      uint32_t rs[32], rd[32];
+      tmem_ld_32x32(tmem + lane_off + kColST + cg * 32, rs);
+      tmem_ld_32x32(tmem + lane_off + kColDPT + cg * 32, rd);
+      tmem_ld_wait();
       if (s > 0) mbar_wait(&sm.pds_free, (s - 1) & 1);
-      auto proc = [&](const uint32_t (&rs)[32], const uint32_t (&rd)[32], int c) {
-        uint32_t wd = kvalid ? 0xffffffffu : 0u;
-        if (p.causal) {  // key (key0 + row) <= query (c*32 + j)  <=>  j >= key0 + row - c*32
-          const int lo = key0 + row - c * 32;
-          wd &= (lo <= 0) ? 0xffffffffu : (lo >= 32 ? 0u : ~((1u << lo) - 1u));
-        }
-        uint8_t* patom = ptrow + (c >> 1) * (SQ * 128);
-        uint8_t* datom = dsrow + (c >> 1) * (SQ * 128);
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          uint32_t po[4], dso[4];
-          const float4 l0 = *reinterpret_cast<const float4*>(&sm.lse[st][c * 32 + g8 * 8]);
-          const float4 l1 = *reinterpret_cast<const float4*>(&sm.lse[st][c * 32 + g8 * 8 + 4]);
-          const float4 d0 = *reinterpret_cast<const float4*>(&sm.dlt[st][c * 32 + g8 * 8]);
-          const float4 d1 = *reinterpret_cast<const float4*>(&sm.dlt[st][c * 32 + g8 * 8 + 4]);
-          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-          const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      for (int g8 = 0; g8 < 4; ++g8) {
+        uint32_t po[4], dso[4];
+        const float4 l0 = *reinterpret_cast<const float4*>(&sm.lse[st][cg * 32 + g8 * 8]);
+        const float4 l1 = *reinterpret_cast<const float4*>(&sm.lse[st][cg * 32 + g8 * 8 + 4]);
+        const float4 d0 = *reinterpret_cast<const float4*>(&sm.dlt[st][cg * 32 + g8 * 8]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&sm.dlt[st][cg * 32 + g8 * 8 + 4]);
+        const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-          for (int e2 = 0; e2 < 4; ++e2) {
-            const int j = g8 * 8 + 2 * e2;
-            const float p0 = ((wd >> j) & 1u) ? inv_n * ex2(fmaf(__uint_as_float(rs[j]), sc, -ls[2 * e2])) : 0.f;
-            const float p1 = ((wd >> (j + 1)) & 1u) ? inv_n * ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -ls[2 * e2 + 1])) : 0.f;
-            po[e2] = pack_bf16(p0, p1);
-            dso[e2] = pack_bf16(p.scale * p0 * (__uint_as_float(rd[j]) - dl[2 * e2]),
-                                p.scale * p1 * (__uint_as_float(rd[j + 1]) - dl[2 * e2 + 1]));
-          }
-          const int chunk = (c & 1) * 4 + g8;
-          *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[0], po[1], po[2], po[3]);
-          *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const int j = g8 * 8 + 2 * e2;
+          const float p0 = ((wd >> j) & 1u) ? inv_n * ex2(fmaf(__uint_as_float(rs[j]), sc, -ls[2 * e2])) : 0.f;
+          const float p1 = ((wd >> (j + 1)) & 1u) ? inv_n * ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -ls[2 * e2 + 1])) : 0.f;
+          po[e2] = pack_bf16(p0, p1);
+          dso[e2] = pack_bf16(p.scale * p0 * (__uint_as_float(rd[j]) - dl[2 * e2]),
+                              p.scale * p1 * (__uint_as_float(rd[j + 1]) - dl[2 * e2 + 1]));
         }
-      };
-      {
-        uint32_t sa[32], da_[32], sb[32], db[32];
-        tmem_ld_32x32(tmem + lane_off + kColST, sa);
-        tmem_ld_32x32(tmem + lane_off + kColDPT, da_);
-#pragma unroll 1
-        for (int c = 0; c < 4; c += 2) {
-          tmem_ld_wait();
-          tmem_ld_32x32(tmem + lane_off + kColST + (c + 1) * 32, sb);
-          tmem_ld_32x32(tmem + lane_off + kColDPT + (c + 1) * 32, db);
-          proc(sa, da_, c);
-          tmem_ld_wait();
-          if (c + 2 < 4) {
-            tmem_ld_32x32(tmem + lane_off + kColST + (c + 2) * 32, sa);
-            tmem_ld_32x32(tmem + lane_off + kColDPT + (c + 2) * 32, da_);
-          }
-          proc(sb, db, c + 1);
-        }
+        const int chunk = (cg & 1) * 4 + g8;
+        *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[0], po[1], po[2], po[3]);
+        *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
       }
       tc_fence_before();
       mbar_arrive(&sm.sdp_empty);
@@ -736,27 +758,26 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
     {
       // every lane issues the (.sync.aligned) TMEM loads; only lanes that own a key store
       const int srow = row < nkeys ? row : 0;
-      bf16* dk = dKV + (long long)(kvrow0 + srow) * p.lddkv + p.dk_col + h * HD;
-      bf16* dv = dKV + (long long)(kvrow0 + srow) * p.lddkv + p.dv_col + h * HD;
+      bf16* dk = dKV + (long long)(kvrow0 + srow) * p.lddkv + p.dk_col + h * HD + cg * 16;
+      bf16* dv = dKV + (long long)(kvrow0 + srow) * p.lddkv + p.dv_col + h * HD + cg * 16;
+      uint32_t rk[16], rv[16];
+      tmem_ld_32x16(tmem + lane_off + kColDK + cg * 16, rk);
+      tmem_ld_32x16(tmem + lane_off + kColDV + cg * 16, rv);
+      tmem_ld_wait();
+      if (row < nkeys) {
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        bf16* dst = which == 0 ? dk : dv;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem + lane_off + (which == 0 ? kColDK : kColDV) + half * 32, r);
-          tmem_ld_wait();
-          if (row < nkeys) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = pack_bf16(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
-              u.y = pack_bf16(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
-              u.z = pack_bf16(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
-              u.w = pack_bf16(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
-              *reinterpret_cast<uint4*>(dst + half * 32 + j * 8) = u;
-            }
-          }
+        for (int j = 0; j < 2; ++j) {
+          uint4 u, w2;
+          u.x = pack_bf16(__uint_as_float(rk[j * 8 + 0]), __uint_as_float(rk[j * 8 + 1]));
+          u.y = pack_bf16(__uint_as_float(rk[j * 8 + 2]), __uint_as_float(rk[j * 8 + 3]));
+          u.z = pack_bf16(__uint_as_float(rk[j * 8 + 4]), __uint_as_float(rk[j * 8 + 5]));
+          u.w = pack_bf16(__uint_as_float(rk[j * 8 + 6]), __uint_as_float(rk[j * 8 + 7]));
+          w2.x = pack_bf16(__uint_as_float(rv[j * 8 + 0]), __uint_as_float(rv[j * 8 + 1]));
+          w2.y = pack_bf16(__uint_as_float(rv[j * 8 + 2]), __uint_as_float(rv[j * 8 + 3]));
+          w2.z = pack_bf16(__uint_as_float(rv[j * 8 + 4]), __uint_as_float(rv[j * 8 + 5]));
+          w2.w = pack_bf16(__uint_as_float(rv[j * 8 + 6]), __uint_as_float(rv[j * 8 + 7]));
+          *reinterpret_cast<uint4*>(dk + j * 8) = u;
+          *reinterpret_cast<uint4*>(dv + j * 8) = w2;
         }
       }
     }
@@ -827,7 +848,7 @@ extern "C" int mmsum_attn_fwd(const MmsumAttnArgs* a, void* stream_v) {
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  attn_fwd_tc_kernel<<<a->n_qseq * a->H, 192, smem, stream>>>(mp, *a);
+  attn_fwd_tc_kernel<<<a->n_qseq * a->H, kAttnThreads, smem, stream>>>(mp, *a);
   MMSUM_CHECK_LAUNCH();
   return 0;
 }
@@ -856,9 +877,9 @@ extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  attn_bwd_dq_tc_kernel<<<a->n_qseq * a->H, 192, smem_q, stream>>>(mp, *a);
+  attn_bwd_dq_tc_kernel<<<a->n_qseq * a->H, kAttnThreads, smem_q, stream>>>(mp, *a);
   MMSUM_CHECK_LAUNCH();
-  attn_bwd_dkv_tc_kernel<<<n_biz * a->H * tiles, 192, smem_kv, stream>>>(mp, kv128, *a, tiles);
+  attn_bwd_dkv_tc_kernel<<<n_biz * a->H * tiles, kAttnThreads, smem_kv, stream>>>(mp, kv128, *a, tiles);
   MMSUM_CHECK_LAUNCH();
   return 0;
 }
