@@ -56,6 +56,17 @@ __device__ __forceinline__ uint32_t chunk_word(const MmsumAttnArgs& p, const Ent
   if (ok && p.key_valid != nullptr) ok = p.key_valid[(long long)it.kv_row0 + j] != 0;
   return __ballot_sync(0xffffffffu, ok);
 }
+// all (entity, chunk) validity words of the CTA, computed up front by the softmax warps (one global-load latency
+// for the whole CTA instead of one per entity on the critical path)
+__device__ __forceinline__ void build_masks(const MmsumAttnArgs& p, const EntItem* items, int n_items, uint32_t (*kmask)[8],
+                                            int sw, int lane) {
+  for (int idx = sw; idx < n_items * 7; idx += kSoftWarps) {
+    const int i = idx / 7, c = idx - i * 7;
+    const uint32_t w = chunk_word(p, items[i], c, lane);
+    if (lane == 0) kmask[i][c] = w;
+  }
+  soft_bar();
+}
 __device__ __forceinline__ uint32_t causal_word(uint32_t wd, int row, int c) {
   const int lim = row - c * 32;   // keys 32c + j <= row
   return wd & ((lim >= 31) ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u)));
@@ -73,25 +84,31 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__device__ int build_ent_items(const MmsumAttnArgs& p, int qseq, EntItem* items) {
+// Enumerate the valid entities of one query sequence (executed by one full warp: lane = candidate entity).
+__device__ int build_ent_items(const MmsumAttnArgs& p, int qseq, EntItem* items, int lane) {
   const int biz = qseq / p.R;
   const int tgt = qseq - biz * p.R;
-  int n = 0;
-  for (int m = 0; m < p.n_mod; ++m) {
-    const MmsumAttnMod& md = p.mods[m];
-    for (int e = 0; e < md.E; ++e) {
-      if (md.loo && e == tgt) continue;
-      const int ge = md.ent_base + e;
-      if (p.ent_valid != nullptr && p.ent_valid[(long long)biz * p.E_total + ge] == 0) continue;
-      EntItem it;
-      it.kv_row0 = (int)(md.kv_row_base + ((long long)biz * md.E + e) * md.Sk);
-      it.nkeys = md.Sk;
-      it.n16 = (md.Sk + 15) & ~15;
-      it.mod = (short)m; it.ent = (short)ge;
-      if (n < kMaxEnt) items[n++] = it;
-    }
+  int m = 0, e = lane, found = 0;
+  for (m = 0; m < p.n_mod; ++m) {
+    if (e < p.mods[m].E) { found = 1; break; }
+    e -= p.mods[m].E;
   }
-  return n;
+  bool ok = false;
+  EntItem it;
+  it.kv_row0 = 0; it.nkeys = 0; it.n16 = 0; it.mod = 0; it.ent = 0;
+  if (found) {
+    const MmsumAttnMod& md = p.mods[m];
+    const int ge = md.ent_base + e;
+    ok = !(md.loo && e == tgt);
+    if (ok && p.ent_valid != nullptr) ok = p.ent_valid[(long long)biz * p.E_total + ge] != 0;
+    it.kv_row0 = (int)(md.kv_row_base + ((long long)biz * md.E + e) * md.Sk);
+    it.nkeys = md.Sk;
+    it.n16 = (md.Sk + 15) & ~15;
+    it.mod = (short)m; it.ent = (short)ge;
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+  if (ok) items[__popc(bal & ((1u << lane) - 1u))] = it;
+  return __popc(bal);
 }
 
 // validity bitmask of the entity's keys: bit j of word w = key 32w + j may be attended
@@ -112,8 +129,9 @@ struct FwdSmem {
   uint8_t p[kPBytes];
   float red_max[2][4][SQ];
   float red_sum[2][4][SQ];
+  uint32_t kmask[kMaxEnt][8];
   EntItem items[kMaxEnt];
-  uint64_t q_full, kv_full[2], kv_empty[2], s_full[2], s_empty[2], p_full, mma2_done;
+  uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], p_full, mma2_done;
   uint32_t tmem_slot;
   int n_items;
 };
@@ -121,7 +139,9 @@ struct FwdSmem {
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the shared window with pointer arithmetic on the __shared__ array so the compiler keeps the
+  // shared address space (LDS/STS instead of generic LD/ST)
+  FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tgt = blockIdx.x % p.R;
   const int h = (blockIdx.x / p.R) % p.H;
@@ -129,11 +149,15 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
   const int qseq = biz * p.R + tgt;
   const int qrow0 = qseq * SQ;
 
-  if (threadIdx.x == 0) {
-    sm.n_items = build_ent_items(p, qseq, sm.items);
+  if (warp == 0) {
+    const int n = build_ent_items(p, qseq, sm.items, lane);
+    if (lane == 0) sm.n_items = n;
+  }
+  if (threadIdx.x == 32) {
     mbar_init(&sm.q_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&sm.kv_full[s], 1); mbar_init(&sm.kv_empty[s], 1);
+      mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1);
+      mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1);
       mbar_init(&sm.s_full[s], 1); mbar_init(&sm.s_empty[s], kSoftThreads);
     }
     mbar_init(&sm.p_full, kSoftThreads);
@@ -156,13 +180,21 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
     if (lane == 0) {
       mbar_expect_tx(&sm.q_full, SQ * 128);
       tma_load_2d(sm.q, &maps.q, &sm.q_full, p.q_col + h * HD, qrow0);
+      // K stages are released as soon as S = Q K^T has retired, V stages only after P V: two independent rings
       for (int i = 0; i < n_items; ++i) {
         const int st = i & 1;
-        mbar_wait(&sm.kv_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_wait(&sm.k_empty[st], ((i >> 1) & 1) ^ 1);
         const EntItem it = sm.items[i];
-        mbar_expect_tx(&sm.kv_full[st], 2 * it.nkeys * 128);
-        tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.kv_full[st], p.k_col + h * HD, it.kv_row0);
-        tma_load_2d(sm.v[st], &maps.kv[it.mod], &sm.kv_full[st], p.v_col + h * HD, it.kv_row0);
+        mbar_expect_tx(&sm.k_full[st], it.nkeys * 128);
+        tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.k_full[st], p.k_col + h * HD, it.kv_row0);
+      }
+    } else if (lane == 1) {
+      for (int i = 0; i < n_items; ++i) {
+        const int st = i & 1;
+        mbar_wait(&sm.v_empty[st], ((i >> 1) & 1) ^ 1);
+        const EntItem it = sm.items[i];
+        mbar_expect_tx(&sm.v_full[st], it.nkeys * 128);
+        tma_load_2d(sm.v[st], &maps.kv[it.mod], &sm.v_full[st], p.v_col + h * HD, it.kv_row0);
       }
     }
   } else if (warp == 1) {
@@ -172,7 +204,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       auto issue_s = [&](int i) {
         const int st = i & 1;
         const EntItem it = sm.items[i];
-        mbar_wait(&sm.kv_full[st], (i >> 1) & 1);
+        mbar_wait(&sm.k_full[st], (i >> 1) & 1);
         mbar_wait(&sm.s_empty[st], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t idesc = umma_idesc_bf16(128, it.n16, 0, 0);
@@ -182,6 +214,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
           umma_bf16(tmem + (st ? kColS1 : kColS0), umma_smem_desc_sw128(qaddr + kk * 32, 16, 1024),
                     umma_smem_desc_sw128(kaddr + kk * 32, 16, 1024), idesc, kk > 0);
         umma_commit(&sm.s_full[st]);
+        umma_commit(&sm.k_empty[st]);
       };
       issue_s(0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
@@ -189,13 +222,14 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
         if (i + 1 < n_items) issue_s(i + 1);
         const int st = i & 1;
         const EntItem it = sm.items[i];
+        mbar_wait(&sm.v_full[st], (i >> 1) & 1);
         mbar_wait(&sm.p_full, i & 1);
         tc_fence_after();
         const uint32_t vaddr = smem_u32(sm.v[st]);
         for (int kk = 0; kk < it.n16 / 16; ++kk)
           umma_bf16(tmem + kColO, umma_smem_desc_sw128(paddr + (kk >> 2) * (SQ * 128) + (kk & 3) * 32, 16, 1024),
                     umma_smem_desc_sw128(vaddr + kk * 2048, 8192, 1024), idesc_o, kk > 0);
-        umma_commit(&sm.kv_empty[st]);
+        umma_commit(&sm.v_empty[st]);
         umma_commit(&sm.mma2_done);
       }
     }
@@ -241,13 +275,14 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       return (l > 0.f) ? invn_prev / l : 0.f;
     };
     int cur_mod = 0;
+    build_masks(p, sm.items, n_items, sm.kmask, warp - 2, lane);
     for (int i = 0; i < n_items; ++i) {
       const EntItem it = sm.items[i];
       const int st = i & 1, par = i & 1;
       const int nchunk = (it.n16 + 31) >> 5;
       const bool has0 = cg < nchunk, has1 = cg + 4 < nchunk;
-      uint32_t w0 = has0 ? chunk_word(p, it, cg, lane) : 0u;
-      uint32_t w1 = has1 ? chunk_word(p, it, cg + 4, lane) : 0u;
+      uint32_t w0 = has0 ? sm.kmask[i][cg] : 0u;
+      uint32_t w1 = has1 ? sm.kmask[i][cg + 4] : 0u;
       if (p.causal) { w0 = causal_word(w0, row, cg); w1 = causal_word(w1, row, cg + 4); }
       const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
       const uint32_t scol = tmem + lane_off + (st ? kColS1 : kColS0);
@@ -354,8 +389,9 @@ struct BwdQSmem {
   uint8_t v[2][kKVStageBytes];
   uint8_t ds[kPBytes];
   float red_delta[2][4][SQ];
+  uint32_t kmask[kMaxEnt][8];
   EntItem items[kMaxEnt];
-  uint64_t q_full, da_full, da_free, kv_full[2], kv_empty[2], sdp_full, sdp_empty, ds_full, ds_free;
+  uint64_t q_full, da_full, da_free, k_full[2], k_empty[2], v_full[2], v_empty[2], sdp_full, sdp_empty, ds_full, ds_free;
   uint32_t tmem_slot;
   int n_items;
 };
@@ -363,7 +399,9 @@ struct BwdQSmem {
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  BwdQSmem& sm = *reinterpret_cast<BwdQSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the shared window with pointer arithmetic on the __shared__ array so the compiler keeps the
+  // shared address space (LDS/STS instead of generic LD/ST)
+  BwdQSmem& sm = *reinterpret_cast<BwdQSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tgt = blockIdx.x % p.R;
   const int h = (blockIdx.x / p.R) % p.H;
@@ -371,10 +409,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
   const int qseq = biz * p.R + tgt;
   const int qrow0 = qseq * SQ;
 
-  if (threadIdx.x == 0) {
-    sm.n_items = build_ent_items(p, qseq, sm.items);
+  if (warp == 0) {
+    const int n = build_ent_items(p, qseq, sm.items, lane);
+    if (lane == 0) sm.n_items = n;
+  }
+  if (threadIdx.x == 32) {
     mbar_init(&sm.q_full, 1); mbar_init(&sm.da_full, 1); mbar_init(&sm.da_free, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&sm.kv_full[s], 1); mbar_init(&sm.kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1);
+      mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1);
+    }
     mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, kSoftThreads);
     mbar_init(&sm.ds_full, kSoftThreads); mbar_init(&sm.ds_free, 1);
     fence_barrier_init();
@@ -403,10 +447,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           tma_load_2d(sm.da, &maps.d_o, &sm.da_full, h * HD, (int)(p.mods[it.mod].o_off / p.ldo) + qrow0);
           cur_mod = it.mod; ++n_da;
         }
-        mbar_wait(&sm.kv_empty[st], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&sm.kv_full[st], 2 * it.nkeys * 128);
-        tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.kv_full[st], p.k_col + h * HD, it.kv_row0);
-        tma_load_2d(sm.v[st], &maps.kv[it.mod], &sm.kv_full[st], p.v_col + h * HD, it.kv_row0);
+        // V is only read by dP' = dA V^T (released early); K also feeds dQ += dS K (released late): two rings
+        mbar_wait(&sm.v_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&sm.v_full[st], it.nkeys * 128);
+        tma_load_2d(sm.v[st], &maps.kv[it.mod], &sm.v_full[st], p.v_col + h * HD, it.kv_row0);
+      }
+    } else if (lane == 1) {
+      for (int i = 0; i < n_items; ++i) {
+        const int st = i & 1;
+        const EntItem it = sm.items[i];
+        mbar_wait(&sm.k_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&sm.k_full[st], it.nkeys * 128);
+        tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.k_full[st], p.k_col + h * HD, it.kv_row0);
       }
     }
   } else if (warp == 1) {
@@ -418,7 +470,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         const int st = i & 1;
         const EntItem it = sm.items[i];
         if (it.mod != cur_mod) { mbar_wait(&sm.da_full, n_da & 1); cur_mod = it.mod; ++n_da; }
-        mbar_wait(&sm.kv_full[st], (i >> 1) & 1);
+        mbar_wait(&sm.k_full[st], (i >> 1) & 1);
+        mbar_wait(&sm.v_full[st], (i >> 1) & 1);
         mbar_wait(&sm.sdp_empty, (i & 1) ^ 1);
         tc_fence_after();
         const uint32_t idesc = umma_idesc_bf16(128, it.n16, 0, 0);
@@ -432,6 +485,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           umma_bf16(tmem + kColDP, umma_smem_desc_sw128(daaddr + kk * 32, 16, 1024),
                     umma_smem_desc_sw128(vaddr + kk * 32, 16, 1024), idesc, kk > 0);
         umma_commit(&sm.sdp_full);
+        umma_commit(&sm.v_empty[st]);
         // last item of its modality: the dA tile may be replaced once these MMAs retire
         if (i + 1 >= n_items || sm.items[i + 1].mod != it.mod) umma_commit(&sm.da_free);
       };
@@ -447,7 +501,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         for (int kk = 0; kk < it.n16 / 16; ++kk)
           umma_bf16(tmem + kColDQ, umma_smem_desc_sw128(dsaddr + (kk >> 2) * (SQ * 128) + (kk & 3) * 32, 16, 1024),
                     umma_smem_desc_sw128(kaddr + kk * 2048, 8192, 1024), idesc_q, (i > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&sm.kv_empty[st]);
+        umma_commit(&sm.k_empty[st]);
         umma_commit(&sm.ds_free);
       }
     }
@@ -458,14 +512,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
     const int row = q4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float sc = p.scale * kLog2e;
+    build_masks(p, sm.items, n_items, sm.kmask, warp - 2, lane);
     for (int i = 0; i < n_items; ++i) {
       const EntItem it = sm.items[i];
       const int par = i & 1;
       const int nchunk = (it.n16 + 31) >> 5;
       const bool has[2] = {cg < nchunk, cg + 4 < nchunk};
       uint32_t wd[2];
-      wd[0] = has[0] ? chunk_word(p, it, cg, lane) : 0u;
-      wd[1] = has[1] ? chunk_word(p, it, cg + 4, lane) : 0u;
+      wd[0] = has[0] ? sm.kmask[i][cg] : 0u;
+      wd[1] = has[1] ? sm.kmask[i][cg + 4] : 0u;
       if (p.causal) { wd[0] = causal_word(wd[0], row, cg); wd[1] = causal_word(wd[1], row, cg + 4); }
       const long long li = (((long long)qseq * p.H + h) * p.E_total + it.ent) * SQ + row;
       const float lse = p.LSE[li];
@@ -579,7 +634,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ CUtensorMap kv128,
                        const MmsumAttnArgs p, int tiles_per_bh) {
   extern __shared__ uint8_t smem_raw[];
-  BwdKVSmem& sm = *reinterpret_cast<BwdKVSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the shared window with pointer arithmetic on the __shared__ array so the compiler keeps the
+  // shared address space (LDS/STS instead of generic LD/ST)
+  BwdKVSmem& sm = *reinterpret_cast<BwdKVSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int rem = blockIdx.x % tiles_per_bh;
   const int bh = blockIdx.x / tiles_per_bh;
@@ -709,16 +766,21 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
     }
     uint8_t* patom = sm.pt + row * 128 + (cg >> 1) * (SQ * 128);
     uint8_t* datom = sm.dst + row * 128 + (cg >> 1) * (SQ * 128);
+    auto lse_index = [&](int s) {
+      return (((long long)(biz * p.R + step_target(s)) * p.H + h) * p.E_total + ge) * SQ + (sw * 32 + lane);
+    };
+    if (sw < 4) {  // stage LSE / DELTA of the first target's 128 query rows
+      sm.lse[0][sw * 32 + lane] = p.LSE[lse_index(0)];
+      sm.dlt[0][sw * 32 + lane] = p.DELTA[lse_index(0)];
+    }
     for (int s = 0; s < n_steps; ++s) {
       const int st = s & 1;
       const int qseq = biz * p.R + step_target(s);
       const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + m] : 1.f;
-      if (sw < 4) {  // stage LSE / DELTA of this target's 128 query rows
-        const long long li = (((long long)qseq * p.H + h) * p.E_total + ge) * SQ + (sw * 32 + lane);
-        sm.lse[st][sw * 32 + lane] = p.LSE[li];
-        sm.dlt[st][sw * 32 + lane] = p.DELTA[li];
-      }
-      soft_bar();
+      soft_bar();   // stage st is visible; everybody is done with stage st^1 (read during step s-1)
+      float l_next = 0.f, d_next = 0.f;
+      const bool stage_next = (sw < 4) && (s + 1 < n_steps);
+      if (stage_next) { l_next = p.LSE[lse_index(s + 1)]; d_next = p.DELTA[lse_index(s + 1)]; }   // in flight during this step
       mbar_wait(&sm.sdp_full, s & 1);
       tc_fence_after();
       uint32_t rs[32], rd[32];
@@ -748,6 +810,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
         *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[0], po[1], po[2], po[3]);
         *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
       }
+      if (stage_next) { sm.lse[st ^ 1][sw * 32 + lane] = l_next; sm.dlt[st ^ 1][sw * 32 + lane] = d_next; }
       tc_fence_before();
       mbar_arrive(&sm.sdp_empty);
       fence_proxy_async_smem();
@@ -798,7 +861,7 @@ static int validate_tc(const MmsumAttnArgs* a, bool bwd) {
     ents += a->mods[m].E;
     if (a->mods[m].o_off % a->ldo) return MMSUM_ERR_INVALID;
   }
-  if (ents > kMaxEnt || ents > a->E_total) return MMSUM_ERR_INVALID;
+  if (ents > kMaxEnt || ents > a->E_total || ents > 32) return MMSUM_ERR_INVALID;
   if (a->causal && (a->n_mod != 1 || a->mods[0].Sk != SQ)) return MMSUM_ERR_INVALID;
   if (bwd) {
     if (!a->DELTA || !a->dQ || !a->dKV) return MMSUM_ERR_INVALID;

@@ -62,15 +62,17 @@ __device__ __forceinline__ float warp_max(float v) {
 // mask without storing it.  (PyTorch's Philox stream cannot be matched — parity
 // is defined at dropout 0)
 // ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t hash_u32(uint64_t x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
-  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
-  x ^= x >> 33;
-  return (uint32_t)x;
+// 32-bit integer hash (two multiply-xorshift rounds): ~8 ALU instructions per call; the 64-bit murmur finaliser used
+// before made the LayerNorm kernels ALU-bound (two 64-bit multiplies per pair of elements).
+__device__ __forceinline__ uint32_t hash_u32(uint32_t h) {
+  h ^= h >> 16; h *= 0x21f0aaadu;
+  h ^= h >> 15; h *= 0x735a2d97u;
+  h ^= h >> 15;
+  return h;
 }
-// returns 4 keep bits worth of randomness as 4 x 8-bit lanes -> caller compares vs threshold
 __device__ __forceinline__ uint32_t dropout_rand(uint64_t seed, uint32_t stream, uint64_t idx) {
-  return hash_u32(seed * 0x9E3779B97F4A7C15ULL + ((uint64_t)stream << 40) + idx);
+  const uint32_t key = (uint32_t)seed ^ (uint32_t)(seed >> 32) ^ (stream * 0x9E3779B1u) ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u);
+  return hash_u32((uint32_t)idx * 0x9E3779B1u + key);
 }
 // keep decision for element idx with keep threshold thr = (uint32)(keep_prob * 2^32)
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t stream, uint64_t idx, uint32_t thr) {
