@@ -157,6 +157,17 @@ int mmsum_table_fwd(const MmsumTableArgs* args, void* stream);
 int mmsum_table_bits_bwd(const void* dX, const int64_t* bits, float* dW, int32_t B, int32_t F, int32_t f0, int32_t nrows,
                          int32_t nb, void* stream);
 
+/* ---- optimizer over the flat arenas ---------------------------------------------------------------
+ * mmsum_grad_sumsq: out[0] = sum g^2 (two deterministic stages; partial needs >= 1184 floats) — the global norm of
+ * torch.nn.utils.clip_grad_norm_ (src/multimodal_train.py:361-362).
+ * mmsum_adamw_step: transformers-3.0.2 AdamW.step (src/transformer/optimization.py:208-267) with the clip coefficient
+ * min(1, max_norm / (sqrt(sumsq) + 1e-6)) folded in; step_size = lr * sqrt(1 - beta2^t) / (1 - beta1^t); flags[i/64]
+ * bit0 = update, bit1 = weight decay; also writes the bf16 compute copy. */
+int mmsum_grad_sumsq(const float* g, int64_t n, float* partial, int32_t n_partial, float* out, void* stream);
+int mmsum_adamw_step(float* w32, void* w16, const float* g, float* m, float* v, const uint8_t* flags, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, float step_size, const float* sumsq,
+                     float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
