@@ -34,7 +34,8 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(CSRC, os.path.basename(s).replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        extra = ["-DMMSUM_ATTN_TRACE"] if os.environ.get("MMSUM_TRACE") else []
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()

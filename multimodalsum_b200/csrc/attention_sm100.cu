@@ -56,16 +56,27 @@ __device__ __forceinline__ uint32_t chunk_word(const MmsumAttnArgs& p, const Ent
   if (ok && p.key_valid != nullptr) ok = p.key_valid[(long long)it.kv_row0 + j] != 0;
   return __ballot_sync(0xffffffffu, ok);
 }
-// all (entity, chunk) validity words of the CTA, computed up front by the softmax warps (one global-load latency
-// for the whole CTA instead of one per entity on the critical path)
-__device__ __forceinline__ void build_masks(const MmsumAttnArgs& p, const EntItem* items, int n_items, uint32_t (*kmask)[8],
-                                            int sw, int lane) {
-  for (int idx = sw; idx < n_items * 7; idx += kSoftWarps) {
+// All (entity, chunk) validity words of the CTA, computed up front by warps 1..17 (one global-load latency for the whole
+// CTA instead of one per entity on the critical path).  Each entity's score tile is then trimmed to its last valid key
+// (n16): pad keys at the tail of a review cost neither MMA columns nor softmax work.
+__device__ __forceinline__ void mask_bar() { asm volatile("bar.sync 2, %0;" ::"n"(kSoftThreads + 32) : "memory"); }
+__device__ __forceinline__ void build_masks(const MmsumAttnArgs& p, EntItem* items, int n_items, uint32_t (*kmask)[8],
+                                            int w, int lane) {   // w = warp - 1 in [0, 17)
+  for (int idx = w; idx < n_items * 7; idx += kSoftWarps + 1) {
     const int i = idx / 7, c = idx - i * 7;
-    const uint32_t w = chunk_word(p, items[i], c, lane);
-    if (lane == 0) kmask[i][c] = w;
+    const uint32_t wd = chunk_word(p, items[i], c, lane);
+    if (lane == 0) kmask[i][c] = wd;
   }
-  soft_bar();
+  mask_bar();
+  const int i = w * 32 + lane;
+  if (i < n_items) {
+    int last = 0;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) { const uint32_t wd = kmask[i][c]; if (wd) last = c * 32 + 32 - __clz(wd); }
+    const int n16 = (last + 15) & ~15;
+    items[i].n16 = n16 < 16 ? 16 : n16;
+  }
+  mask_bar();
 }
 __device__ __forceinline__ uint32_t causal_word(uint32_t wd, int row, int c) {
   const int lim = row - c * 32;   // keys 32c + j <= row
@@ -77,6 +88,19 @@ struct AttnMaps {
   CUtensorMap kv[3];   // per modality: KV rows, box {64, Sk}
   CUtensorMap d_o;     // bwd: upstream gradient rows (all modalities stacked), box {64, 128}
 };
+
+#ifdef MMSUM_ATTN_TRACE
+// debug-only timeline of CTA 0 (build with MMSUM_TRACE=1): g_trace[role][event index] = clock64
+__device__ long long g_trace[8][512];
+#define TRACE(role, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_trace[role][idx] = clock64(); } while (0)
+#else
+#define TRACE(role, idx) do { } while (0)
+#endif
+
+// The MMA issuer is ONE thread: every ALU instruction between two tcgen05.mma issues is exposed latency (measured: the
+// P V issue loop with per-step descriptor construction took ~1300 clk for 13 x 32-clk MMAs).  Descriptors are therefore
+// built once per operand and advanced with a single 64-bit add of a compile-time constant.
+__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -186,6 +210,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
         mbar_wait(&sm.k_empty[st], ((i >> 1) & 1) ^ 1);
         const EntItem it = sm.items[i];
         mbar_expect_tx(&sm.k_full[st], it.nkeys * 128);
+        TRACE(0, i);
         tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.k_full[st], p.k_col + h * HD, it.kv_row0);
       }
     } else if (lane == 1) {
@@ -198,23 +223,29 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_items > 0) {
-      const uint32_t qaddr = smem_u32(sm.q), paddr = smem_u32(sm.p);
+    build_masks(p, sm.items, n_items, sm.kmask, 0, lane);
+    if (n_items > 0) {   // whole warp runs the issue loop; elect.sync picks the issuing lane per instruction
+      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sm.q), 16, 1024);
+      const uint64_t kdesc0 = umma_smem_desc_sw128(smem_u32(sm.k[0]), 16, 1024), kdesc1 = umma_smem_desc_sw128(smem_u32(sm.k[1]), 16, 1024);
+      const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sm.p), 16, 1024);
+      const uint64_t vdesc0 = umma_smem_desc_sw128(smem_u32(sm.v[0]), 8192, 1024), vdesc1 = umma_smem_desc_sw128(smem_u32(sm.v[1]), 8192, 1024);
       mbar_wait(&sm.q_full, 0);
       auto issue_s = [&](int i) {
         const int st = i & 1;
         const EntItem it = sm.items[i];
         mbar_wait(&sm.k_full[st], (i >> 1) & 1);
+        if (lane == 0) TRACE(1, 2 * i);
         mbar_wait(&sm.s_empty[st], ((i >> 1) & 1) ^ 1);
+        if (lane == 0) TRACE(1, 2 * i + 1);
         tc_fence_after();
         const uint32_t idesc = umma_idesc_bf16(128, it.n16, 0, 0);
-        const uint32_t kaddr = smem_u32(sm.k[st]);
+        const uint64_t kdesc = st ? kdesc1 : kdesc0;
+        const uint32_t dcol = tmem + (st ? kColS1 : kColS0);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16(tmem + (st ? kColS1 : kColS0), umma_smem_desc_sw128(qaddr + kk * 32, 16, 1024),
-                    umma_smem_desc_sw128(kaddr + kk * 32, 16, 1024), idesc, kk > 0);
-        umma_commit(&sm.s_full[st]);
-        umma_commit(&sm.k_empty[st]);
+          umma_bf16_w(dcol, desc_adv(qdesc, kk * 32), desc_adv(kdesc, kk * 32), idesc, kk > 0);
+        umma_commit_w(&sm.s_full[st]);
+        umma_commit_w(&sm.k_empty[st]);
       };
       issue_s(0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
@@ -223,14 +254,23 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
         const int st = i & 1;
         const EntItem it = sm.items[i];
         mbar_wait(&sm.v_full[st], (i >> 1) & 1);
+        if (lane == 0) TRACE(2, 2 * i);
         mbar_wait(&sm.p_full, i & 1);
+        if (lane == 0) TRACE(2, 2 * i + 1);
         tc_fence_after();
-        const uint32_t vaddr = smem_u32(sm.v[st]);
-        for (int kk = 0; kk < it.n16 / 16; ++kk)
-          umma_bf16(tmem + kColO, umma_smem_desc_sw128(paddr + (kk >> 2) * (SQ * 128) + (kk & 3) * 32, 16, 1024),
-                    umma_smem_desc_sw128(vaddr + kk * 2048, 8192, 1024), idesc_o, kk > 0);
-        umma_commit(&sm.v_empty[st]);
-        umma_commit(&sm.mma2_done);
+        const uint64_t vdesc = st ? vdesc1 : vdesc0;
+        const int nk = it.n16 >> 4;
+#pragma unroll
+        for (int kk = 0; kk < kMaxKeys / 16; ++kk)
+          if (kk < nk)
+            umma_bf16_w(tmem + kColO, desc_adv(pdesc, (kk >> 2) * (SQ * 128) + (kk & 3) * 32), desc_adv(vdesc, kk * 2048), idesc_o, kk > 0);
+        if (lane == 0) TRACE(4, 2 * i);
+        umma_commit_w(&sm.v_empty[st]);
+        umma_commit_w(&sm.mma2_done);
+#ifdef MMSUM_ATTN_TRACE
+        mbar_wait(&sm.mma2_done, i & 1);
+        if (lane == 0) TRACE(4, 2 * i + 1);
+#endif
       }
     }
   } else {
@@ -271,11 +311,11 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       const float l = (sm.red_sum[par_prev][0][row] + sm.red_sum[par_prev][1][row]) +
                       (sm.red_sum[par_prev][2][row] + sm.red_sum[par_prev][3][row]);
       if (cg == 0)
-        p.LSE[(((long long)qseq * p.H + h) * p.E_total + ent_prev) * SQ + row] = (l > 0.f) ? (msc_prev + log2f(l)) : INFINITY;
-      return (l > 0.f) ? invn_prev / l : 0.f;
+        p.LSE[(((long long)qseq * p.H + h) * p.E_total + ent_prev) * SQ + row] = (l > 0.f) ? (msc_prev + __log2f(l)) : INFINITY;
+      return (l > 0.f) ? __fdividef(invn_prev, l) : 0.f;
     };
     int cur_mod = 0;
-    build_masks(p, sm.items, n_items, sm.kmask, warp - 2, lane);
+    build_masks(p, sm.items, n_items, sm.kmask, warp - 1, lane);
     for (int i = 0; i < n_items; ++i) {
       const EntItem it = sm.items[i];
       const int st = i & 1, par = i & 1;
@@ -286,7 +326,9 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       if (p.causal) { w0 = causal_word(w0, row, cg); w1 = causal_word(w1, row, cg + 4); }
       const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
       const uint32_t scol = tmem + lane_off + (st ? kColS1 : kColS0);
+      if (threadIdx.x == 64) TRACE(3, 6 * i);
       mbar_wait(&sm.s_full[st], (i >> 1) & 1);
+      if (threadIdx.x == 64) TRACE(3, 6 * i + 1);
       tc_fence_after();
       // max pass (one 32-column chunk in registers at a time; 4 softmax warps per scheduler hide the TMEM latency)
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -308,7 +350,9 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
         }
       }
       sm.red_max[par][cg][row] = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if (threadIdx.x == 64) TRACE(3, 6 * i + 2);
       soft_bar();
+      if (threadIdx.x == 64) TRACE(3, 6 * i + 3);
       const float mx = fmaxf(fmaxf(sm.red_max[par][0][row], sm.red_max[par][1][row]),
                              fmaxf(sm.red_max[par][2][row], sm.red_max[par][3][row]));
       const float msc = (mx == -INFINITY) ? 0.f : mx * sc;
@@ -316,6 +360,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       if (i > 0) {
         const float w_prev = close_prev(par ^ 1);
         mbar_wait(&sm.mma2_done, (i - 1) & 1);
+        if (threadIdx.x == 64) TRACE(3, 6 * i + 4);
         tc_fence_after();
         add_o(w_prev);
       }
@@ -355,6 +400,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
         }
       }
       sm.red_sum[par][cg][row] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      if (threadIdx.x == 64) TRACE(3, 6 * i + 5);
       tc_fence_before();
       mbar_arrive(&sm.s_empty[st]);
       fence_proxy_async_smem();
@@ -462,8 +508,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_items > 0) {
-      const uint32_t qaddr = smem_u32(sm.q), daaddr = smem_u32(sm.da), dsaddr = smem_u32(sm.ds);
+    build_masks(p, sm.items, n_items, sm.kmask, 0, lane);
+    if (n_items > 0) {   // whole warp runs the issue loop; elect.sync picks the issuing lane per instruction
+      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sm.q), 16, 1024), dadesc = umma_smem_desc_sw128(smem_u32(sm.da), 16, 1024);
+      const uint64_t dsdesc = umma_smem_desc_sw128(smem_u32(sm.ds), 16, 1024);
+      const uint64_t kdesc_k[2] = {umma_smem_desc_sw128(smem_u32(sm.k[0]), 16, 1024), umma_smem_desc_sw128(smem_u32(sm.k[1]), 16, 1024)};
+      const uint64_t kdesc_mn[2] = {umma_smem_desc_sw128(smem_u32(sm.k[0]), 8192, 1024), umma_smem_desc_sw128(smem_u32(sm.k[1]), 8192, 1024)};
+      const uint64_t vdesc_k[2] = {umma_smem_desc_sw128(smem_u32(sm.v[0]), 16, 1024), umma_smem_desc_sw128(smem_u32(sm.v[1]), 16, 1024)};
       mbar_wait(&sm.q_full, 0);
       int cur_mod = -1, n_da = 0;
       auto issue_sdp = [&](int i) {
@@ -475,19 +526,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         mbar_wait(&sm.sdp_empty, (i & 1) ^ 1);
         tc_fence_after();
         const uint32_t idesc = umma_idesc_bf16(128, it.n16, 0, 0);
-        const uint32_t kaddr = smem_u32(sm.k[st]), vaddr = smem_u32(sm.v[st]);
+        const uint64_t kd = st ? kdesc_k[1] : kdesc_k[0], vd = st ? vdesc_k[1] : vdesc_k[0];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16(tmem + kColS0, umma_smem_desc_sw128(qaddr + kk * 32, 16, 1024),
-                    umma_smem_desc_sw128(kaddr + kk * 32, 16, 1024), idesc, kk > 0);
+          umma_bf16_w(tmem + kColS0, desc_adv(qdesc, kk * 32), desc_adv(kd, kk * 32), idesc, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16(tmem + kColDP, umma_smem_desc_sw128(daaddr + kk * 32, 16, 1024),
-                    umma_smem_desc_sw128(vaddr + kk * 32, 16, 1024), idesc, kk > 0);
-        umma_commit(&sm.sdp_full);
-        umma_commit(&sm.v_empty[st]);
+          umma_bf16_w(tmem + kColDP, desc_adv(dadesc, kk * 32), desc_adv(vd, kk * 32), idesc, kk > 0);
+        umma_commit_w(&sm.sdp_full);
+        umma_commit_w(&sm.v_empty[st]);
         // last item of its modality: the dA tile may be replaced once these MMAs retire
-        if (i + 1 >= n_items || sm.items[i + 1].mod != it.mod) umma_commit(&sm.da_free);
+        if (i + 1 >= n_items || sm.items[i + 1].mod != it.mod) umma_commit_w(&sm.da_free);
       };
       issue_sdp(0);
       const uint32_t idesc_q = umma_idesc_bf16(128, HD, 0, 1);
@@ -497,12 +546,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         const EntItem it = sm.items[i];
         mbar_wait(&sm.ds_full, i & 1);
         tc_fence_after();
-        const uint32_t kaddr = smem_u32(sm.k[st]);
-        for (int kk = 0; kk < it.n16 / 16; ++kk)
-          umma_bf16(tmem + kColDQ, umma_smem_desc_sw128(dsaddr + (kk >> 2) * (SQ * 128) + (kk & 3) * 32, 16, 1024),
-                    umma_smem_desc_sw128(kaddr + kk * 2048, 8192, 1024), idesc_q, (i > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&sm.k_empty[st]);
-        umma_commit(&sm.ds_free);
+        const uint64_t kd = st ? kdesc_mn[1] : kdesc_mn[0];
+        const int nk = it.n16 >> 4;
+#pragma unroll
+        for (int kk = 0; kk < kMaxKeys / 16; ++kk)
+          if (kk < nk)
+            umma_bf16_w(tmem + kColDQ, desc_adv(dsdesc, (kk >> 2) * (SQ * 128) + (kk & 3) * 32), desc_adv(kd, kk * 2048), idesc_q,
+                      (i > 0 || kk > 0) ? 1u : 0u);
+        umma_commit_w(&sm.k_empty[st]);
+        umma_commit_w(&sm.ds_free);
       }
     }
   } else {
@@ -512,7 +564,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
     const int row = q4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float sc = p.scale * kLog2e;
-    build_masks(p, sm.items, n_items, sm.kmask, warp - 2, lane);
+    build_masks(p, sm.items, n_items, sm.kmask, warp - 1, lane);
     for (int i = 0; i < n_items; ++i) {
       const EntItem it = sm.items[i];
       const int par = i & 1;
@@ -710,8 +762,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t kaddr = smem_u32(sm.k), vaddr = smem_u32(sm.v), ptaddr = smem_u32(sm.pt), dsaddr = smem_u32(sm.dst);
+    {   // whole warp runs the issue loop; elect.sync picks the issuing lane per instruction
+      const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sm.k), 16, 1024), vdesc = umma_smem_desc_sw128(smem_u32(sm.v), 16, 1024);
+      const uint64_t ptdesc = umma_smem_desc_sw128(smem_u32(sm.pt), 16, 1024), dstdesc = umma_smem_desc_sw128(smem_u32(sm.dst), 16, 1024);
+      const uint64_t qdesc_k[2] = {umma_smem_desc_sw128(smem_u32(sm.q[0]), 16, 1024), umma_smem_desc_sw128(smem_u32(sm.q[1]), 16, 1024)};
+      const uint64_t qdesc_mn[2] = {umma_smem_desc_sw128(smem_u32(sm.q[0]), 8192, 1024), umma_smem_desc_sw128(smem_u32(sm.q[1]), 8192, 1024)};
+      const uint64_t dadesc_k[2] = {umma_smem_desc_sw128(smem_u32(sm.da[0]), 16, 1024), umma_smem_desc_sw128(smem_u32(sm.da[1]), 16, 1024)};
+      const uint64_t dadesc_mn[2] = {umma_smem_desc_sw128(smem_u32(sm.da[0]), 8192, 1024), umma_smem_desc_sw128(smem_u32(sm.da[1]), 8192, 1024)};
       const uint32_t idesc_s = umma_idesc_bf16(128, SQ, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
       mbar_wait(&sm.kv_full, 0);
@@ -720,16 +777,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
         mbar_wait(&sm.qd_full[st], (s >> 1) & 1);
         mbar_wait(&sm.sdp_empty, (s & 1) ^ 1);
         tc_fence_after();
-        const uint32_t qaddr = smem_u32(sm.q[st]), daaddr = smem_u32(sm.da[st]);
+        const uint64_t qd = st ? qdesc_k[1] : qdesc_k[0], dd = st ? dadesc_k[1] : dadesc_k[0];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16(tmem + kColST, umma_smem_desc_sw128(kaddr + kk * 32, 16, 1024),
-                    umma_smem_desc_sw128(qaddr + kk * 32, 16, 1024), idesc_s, kk > 0);
+          umma_bf16_w(tmem + kColST, desc_adv(kdesc, kk * 32), desc_adv(qd, kk * 32), idesc_s, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16(tmem + kColDPT, umma_smem_desc_sw128(vaddr + kk * 32, 16, 1024),
-                    umma_smem_desc_sw128(daaddr + kk * 32, 16, 1024), idesc_s, kk > 0);
-        umma_commit(&sm.sdp_full);
+          umma_bf16_w(tmem + kColDPT, desc_adv(vdesc, kk * 32), desc_adv(dd, kk * 32), idesc_s, kk > 0);
+        umma_commit_w(&sm.sdp_full);
       };
       issue_sdp(0);
       for (int s = 0; s < n_steps; ++s) {
@@ -737,17 +792,17 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
         const int st = s & 1;
         mbar_wait(&sm.pds_full, s & 1);
         tc_fence_after();
-        const uint32_t qaddr = smem_u32(sm.q[st]), daaddr = smem_u32(sm.da[st]);
+        const uint64_t qd = st ? qdesc_mn[1] : qdesc_mn[0], dd = st ? dadesc_mn[1] : dadesc_mn[0];
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)   // contraction over the 128 queries
-          umma_bf16(tmem + kColDV, umma_smem_desc_sw128(ptaddr + (kk >> 2) * (SQ * 128) + (kk & 3) * 32, 16, 1024),
-                    umma_smem_desc_sw128(daaddr + kk * 2048, 8192, 1024), idesc_o, (s > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_w(tmem + kColDV, desc_adv(ptdesc, (kk >> 2) * (SQ * 128) + (kk & 3) * 32), desc_adv(dd, kk * 2048), idesc_o,
+                    (s > 0 || kk > 0) ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_bf16(tmem + kColDK, umma_smem_desc_sw128(dsaddr + (kk >> 2) * (SQ * 128) + (kk & 3) * 32, 16, 1024),
-                    umma_smem_desc_sw128(qaddr + kk * 2048, 8192, 1024), idesc_o, (s > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&sm.qd_empty[st]);
-        umma_commit(&sm.pds_free);
+          umma_bf16_w(tmem + kColDK, desc_adv(dstdesc, (kk >> 2) * (SQ * 128) + (kk & 3) * 32), desc_adv(qd, kk * 2048), idesc_o,
+                    (s > 0 || kk > 0) ? 1u : 0u);
+        umma_commit_w(&sm.qd_empty[st]);
+        umma_commit_w(&sm.pds_free);
       }
     }
   } else {
@@ -946,3 +1001,9 @@ extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
   MMSUM_CHECK_LAUNCH();
   return 0;
 }
+
+#ifdef MMSUM_ATTN_TRACE
+extern "C" int mmsum_debug_read_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, mmsum::g_trace, sizeof(long long) * 8 * 512);
+}
+#endif

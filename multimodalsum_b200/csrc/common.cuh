@@ -184,6 +184,44 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-converged issue: the WHOLE warp runs the issue loop (so descriptors / coordinates stay in uniform registers and
+// the loop is not a chain of R2UR conversions inside a divergent lane-0 branch — measured ~160 clk per issue that way),
+// and only the lane chosen by elect.sync (inside the same asm block, so ptxas knows it is a single lane) executes it.
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_w(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_w(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // mbarrier arrives once all previously issued tcgen05.mma of this thread retire.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

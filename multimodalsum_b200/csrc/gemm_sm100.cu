@@ -106,73 +106,69 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int mt, nt, sp; decode_tile(g, t, mt, nt, sp);
-        const int m0 = mt * BM, n0 = nt * BN;
-        const int k_begin = sp * g.k_per_split;
-        const int k_end = min(g.K, k_begin + g.k_per_split);
-        for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * L::kStageBytes;
-          uint8_t* sB = sA + L::kABytes;
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-          if (A_MN) {
+    // ===================== TMA producer (whole warp runs the loop; lane 0 issues) =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int mt, nt, sp; decode_tile(g, t, mt, nt, sp);
+      const int m0 = mt * BM, n0 = nt * BN;
+      const int k_begin = sp * g.k_per_split;
+      const int k_end = min(g.K, k_begin + g.k_per_split);
+      for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * L::kStageBytes;
+        uint8_t* sB = sA + L::kABytes;
+        mbar_expect_tx_w(&full_bar[stage], L::kStageBytes);
+        if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, k0);
-          } else if (g.k_split > 0 && k0 >= g.k_split) {
-            tma_load_2d(sA, &tmA2, &full_bar[stage], k0 - g.k_split, m0);
-          } else {
-            tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
-          }
-          if (B_MN) {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, k0);
-          } else {
-            tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
-          }
-          if (++stage == L::kStages) { stage = 0; phase ^= 1; }
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d_w(sA + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, k0);
+        } else if (g.k_split > 0 && k0 >= g.k_split) {
+          tma_load_2d_w(sA, &tmA2, &full_bar[stage], k0 - g.k_split, m0);
+        } else {
+          tma_load_2d_w(sA, &tmA, &full_bar[stage], k0, m0);
         }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d_w(sB + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, k0);
+        } else {
+          tma_load_2d_w(sB, &tmB, &full_bar[stage], k0, n0);
+        }
+        if (++stage == L::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      int stage = 0; uint32_t phase = 0;
-      int as = 0; uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int mt, nt, sp; decode_tile(g, t, mt, nt, sp);
-        const int k_begin = sp * g.k_per_split;
-        const int k_end = min(g.K, k_begin + g.k_per_split);
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+    // ===================== MMA issuer (whole warp runs the loop; lane 0 issues) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int mt, nt, sp; decode_tile(g, t, mt, nt, sp);
+      const int k_begin = sp * g.k_per_split;
+      const int k_end = min(g.K, k_begin + g.k_per_split);
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      uint32_t accum = 0;
+      for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        uint32_t accum = 0;
-        for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t aaddr = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t baddr = aaddr + L::kABytes;
+        const uint32_t aaddr = smem_base + stage * L::kStageBytes;
+        const uint32_t baddr = aaddr + L::kABytes;
+        // K-major: 8-row groups are 1024 B apart (SBO); a K step of 16 elements is +32 B inside the swizzle row.
+        // MN-major: 64-wide MN blocks are 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO); K step = 16 rows = 2048 B.
+        const uint64_t ad0 = A_MN ? umma_smem_desc_sw128(aaddr, 8192, 1024) : umma_smem_desc_sw128(aaddr, 16, 1024);
+        const uint64_t bd0 = B_MN ? umma_smem_desc_sw128(baddr, 8192, 1024) : umma_smem_desc_sw128(baddr, 16, 1024);
 #pragma unroll
-          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-            // K-major: 8-row groups are 1024 B apart (SBO); a K step of 16 elements is +32 B inside the swizzle row.
-            // MN-major: 64-wide MN blocks are 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO); K step = 16 rows = 2048 B.
-            const uint64_t ad = A_MN ? umma_smem_desc_sw128(aaddr + kk * 2048, 8192, 1024)
-                                     : umma_smem_desc_sw128(aaddr + kk * 32, 16, 1024);
-            const uint64_t bd = B_MN ? umma_smem_desc_sw128(baddr + kk * 2048, 8192, 1024)
-                                     : umma_smem_desc_sw128(baddr + kk * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, accum);
-            accum = 1;
-          }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
-          if (++stage == L::kStages) { stage = 0; phase ^= 1; }
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          umma_bf16_w(d_tmem, ad0 + (uint64_t)((A_MN ? kk * 2048 : kk * 32) >> 4),
+                      bd0 + (uint64_t)((B_MN ? kk * 2048 : kk * 32) >> 4), idesc, accum);
+          accum = 1;
         }
-        umma_commit(&tfull_bar[as]);       // accumulator complete
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        umma_commit_w(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+        if (++stage == L::kStages) { stage = 0; phase ^= 1; }
       }
+      umma_commit_w(&tfull_bar[as]);       // accumulator complete
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
     // ===================== epilogue warps (2..5) =====================
