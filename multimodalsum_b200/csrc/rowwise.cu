@@ -55,6 +55,8 @@ __device__ __forceinline__ void load_row_f32(const float* row, int lane, float (
   }
 }
 __device__ __forceinline__ int col_of(int lane, int i) { return (i >> 3) * 256 + lane * 8 + (i & 7); }
+// per-column fp32 vector (gamma, beta) in the same lane layout, coalesced 128-bit loads
+__device__ __forceinline__ void load_cols_f32(const float* __restrict__ v, int lane, float (&o)[VPL]) { load_row_f32(v, lane, o); }
 
 __device__ __forceinline__ void ln_stats(const float (&z)[VPL], float& mean, float& rstd) {
   float s = 0.f;
@@ -234,75 +236,90 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const bf16* __restrict_
   float mean, rstd;
   ln_stats(z, mean, rstd);
   if (lane == 0) { mean_o[row] = mean; rstd_o[row] = rstd; }
+  load_cols_f32(gamma, lane, r);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) { const int c = col_of(lane, i); z[i] = (z[i] - mean) * rstd * gamma[c] + beta[c]; }
+  for (int i = 0; i < VPL; ++i) z[i] = (z[i] - mean) * rstd * r[i];
+  load_cols_f32(beta, lane, r);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) z[i] += r[i];
   store_row_bf16(out + (long long)row * D, lane, z);
 }
 
 // backward: dout = d1 (+ d2); z recomputed from res, y.  dres = dz (bf16), dy = dz * dropmask (bf16; same buffer
 // allowed when dropout is off), dgamma/dbeta accumulated with atomics (fp32).
-__global__ void __launch_bounds__(256) add_ln_bwd_kernel(const bf16* __restrict__ d1, const bf16* __restrict__ d2,
-                                                         const bf16* __restrict__ res, const bf16* __restrict__ y,
-                                                         const float* __restrict__ gamma, const float* __restrict__ mean_i,
-                                                         const float* __restrict__ rstd_i, bf16* __restrict__ dres,
-                                                         bf16* __restrict__ dy_out, float* __restrict__ dgamma,
-                                                         float* __restrict__ dbeta, int rows, DropCfg dc) {
-  __shared__ float sg[8][256];
+// dgamma / dbeta partial sums live in shared memory ([warp][value i][lane]: conflict-free), not in 64 registers, so
+// three 128-thread blocks fit per SM; one atomic per column per block at the end.
+__global__ void __launch_bounds__(128, 3) add_ln_bwd_kernel(const bf16* __restrict__ d1, const bf16* __restrict__ d2,
+                                                            const bf16* __restrict__ res, const bf16* __restrict__ y,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean_i,
+                                                            const float* __restrict__ rstd_i, bf16* __restrict__ dres,
+                                                            bf16* __restrict__ dy_out, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int rows, DropCfg dc) {
+  extern __shared__ float sacc[];                      // [4 warps][2][VPL][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float ag[VPL], ab[VPL];
+  float* sg = sacc + warp * (2 * VPL * 32);
+  float* sb = sg + VPL * 32;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  for (int i = 0; i < VPL; ++i) { sg[i * 32 + lane] = 0.f; sb[i * 32 + lane] = 0.f; }
   for (int row = blockIdx.x * nw + warp; row < rows; row += gridDim.x * nw) {
-    float z[VPL], r[VPL], dy[VPL], mk[VPL];
+    float z[VPL], t[VPL];
+    uint32_t keep = 0;   // bit i: element i survived dropout
     load_row_bf16(y + (long long)row * D, lane, z);
-    load_row_bf16(res + (long long)row * D, lane, r);
-    load_row_bf16(d1 + (long long)row * D, lane, dy);
-    if (d2 != nullptr) {
-      load_row_bf16(d2 + (long long)row * D, lane, mk);
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) dy[i] += mk[i];
-    }
 #pragma unroll
     for (int i = 0; i < VPL; i += 2) {
       const float2 m = drop_pair(dc, (unsigned long long)row * D + col_of(lane, i));
-      mk[i] = m.x; mk[i + 1] = m.y;
-      z[i] = r[i] + z[i] * m.x; z[i + 1] = r[i + 1] + z[i + 1] * m.y;
+      z[i] *= m.x; z[i + 1] *= m.y;
+      keep |= (m.x != 0.f ? 1u : 0u) << i;
+      keep |= (m.y != 0.f ? 1u : 0u) << (i + 1);
     }
+    load_row_bf16(res + (long long)row * D, lane, t);
     const float mean = mean_i[row], rstd = rstd_i[row];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) z[i] = (z[i] + t[i] - mean) * rstd;          // z := xhat
+    load_row_bf16(d1 + (long long)row * D, lane, t);                            // t := upstream gradient
+    if (d2 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = *reinterpret_cast<const uint4*>(d2 + (long long)row * D + j * 256 + lane * 8);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16(w[e]); t[j * 8 + 2 * e] += f.x; t[j * 8 + 2 * e + 1] += f.y; }
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int c = col_of(lane, i);
-      const float xh = (z[i] - mean) * rstd;
-      ag[i] += dy[i] * xh; ab[i] += dy[i];
-      const float dxh = dy[i] * gamma[c];
-      s1 += dxh; s2 += dxh * xh;
-      z[i] = xh; dy[i] = dxh;
+    for (int j = 0; j < 4; ++j) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + j * 256 + lane * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + j * 256 + lane * 8 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = j * 8 + k;
+        sg[i * 32 + lane] += t[i] * z[i];
+        sb[i * 32 + lane] += t[i];
+        t[i] *= gg[k];                                                          // t := d xhat
+        s1 += t[i]; s2 += t[i] * z[i];
+      }
     }
     s1 = warp_sum(s1) * (1.f / D); s2 = warp_sum(s2) * (1.f / D);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) dy[i] = rstd * (dy[i] - s1 - z[i] * s2);
-    store_row_bf16(dres + (long long)row * D, lane, dy);
+    for (int i = 0; i < VPL; ++i) t[i] = rstd * (t[i] - s1 - z[i] * s2);        // t := dz
+    store_row_bf16(dres + (long long)row * D, lane, t);
     if (dy_out != dres) {
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) dy[i] *= mk[i];
-      store_row_bf16(dy_out + (long long)row * D, lane, dy);
+      for (int i = 0; i < VPL; ++i) t[i] = ((keep >> i) & 1u) ? t[i] * dc.scale : 0.f;
+      store_row_bf16(dy_out + (long long)row * D, lane, t);
     }
   }
-  for (int pass = 0; pass < 2; ++pass) {
-    float* acc = pass == 0 ? ag : ab;
-    float* dst = pass == 0 ? dgamma : dbeta;
-    for (int quarter = 0; quarter < 4; ++quarter) {
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sg[warp][lane * 8 + i] = acc[quarter * 8 + i];
-      __syncthreads();
-      for (int c = threadIdx.x; c < 256; c += blockDim.x) {
-        float s = 0.f;
-        for (int w = 0; w < nw; ++w) s += sg[w][c];
-        atomicAdd(dst + quarter * 256 + c, s);
-      }
-    }
+  __syncthreads();
+  // column c = (i>>3)*256 + lane*8 + (i&7)  <->  (i, lane)
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const int j = c >> 8, l = (c & 255) >> 3, k = c & 7;
+    const int idx = (j * 8 + k) * 32 + l;
+    float a = 0.f, bsum = 0.f;
+    for (int w = 0; w < nw; ++w) { a += sacc[w * (2 * VPL * 32) + idx]; bsum += sacc[w * (2 * VPL * 32) + VPL * 32 + idx]; }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, bsum);
   }
 }
 
@@ -809,7 +826,13 @@ extern "C" int mmsum_add_ln_bwd(const void* d1, const void* d2, const void* res,
                                 int32_t rows, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream) {
   if (d_model != D || rows <= 0 || !d1 || !res || !y || !dres || !dy) return MMSUM_ERR_INVALID;
   if (p_drop > 0.f && dres == dy) return MMSUM_ERR_INVALID;
-  add_ln_bwd_kernel<<<nblocks(rows, 8 * 4, 148 * 4), 256, 0, STREAM(stream)>>>(
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(add_ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2 * VPL * 32 * 4);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  add_ln_bwd_kernel<<<nblocks(rows, 4 * 4, 148 * 3), 128, 4 * 2 * VPL * 32 * 4, STREAM(stream)>>>(
       reinterpret_cast<const bf16*>(d1), reinterpret_cast<const bf16*>(d2), reinterpret_cast<const bf16*>(res),
       reinterpret_cast<const bf16*>(y), gamma, mean, rstd, reinterpret_cast<bf16*>(dres), reinterpret_cast<bf16*>(dy),
       dgamma, dbeta, rows, make_drop(p_drop, seed, stream_id));
