@@ -23,7 +23,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TFLOP_PER_BUSINESS = 4.187   # algorithmic fwd+bwd FLOPs per Yelp business, SURVEY.md §8(d) / App. C
+TFLOP_PER_BUSINESS = 4.187   # algorithmic fwd+bwd FLOPs per Yelp business, SURVEY.md §8(d) / App. C (Amazon: 3.640)
 METRIC = "train businesses/sec (BART-large, Yelp shape)"
 
 
@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--businesses", type=int, default=16, help="businesses per GPU (BASELINE config 2: 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dataset", default="yelp", choices=["yelp", "amazon"],
+                    help="yelp = BASELINE configs[1-2] (headline); amazon = configs[3] shape (133 table fields, 1 image, 70 valid tokens)")
     ap.add_argument("--cpu-seconds", type=float, default=240.0, help="time budget of the reference arm")
     return ap.parse_args()
 
@@ -152,7 +154,7 @@ def run_b200(args):
     import torch.distributed as dist
     from multimodalsum_b200 import ops
     from multimodalsum_b200.dp import GradAllReducer
-    from multimodalsum_b200.modules import MultimodalSum, YelpTableEncoder
+    from multimodalsum_b200.modules import AmazonTableEncoder, MultimodalSum, YelpTableEncoder
     from multimodalsum_b200.optim import get_optimizer
     from multimodalsum_b200.synth import ModelConfig, make_batch
 
@@ -166,12 +168,14 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group(backend="nccl", init_method="env://", device_id=dev)
     B = args.businesses
-    cfg = ModelConfig(dataset="yelp", dropout=0.1)
+    amazon = args.dataset == "amazon"
+    cfg = ModelConfig(dataset=args.dataset, dropout=0.1)
     torch.manual_seed(0)                                   # identical random-init bart-large weights on every rank
-    model = MultimodalSum(TableEncoder=YelpTableEncoder, config=cfg, label_smoothing=0.1).to(dev).train()
+    model = MultimodalSum(TableEncoder=AmazonTableEncoder if amazon else YelpTableEncoder, config=cfg, label_smoothing=0.1).to(dev).train()
     # distinct synthetic shards per rank (businesses are independent units: weak scaling, no data-path collective)
     n_host_batches = 2
-    host = [make_batch(cfg, B, seed=1234 + rank * 17 + i, fixed_len=100, n_valid_imgs=10).pin() for i in range(n_host_batches)]
+    host = [make_batch(cfg, B, seed=1234 + rank * 17 + i, fixed_len=70 if amazon else 100, n_valid_imgs=1 if amazon else 10).pin()
+            for i in range(n_host_batches)]
     resident = host[0].to(dev)
     h2d_bytes = host[0].nbytes()
 
@@ -280,24 +284,25 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     peaks = load_peaks()
+    tfb = 3.640 if amazon else TFLOP_PER_BUSINESS
     achieved_tf = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": "businesses/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: Yelp-shape multimodal_train step (fwd + bwd%s + fused clip/AdamW), BART-large random init" % (
+        "config": {"workload": ("BASELINE configs[3] shape: Amazon-shape multimodal_train step" if amazon else "BASELINE configs[1]: Yelp-shape multimodal_train step") + "  (fwd + bwd%s + fused clip/AdamW), BART-large random init" % (
                        " + bucketed NCCL grad all-reduce overlapped with backward" if world > 1 else ""),
-                   "businesses_per_gpu": B, "reviews": 9, "frame": 128, "valid_tokens": 100, "table_fields": 47,
-                   "images": "10x196", "dropout": 0.1, "label_smoothing": 0.1, "parallelism": "dp%d" % world,
+                   "businesses_per_gpu": B, "reviews": 9, "frame": 128, "valid_tokens": 70 if amazon else 100,
+                   "table_fields": 133 if amazon else 47, "images": "1x196" if amazon else "10x196", "dropout": 0.1, "label_smoothing": 0.1, "parallelism": "dp%d" % world,
                    "l2_policy": "per-step working set (>25 GB activations + 2.8 GB weights) exceeds the 126 MB L2",
                    "final_loss": final_loss},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "businesses/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
-        "tc_fraction_step": {"algorithmic_tflop_per_business": TFLOP_PER_BUSINESS,
-                             "achieved_tflops_per_gpu": value / world * TFLOP_PER_BUSINESS,
-                             "frac_of_sustained_peak": value / world * TFLOP_PER_BUSINESS / peaks["tf_sustained"]},
+        "tc_fraction_step": {"algorithmic_tflop_per_business": tfb,
+                             "achieved_tflops_per_gpu": value / world * tfb,
+                             "frac_of_sustained_peak": value / world * tfb / peaks["tf_sustained"]},
         "roofline": {"kernel": "gemm_tcgen05_kernel (all %d GEMM launches of the timed steps)" % n_gemm, "bound": "tensor",
                      "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": achieved_tf / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",

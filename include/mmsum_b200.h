@@ -55,12 +55,14 @@ int mmsum_gemm_bf16(const MmsumGemmArgs* args, void* stream);
  * and the backward autograd derives from them.  128 query positions per sequence, head_dim 64.
  * Query sequence `qseq` belongs to business `qseq / R` and is leave-one-out target `qseq % R`. */
 typedef struct MmsumAttnMod {
-  int64_t kv_row_base; /* first KV row of this modality; entity (biz,e) starts at kv_row_base + (biz*E+e)*Sk */
+  int64_t kv_row_base; /* first KV row of this modality; entity (biz,e) starts at kv_row_base + (biz*E+e)*ent_stride */
   int64_t o_off;       /* element offset of this modality's [n_qseq*128, ldo] output (fwd) / upstream grad (bwd) */
   int32_t E;           /* entities per business */
   int32_t Sk;          /* keys per entity */
   int32_t loo;         /* 1: entity e is skipped for target e */
   int32_t ent_base;    /* index of entity 0 of this modality in the [.., E_total] arrays */
+  int32_t ent_stride;  /* KV rows between consecutive entities (0 = Sk); > Sk when entity frames are padded */
+  int32_t reserved;
 } MmsumAttnMod;
 
 typedef struct MmsumAttnArgs {

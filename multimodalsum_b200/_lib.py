@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 class AttnMod(C.Structure):
     _fields_ = [("kv_row_base", C.c_int64), ("o_off", C.c_int64), ("E", C.c_int32), ("Sk", C.c_int32),
-                ("loo", C.c_int32), ("ent_base", C.c_int32)]
+                ("loo", C.c_int32), ("ent_base", C.c_int32), ("ent_stride", C.c_int32), ("reserved", C.c_int32)]
 
 
 class AttnArgs(C.Structure):

@@ -125,7 +125,7 @@ __device__ int build_ent_items(const MmsumAttnArgs& p, int qseq, EntItem* items,
     const int ge = md.ent_base + e;
     ok = !(md.loo && e == tgt);
     if (ok && p.ent_valid != nullptr) ok = p.ent_valid[(long long)biz * p.E_total + ge] != 0;
-    it.kv_row0 = (int)(md.kv_row_base + ((long long)biz * md.E + e) * md.Sk);
+    it.kv_row0 = (int)(md.kv_row_base + ((long long)biz * md.E + e) * (md.ent_stride > 0 ? md.ent_stride : md.Sk));
     it.nkeys = md.Sk;
     it.n16 = (md.Sk + 15) & ~15;
     it.mod = (short)m; it.ent = (short)ge;
@@ -704,7 +704,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
   const int ge = md.ent_base + e;
   const int key0 = tile * SQ;
   const int nkeys = min(SQ, md.Sk - key0);
-  const int kvrow0 = (int)(md.kv_row_base + ((long long)biz * md.E + e) * md.Sk) + key0;
+  const int kvrow0 = (int)(md.kv_row_base + ((long long)biz * md.E + e) * (md.ent_stride > 0 ? md.ent_stride : md.Sk)) + key0;
   const bool ent_ok = (p.ent_valid == nullptr) || (p.ent_valid[(long long)biz * p.E_total + ge] != 0);
   bf16* dKV = reinterpret_cast<bf16*>(p.dKV);
 
@@ -913,6 +913,7 @@ static int validate_tc(const MmsumAttnArgs* a, bool bwd) {
   int ents = 0;
   for (int m = 0; m < a->n_mod; ++m) {
     if (a->mods[m].E <= 0 || a->mods[m].Sk <= 0 || a->mods[m].Sk > kMaxKeys) return MMSUM_ERR_INVALID;
+    if (a->mods[m].ent_stride != 0 && a->mods[m].ent_stride < a->mods[m].Sk) return MMSUM_ERR_INVALID;
     ents += a->mods[m].E;
     if (a->mods[m].o_off % a->ldo) return MMSUM_ERR_INVALID;
   }
@@ -932,7 +933,7 @@ static int build_maps(const MmsumAttnArgs* a, AttnMaps* mp, bool bwd) {
   if (rc) return rc;
   for (int m = 0; m < 3; ++m) {
     const MmsumAttnMod& md = a->mods[m < a->n_mod ? m : 0];
-    const uint64_t rows = (uint64_t)md.kv_row_base + (uint64_t)n_biz * md.E * md.Sk;
+    const uint64_t rows = (uint64_t)md.kv_row_base + (uint64_t)n_biz * md.E * (md.ent_stride > 0 ? md.ent_stride : md.Sk);
     rc = make_tmap(&mp->kv[m], a->KV, 0, (uint64_t)a->ldkv, rows, (uint64_t)a->ldkv * 2, 64, (uint32_t)md.Sk);
     if (rc) return rc;
   }
@@ -980,7 +981,7 @@ extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
   uint64_t kvrows = 0;
   int tiles = 0;
   for (int m = 0; m < a->n_mod; ++m) {
-    const uint64_t r = (uint64_t)a->mods[m].kv_row_base + (uint64_t)n_biz * a->mods[m].E * a->mods[m].Sk;
+    const uint64_t r = (uint64_t)a->mods[m].kv_row_base + (uint64_t)n_biz * a->mods[m].E * (a->mods[m].ent_stride > 0 ? a->mods[m].ent_stride : a->mods[m].Sk);
     if (r > kvrows) kvrows = r;
     tiles += a->mods[m].E * ((a->mods[m].Sk + SQ - 1) / SQ);
   }

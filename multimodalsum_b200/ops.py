@@ -184,7 +184,8 @@ def attn_args(**kw):
         setattr(a, k, v)
     a.n_mod = len(mods)
     for i, m in enumerate(mods):
-        a.mods[i].kv_row_base, a.mods[i].o_off, a.mods[i].E, a.mods[i].Sk, a.mods[i].loo, a.mods[i].ent_base = m
+        a.mods[i].kv_row_base, a.mods[i].o_off, a.mods[i].E, a.mods[i].Sk, a.mods[i].loo, a.mods[i].ent_base = m[:6]
+        a.mods[i].ent_stride = m[6] if len(m) > 6 else 0
     return a
 
 

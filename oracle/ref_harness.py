@@ -149,3 +149,19 @@ def reference_text_step(cfg, state_dict, batch, dtype=torch.float32, label_smoot
     loss.backward()
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
     return loss.detach(), grads, model
+
+
+def reference_generate(cfg, state_dict, batch, num_beams=4, max_length=20, length_penalty=1.0, no_repeat_ngram_size=3,
+                       early_stopping=True, dtype=torch.float32):
+    """BASELINE config 5: the reference's own generation path, as src/test.py:152-158 drives it —
+    get_multimodal_outputs (no_grad), rating_diff = 0, bart_model.generate(beam search)."""
+    model = build_reference_model(cfg, state_dict, dtype=dtype)
+    model.eval()
+    with torch.no_grad():
+        _, th, tm, tabh, tabm, ih, im = model.get_multimodal_outputs(batch.reviews, batch.reviews_mask, batch.field, batch.field_value,
+                                                                       batch.img.to(dtype), batch.img_mask)
+        rating_diff = torch.zeros([th.size(0), 1], dtype=dtype)
+        out = model.bart_model.generate(th, tm, tabh, tabm, ih, im, rating_diff=rating_diff, num_beams=num_beams,
+                                        length_penalty=length_penalty, max_length=max_length,
+                                        no_repeat_ngram_size=no_repeat_ngram_size, early_stopping=early_stopping)
+    return out

@@ -35,6 +35,31 @@ CASES = {
 }
 
 
+GEN_CFG = dict(encoder_layers=2, decoder_layers=2, ffn_dim=256, vocab_size=512, max_position_embeddings=256, dropout=0.0,
+               dataset="yelp", init_std=0.08)
+GEN_CASES = {
+    # name: (cfg kwargs, state-dict kwargs, batch kwargs, generate kwargs) — BASELINE config 5 semantics at toy size
+    "gen_small_yelp_s128": (GEN_CFG, dict(seed=21, gates_open=True), dict(B=3, seed=31, n_reviews=3, max_imgs=2, seq_len=128, len_range=(68, 118)),
+                            dict(num_beams=4, max_length=24, length_penalty=1.0, no_repeat_ngram_size=3, early_stopping=True)),
+    "gen_small_yelp_s150": (GEN_CFG, dict(seed=21, gates_open=True), dict(B=3, seed=32, n_reviews=3, max_imgs=2, seq_len=150, len_range=(90, 140)),
+                            dict(num_beams=4, max_length=24, length_penalty=1.0, no_repeat_ngram_size=3, early_stopping=True)),
+}
+
+
+def make_generation_goldens():
+    for name, (ck, sk, bk, gk) in GEN_CASES.items():
+        t0 = time.time()
+        cfg = ModelConfig(**ck)
+        sd = make_state_dict(cfg, **sk)
+        bk2 = dict(bk)
+        batch = make_batch(cfg, bk2.pop("B"), **bk2)
+        out = RH.reference_generate(cfg, sd, batch, **gk)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"),
+                            case=json.dumps(dict(name=name, cfg=ck, sd=sk, batch=bk, gen=gk, torch=torch.__version__, ref_dtype="float32")),
+                            tokens=out.numpy())
+        print("%s: tokens %s, %.1fs" % (name, tuple(out.shape), time.time() - t0), flush=True)
+
+
 def build_case(name):
     ck, sk, bk = CASES[name]
     cfg = ModelConfig(**ck)
@@ -70,4 +95,8 @@ def main(which):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "all")
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "gen"):
+        make_generation_goldens()
+    if which != "gen":
+        main(which)
