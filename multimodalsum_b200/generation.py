@@ -228,92 +228,99 @@ class Generator:
         g(last, eng.w16(bm + "shared.weight"), w["logits"], bias=eng.w32_flb())
         return w["logits"]
 
-    # ------------------------------------------------------------------ beam search (:2803-3067)
+    # ------------------------------------------------------------------ public entry point (src/test.py:152-158)
     @torch.no_grad()
     def generate(self, reviews, reviews_mask, field, field_value, img, img_mask, rating_diff=None, num_beams=4, max_length=20,
                  min_length=0, length_penalty=1.0, no_repeat_ngram_size=3, early_stopping=True):
         cfg = self.model.cfg
-        dev = reviews.device
         B = reviews.shape[0]
-        V = cfg.vocab_size
-        pad, bos, eos = cfg.pad_token_id, cfg.bos_token_id, cfg.eos_token_id
         st = self.encode(reviews, reviews_mask, field, field_value, img, img_mask, num_beams)
-        N = B * num_beams
-        rd = torch.zeros(B, device=dev) if rating_diff is None else rating_diff.reshape(B).float()
+        rd = torch.zeros(B, device=reviews.device) if rating_diff is None else rating_diff.reshape(B).float()
         rd = rd.repeat_interleave(num_beams).contiguous()
-        input_ids = torch.full((N, 1), eos, dtype=torch.long, device=dev)     # decoder_start_token_id = 2 (cfg/bart-large.json)
-        hyps = [BeamHypotheses(num_beams, max_length, length_penalty, early_stopping) for _ in range(B)]
-        beam_scores = torch.zeros(B, num_beams, device=dev)
-        beam_scores[:, 1:] = -1e9
-        beam_scores = beam_scores.view(-1)
-        done = [False] * B
-        cur_len = 1
-        next_scores = next_tokens = None
-        while cur_len < max_length:
-            logits = self.last_logits(st, input_ids, rd).clone()
-            # adjust_logits_during_generation (:3084-3089)
-            if cur_len == 1:
-                keep = logits[:, bos].clone(); logits.fill_(float("-inf")); logits[:, bos] = keep
-            if cur_len == max_length - 1:
-                keep = logits[:, eos].clone(); logits.fill_(float("-inf")); logits[:, eos] = keep
-            scores = torch.log_softmax(logits, dim=-1)
-            # postprocess_next_token_scores (generation_utils.py:57-99)
-            if cur_len < min_length:
-                scores[:, eos] = float("-inf")
-            ids_host = input_ids.tolist()
-            if no_repeat_ngram_size > 0:
-                for i, banned in enumerate(calc_banned_ngram_tokens(ids_host, N, no_repeat_ngram_size, cur_len)):
-                    if banned:
-                        scores[i, banned] = float("-inf")
-            nxt = (scores + beam_scores[:, None]).view(B, num_beams * V)
-            next_scores, next_tokens = torch.topk(nxt, 2 * num_beams, dim=1, largest=True, sorted=True)
-            ns_host, nt_host = next_scores.tolist(), next_tokens.tolist()
-            next_batch_beam = []
-            for b in range(B):
-                if done[b]:
-                    next_batch_beam.extend([(0.0, pad, 0)] * num_beams)
-                    continue
-                sent = []
-                for rank, (tok_id, tok_score) in enumerate(zip(nt_host[b], ns_host[b])):
-                    beam_id, token_id = tok_id // V, tok_id % V
-                    eff = b * num_beams + beam_id
-                    if token_id == eos:
-                        if rank >= num_beams:
-                            continue
-                        hyps[b].add(list(ids_host[eff]), tok_score)
-                    else:
-                        sent.append((tok_score, token_id, eff))
-                    if len(sent) == num_beams:
-                        break
-                done[b] = done[b] or hyps[b].is_done(max(ns_host[b]), cur_len)
-                assert len(sent) == num_beams, "Beam should always be full"
-                next_batch_beam.extend(sent)
-            if all(done):
-                break
-            beam_scores = torch.tensor([x[0] for x in next_batch_beam], device=dev, dtype=torch.float32)
-            beam_tokens = torch.tensor([x[1] for x in next_batch_beam], device=dev, dtype=torch.long)
-            beam_idx = torch.tensor([x[2] for x in next_batch_beam], device=dev, dtype=torch.long)
-            input_ids = torch.cat([input_ids[beam_idx, :], beam_tokens.unsqueeze(1)], dim=-1)
-            cur_len += 1
-            # (the reference re-gathers memories / caches with beam_idx here; the un-expanded per-business memory and the
-            #  prefix recompute make that unnecessary: beam_idx never crosses businesses, :2957)
+        return beam_search(lambda ids: self.last_logits(st, ids, rd), B, cfg.vocab_size, reviews.device, num_beams=num_beams,
+                           max_length=max_length, min_length=min_length, length_penalty=length_penalty,
+                           no_repeat_ngram_size=no_repeat_ngram_size, early_stopping=early_stopping, pad=cfg.pad_token_id,
+                           bos=cfg.bos_token_id, eos=cfg.eos_token_id)
+
+
+def beam_search(logits_fn, B, V, dev, num_beams=4, max_length=20, min_length=0, length_penalty=1.0, no_repeat_ngram_size=3,
+                early_stopping=True, pad=1, bos=0, eos=2):
+    """_generate_beam_search (modeling_multimodalsum.py:2803-3067), do_sample=False.  `logits_fn(input_ids[N, cur_len])`
+    returns the fp32 next-token logits [N, V] of the last position (N = B*num_beams, beams of a business adjacent)."""
+    N = B * num_beams
+    input_ids = torch.full((N, 1), eos, dtype=torch.long, device=dev)     # decoder_start_token_id = 2 (cfg/bart-large.json)
+    hyps = [BeamHypotheses(num_beams, max_length, length_penalty, early_stopping) for _ in range(B)]
+    beam_scores = torch.zeros(B, num_beams, device=dev)
+    beam_scores[:, 1:] = -1e9
+    beam_scores = beam_scores.view(-1)
+    done = [False] * B
+    cur_len = 1
+    next_scores = next_tokens = None
+    while cur_len < max_length:
+        logits = logits_fn(input_ids).clone()
+        # adjust_logits_during_generation (:3084-3089)
+        if cur_len == 1:
+            keep = logits[:, bos].clone(); logits.fill_(float("-inf")); logits[:, bos] = keep
+        if cur_len == max_length - 1:
+            keep = logits[:, eos].clone(); logits.fill_(float("-inf")); logits[:, eos] = keep
+        scores = torch.log_softmax(logits, dim=-1)
+        # postprocess_next_token_scores (generation_utils.py:57-99)
+        if cur_len < min_length:
+            scores[:, eos] = float("-inf")
         ids_host = input_ids.tolist()
-        bs_host = beam_scores.tolist()
+        if no_repeat_ngram_size > 0:
+            for i, banned in enumerate(calc_banned_ngram_tokens(ids_host, N, no_repeat_ngram_size, cur_len)):
+                if banned:
+                    scores[i, banned] = float("-inf")
+        nxt = (scores + beam_scores[:, None]).view(B, num_beams * V)
+        next_scores, next_tokens = torch.topk(nxt, 2 * num_beams, dim=1, largest=True, sorted=True)
+        ns_host, nt_host = next_scores.tolist(), next_tokens.tolist()
+        next_batch_beam = []
         for b in range(B):
             if done[b]:
+                next_batch_beam.extend([(0.0, pad, 0)] * num_beams)
                 continue
-            for k in range(num_beams):
-                eff = b * num_beams + k
-                hyps[b].add(list(ids_host[eff]), bs_host[eff])
-        best = [sorted(h.beams, key=lambda x: x[0])[-1][1] for h in hyps]
-        lens = [len(h) for h in best]
-        if min(lens) != max(lens):
-            width = min(max(lens) + 1, max_length)
-            out = torch.full((B, width), pad, dtype=torch.long)
-            for i, h in enumerate(best):
-                out[i, :lens[i]] = torch.tensor(h)
-                if lens[i] < max_length:
-                    out[i, lens[i]] = eos
-        else:
-            out = torch.tensor(best, dtype=torch.long)
-        return out.to(dev)
+            sent = []
+            for rank, (tok_id, tok_score) in enumerate(zip(nt_host[b], ns_host[b])):
+                beam_id, token_id = tok_id // V, tok_id % V
+                eff = b * num_beams + beam_id
+                if token_id == eos:
+                    if rank >= num_beams:
+                        continue
+                    hyps[b].add(list(ids_host[eff]), tok_score)
+                else:
+                    sent.append((tok_score, token_id, eff))
+                if len(sent) == num_beams:
+                    break
+            done[b] = done[b] or hyps[b].is_done(max(ns_host[b]), cur_len)
+            assert len(sent) == num_beams, "Beam should always be full"
+            next_batch_beam.extend(sent)
+        if all(done):
+            break
+        beam_scores = torch.tensor([x[0] for x in next_batch_beam], device=dev, dtype=torch.float32)
+        beam_tokens = torch.tensor([x[1] for x in next_batch_beam], device=dev, dtype=torch.long)
+        beam_idx = torch.tensor([x[2] for x in next_batch_beam], device=dev, dtype=torch.long)
+        input_ids = torch.cat([input_ids[beam_idx, :], beam_tokens.unsqueeze(1)], dim=-1)
+        cur_len += 1
+        # (the reference re-gathers memories / caches with beam_idx here; the un-expanded per-business memory and the
+        #  prefix recompute make that unnecessary: beam_idx never crosses businesses, :2957)
+    ids_host = input_ids.tolist()
+    bs_host = beam_scores.tolist()
+    for b in range(B):
+        if done[b]:
+            continue
+        for k in range(num_beams):
+            eff = b * num_beams + k
+            hyps[b].add(list(ids_host[eff]), bs_host[eff])
+    best = [sorted(h.beams, key=lambda x: x[0])[-1][1] for h in hyps]
+    lens = [len(h) for h in best]
+    if min(lens) != max(lens):
+        width = min(max(lens) + 1, max_length)
+        out = torch.full((B, width), pad, dtype=torch.long)
+        for i, h in enumerate(best):
+            out[i, :lens[i]] = torch.tensor(h)
+            if lens[i] < max_length:
+                out[i, lens[i]] = eos
+    else:
+        out = torch.tensor(best, dtype=torch.long)
+    return out.to(dev)

@@ -111,7 +111,7 @@ def param_shapes(cfg: ModelConfig):
 ALIASES = ("model.encoder.embed_tokens.weight", "model.decoder.embed_tokens.weight", "table_encoder.bart_embedding.weight")
 
 
-def make_state_dict(cfg: ModelConfig, seed=0, perturb=True, gates_open=False):
+def make_state_dict(cfg: ModelConfig, seed=0, perturb=True, gates_open=False, logits_bias_std=0.0):
     """fp32 CPU state_dict with the reference's keys.  `gates_open` = stress init of SURVEY App. G (alpha/beta
     bias +1, weights x5) so table / image branches contribute O(1) to the loss."""
     sd = {}
@@ -121,7 +121,7 @@ def make_state_dict(cfg: ModelConfig, seed=0, perturb=True, gates_open=False):
             sd[name] = shared
             continue
         if name.endswith("final_logits_bias"):
-            sd[name] = torch.zeros(shape)
+            sd[name] = _draw(name, shape, logits_bias_std, 77) if logits_bias_std > 0 else torch.zeros(shape)
         elif "layer_norm" in name or "layernorm_embedding" in name:
             if name.endswith(".weight"):
                 sd[name] = _draw(name, shape, 0.05 if perturb else 0.0, seed, mean=1.0)

@@ -133,13 +133,13 @@ def shift_tokens_right(labels, pad, bos, eos):
     return out
 
 
-def decoder(p, cfg, dec_ids, mems, valids, rating_diff, training=False):
+def decoder(p, cfg, dec_ids, mems, valids, rating_diff, training=False, use_pad_mask=True):
     """BartDecoder.forward :530-660 with DecoderLayer :432-494; mems/valids lists [text, table, img] or a single
     text memory (text-only model).  Returns hidden states [B,T,D]."""
     pre = "bart_model.model.decoder."
     pd = cfg.dropout
     pad_mask = dec_ids.eq(cfg.pad_token_id)
-    key_pad = pad_mask if bool(pad_mask.any()) else None   # make_padding_mask :249-254
+    key_pad = pad_mask if (use_pad_mask and bool(pad_mask.any())) else None   # make_padding_mask :249-254; generation passes no mask (:2253)
     x = _drop(embed(dec_ids, p, pre, rating_diff), pd, training)
     for i in range(cfg.decoder_layers):
         lp = pre + "layers.%d." % i
@@ -294,3 +294,22 @@ def step_loss_and_grads(sd, cfg, batch, label_smoothing=0.1, dtype=torch.float32
     loss.backward()
     grads = {k: t.grad for k, t in leaf.items() if t.grad is not None}
     return loss.detach(), grads, p
+
+
+def generation_logits_fn(p, cfg, batch, num_beams):
+    """Next-token logits for beam search as the reference computes them in `generate` (modeling_multimodalsum.py:2857-2866):
+    memories from get_multimodal_outputs, rating_diff = 0 (src/test.py:155), every beam of a business attends to the same
+    memory, no decoder padding mask.  The reference's incremental cache (:889-920) is a pure optimisation: the logits of the
+    last position over the full prefix are identical, which is what this closure evaluates."""
+    with torch.no_grad():
+        text, text_valid, table, table_valid, img, img_valid = multimodal_memories(p, cfg, batch, training=False)
+        rep = lambda t: t.repeat_interleave(num_beams, dim=0)
+        mems = [rep(text), rep(table), rep(img)]
+        valids = [rep(text_valid), rep(table_valid), rep(img_valid)]
+        rd = torch.zeros(mems[0].shape[0], 1, dtype=text.dtype, device=text.device)
+
+    def fn(input_ids):
+        with torch.no_grad():
+            x = decoder(p, cfg, input_ids, mems, valids, rd, training=False, use_pad_mask=False)
+            return lm_logits(x[:, -1], p).float()
+    return fn

@@ -41,6 +41,10 @@ GEN_CASES = {
     # name: (cfg kwargs, state-dict kwargs, batch kwargs, generate kwargs) — BASELINE config 5 semantics at toy size
     "gen_small_yelp_s128": (GEN_CFG, dict(seed=21, gates_open=True), dict(B=3, seed=31, n_reviews=3, max_imgs=2, seq_len=128, len_range=(68, 118)),
                             dict(num_beams=4, max_length=24, length_penalty=1.0, no_repeat_ngram_size=3, early_stopping=True)),
+    # tie-free variant: a wide random final_logits_bias (seed 77, std 2) separates the candidates by far more than bf16 noise,
+    # so the CUDA path must reproduce the ids exactly
+    "gen_small_yelp_biased": (GEN_CFG, dict(seed=21, gates_open=True, logits_bias_std=2.0), dict(B=3, seed=33, n_reviews=3, max_imgs=2, seq_len=150, len_range=(90, 140)),
+                              dict(num_beams=4, max_length=24, length_penalty=1.0, no_repeat_ngram_size=3, early_stopping=True)),
     "gen_small_yelp_s150": (GEN_CFG, dict(seed=21, gates_open=True), dict(B=3, seed=32, n_reviews=3, max_imgs=2, seq_len=150, len_range=(90, 140)),
                             dict(num_beams=4, max_length=24, length_penalty=1.0, no_repeat_ngram_size=3, early_stopping=True)),
 }

@@ -13,8 +13,7 @@ from multimodalsum_b200.synth import ModelConfig, make_batch, make_state_dict
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["gen_small_yelp_s128", "gen_small_yelp_s150"])
-def test_beam_search_matches_reference_tokens(name):
+def _setup(name):
     from multimodalsum_b200.generation import Generator
     from multimodalsum_b200.modules import MultimodalSum, YelpTableEncoder
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
@@ -26,11 +25,41 @@ def test_beam_search_matches_reference_tokens(name):
     model = MultimodalSum(TableEncoder=YelpTableEncoder, config=cfg)
     model.load_state_dict(sd, strict=False)
     model = model.cuda().eval()
-    gen = Generator(model)
-    out = gen.generate(batch.reviews, batch.reviews_mask, batch.field, batch.field_value, batch.img, batch.img_mask, **case["gen"])
-    ref = torch.from_numpy(z["tokens"])
-    assert tuple(out.shape) == tuple(ref.shape), (out.shape, ref.shape)
+    return Generator(model), cfg, sd, batch, case["gen"], torch.from_numpy(z["tokens"])
+
+
+def test_beam_search_exact_ids_on_tie_free_case():
+    """Wide logit bias -> candidates separated by far more than bf16 noise: generated ids must equal the reference's."""
+    gen, cfg, sd, batch, gk, ref = _setup("gen_small_yelp_biased")
+    out = gen.generate(batch.reviews, batch.reviews_mask, batch.field, batch.field_value, batch.img, batch.img_mask, **gk)
     assert torch.equal(out.cpu(), ref), (out.cpu().tolist(), ref.tolist())
+
+
+@pytest.mark.parametrize("name", ["gen_small_yelp_s128", "gen_small_yelp_s150"])
+def test_teacher_forced_next_token_logits(name):
+    """Per-step log-probabilities along the reference's own generated sequences (teacher forcing), CUDA vs fp32 oracle:
+    max |delta log p| over the vocabulary <= 0.05 nats, and the arg-max token agrees wherever the oracle's top-2 margin
+    exceeds 0.1 nats (tie-free positions).  Frames of 128 and 150 review tokens (two encoder query tiles)."""
+    from oracle import mmsum_oracle as OR
+    gen, cfg, sd, batch, gk, ref = _setup(name)
+    p = {k: v.cuda() for k, v in sd.items()}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ofn = OR.generation_logits_fn(p, cfg, batch, 1)
+    st = gen.encode(batch.reviews, batch.reviews_mask, batch.field, batch.field_value, batch.img, batch.img_mask, 1)
+    rd = torch.zeros(batch.reviews.shape[0], device="cuda")
+    ref = ref.cuda()
+    worst, checked = 0.0, 0
+    for cur in range(1, ref.shape[1]):
+        ids = ref[:, :cur].contiguous()
+        lc = torch.log_softmax(gen.last_logits(st, ids, rd).float(), -1)
+        lo = torch.log_softmax(ofn(ids), -1)
+        worst = max(worst, (lc - lo).abs().max().item())
+        top2 = lo.topk(2, dim=-1).values
+        tie_free = (top2[:, 0] - top2[:, 1]) > 0.1
+        assert torch.equal(lc.argmax(-1)[tie_free], lo.argmax(-1)[tie_free])
+        checked += int(tie_free.sum())
+    assert worst <= 0.05, worst
+    assert checked > 0
 
 
 def test_ngram_blocking_and_hypothesis_heap_host_logic():
