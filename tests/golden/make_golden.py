@@ -36,7 +36,7 @@ CASES = {
 
 
 GEN_CFG = dict(encoder_layers=2, decoder_layers=2, ffn_dim=256, vocab_size=512, max_position_embeddings=256, dropout=0.0,
-               dataset="yelp", init_std=0.08)
+               dataset="yelp")
 GEN_CASES = {
     # name: (cfg kwargs, state-dict kwargs, batch kwargs, generate kwargs) — BASELINE config 5 semantics at toy size
     "gen_small_yelp_s128": (GEN_CFG, dict(seed=21, gates_open=True), dict(B=3, seed=31, n_reviews=3, max_imgs=2, seq_len=128, len_range=(68, 118)),
