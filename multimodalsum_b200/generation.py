@@ -184,7 +184,7 @@ class Generator:
             st["ws"] = dict(x=bf(T, D), x1=bf(T, D), x2=bf(T, D), nxt=bf(T, D), qkv=bf(T, 3 * D), ctx=bf(T, D), o=bf(T, D), qc=bf(T, D),
                             A3=bf(3, T, D), O3=bf(3, T, D), U=bf(2, T, D), AB=bf(2, T, D), yc=bf(T, D), a=bf(T, cfg.ffn_dim), f=bf(T, D),
                             mean=f32(T), rstd=f32(T), lse=f32(N, H, 1, S), lse_c=f32(N, H, Et, S),
-                            ids=torch.ones(N, S, device=dev, dtype=torch.int32), logits=f32(N, V))
+                            ids=torch.ones(N, S, device=dev, dtype=torch.int32), logits=f32(N, (V + 3) // 4 * 4)[:, :V])   # 16-byte row pitch for TMA
         w = st["ws"]
         g = ops.gemm
         bm = "bart_model.model."
