@@ -590,10 +590,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           tmem_ld_32x32(tmem + lane_off + kColS0 + c * 32, rs);
           tmem_ld_32x32(tmem + lane_off + kColDP + c * 32, rd);
           tmem_ld_wait();
+          const bool full = (wd[t] == 0xffffffffu);
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const float p0 = ((wd[t] >> j) & 1u) ? ex2(fmaf(__uint_as_float(rs[j]), sc, -lse)) : 0.f;
-            const float p1 = ((wd[t] >> (j + 1)) & 1u) ? ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse)) : 0.f;
+            float p0 = ex2(fmaf(__uint_as_float(rs[j]), sc, -lse));
+            float p1 = ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse));
+            if (!full) { p0 = ((wd[t] >> j) & 1u) ? p0 : 0.f; p1 = ((wd[t] >> (j + 1)) & 1u) ? p1 : 0.f; }
             dl4[(j >> 1) & 3] = fmaf(p0, __uint_as_float(rd[j]), dl4[(j >> 1) & 3]);
             dl4[(j >> 1) & 3] = fmaf(p1, __uint_as_float(rd[j + 1]), dl4[(j >> 1) & 3]);
             pp[t][j >> 1] = pack_bf16(p0, p1);
@@ -608,6 +610,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       if (i > 0) mbar_wait(&sm.ds_free, (i - 1) & 1);   // dQ MMA of the previous entity has consumed the dS tile
       // pass 2: dS = scale*inv_n * P o (dP' - delta') -> bf16 A-operand tile
       const float wgt = p.scale * inv_n;
+      const float dw = delta * wgt;   // dS = P * (wgt*dP' - wgt*delta')
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (has[t]) {
@@ -623,7 +626,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
             for (int e = 0; e < 4; ++e) {
               const float2 pr = unpack_bf16(pp[t][g8 * 4 + e]);
               const int j = g8 * 8 + 2 * e;
-              o[e] = pack_bf16(wgt * pr.x * (__uint_as_float(rd[j]) - delta), wgt * pr.y * (__uint_as_float(rd[j + 1]) - delta));
+              o[e] = pack_bf16(pr.x * fmaf(__uint_as_float(rd[j]), wgt, -dw), pr.y * fmaf(__uint_as_float(rd[j + 1]), wgt, -dw));
             }
             const int chunk = (c & 1) * 4 + g8;
             *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -775,7 +778,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
       auto issue_sdp = [&](int s) {
         const int st = s & 1;
         mbar_wait(&sm.qd_full[st], (s >> 1) & 1);
+        if (lane == 0) TRACE(5, 4 * s);
         mbar_wait(&sm.sdp_empty, (s & 1) ^ 1);
+        if (lane == 0) TRACE(5, 4 * s + 1);
         tc_fence_after();
         const uint64_t qd = st ? qdesc_k[1] : qdesc_k[0], dd = st ? dadesc_k[1] : dadesc_k[0];
 #pragma unroll
@@ -791,6 +796,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
         if (s + 1 < n_steps) issue_sdp(s + 1);
         const int st = s & 1;
         mbar_wait(&sm.pds_full, s & 1);
+        if (lane == 0) TRACE(5, 4 * s + 2);
         tc_fence_after();
         const uint64_t qd = st ? qdesc_mn[1] : qdesc_mn[0], dd = st ? dadesc_mn[1] : dadesc_mn[0];
 #pragma unroll
@@ -801,6 +807,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
         for (int kk = 0; kk < 8; ++kk)
           umma_bf16_w(tmem + kColDK, desc_adv(dstdesc, (kk >> 2) * (SQ * 128) + (kk & 3) * 32), desc_adv(qd, kk * 2048), idesc_o,
                     (s > 0 || kk > 0) ? 1u : 0u);
+        if (lane == 0) TRACE(5, 4 * s + 3);
         umma_commit_w(&sm.qd_empty[st]);
         umma_commit_w(&sm.pds_free);
       }
@@ -824,25 +831,38 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
     auto lse_index = [&](int s) {
       return (((long long)(biz * p.R + step_target(s)) * p.H + h) * p.E_total + ge) * SQ + (sw * 32 + lane);
     };
-    if (sw < 4) {  // stage LSE / DELTA of the first target's 128 query rows
-      sm.lse[0][sw * 32 + lane] = p.LSE[lse_index(0)];
-      sm.dlt[0][sw * 32 + lane] = p.DELTA[lse_index(0)];
+    // staged per target: lse' = LSE - log2(inv_n)  (so P already carries 1/n) and dl' = scale * delta'
+    auto stage_vals = [&](int s, float& l, float& d) {
+      const int qs = biz * p.R + step_target(s);
+      const float inv_n = p.inv_n ? p.inv_n[(long long)qs * p.n_mod + m] : 1.f;
+      l = p.LSE[lse_index(s)] - __log2f(inv_n);
+      d = p.DELTA[lse_index(s)] * p.scale;
+    };
+    if (sw < 4) {
+      float l, d;
+      stage_vals(0, l, d);
+      sm.lse[0][sw * 32 + lane] = l;
+      sm.dlt[0][sw * 32 + lane] = d;
     }
     for (int s = 0; s < n_steps; ++s) {
       const int st = s & 1;
-      const int qseq = biz * p.R + step_target(s);
-      const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + m] : 1.f;
+      if (threadIdx.x == 64) TRACE(6, 6 * s);
       soft_bar();   // stage st is visible; everybody is done with stage st^1 (read during step s-1)
+      if (threadIdx.x == 64) TRACE(6, 6 * s + 1);
       float l_next = 0.f, d_next = 0.f;
       const bool stage_next = (sw < 4) && (s + 1 < n_steps);
-      if (stage_next) { l_next = p.LSE[lse_index(s + 1)]; d_next = p.DELTA[lse_index(s + 1)]; }   // in flight during this step
+      if (stage_next) stage_vals(s + 1, l_next, d_next);   // loads in flight during this step
       mbar_wait(&sm.sdp_full, s & 1);
+      if (threadIdx.x == 64) TRACE(6, 6 * s + 2);
       tc_fence_after();
       uint32_t rs[32], rd[32];
       tmem_ld_32x32(tmem + lane_off + kColST + cg * 32, rs);
       tmem_ld_32x32(tmem + lane_off + kColDPT + cg * 32, rd);
       tmem_ld_wait();
+      if (threadIdx.x == 64) TRACE(6, 6 * s + 3);
       if (s > 0) mbar_wait(&sm.pds_free, (s - 1) & 1);
+      if (threadIdx.x == 64) TRACE(6, 6 * s + 4);
+      const bool full = (wd == 0xffffffffu);
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {
         uint32_t po[4], dso[4];
@@ -855,17 +875,19 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
           const int j = g8 * 8 + 2 * e2;
-          const float p0 = ((wd >> j) & 1u) ? inv_n * ex2(fmaf(__uint_as_float(rs[j]), sc, -ls[2 * e2])) : 0.f;
-          const float p1 = ((wd >> (j + 1)) & 1u) ? inv_n * ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -ls[2 * e2 + 1])) : 0.f;
+          float p0 = ex2(fmaf(__uint_as_float(rs[j]), sc, -ls[2 * e2]));
+          float p1 = ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -ls[2 * e2 + 1]));
+          if (!full) { p0 = ((wd >> j) & 1u) ? p0 : 0.f; p1 = ((wd >> (j + 1)) & 1u) ? p1 : 0.f; }
           po[e2] = pack_bf16(p0, p1);
-          dso[e2] = pack_bf16(p.scale * p0 * (__uint_as_float(rd[j]) - dl[2 * e2]),
-                              p.scale * p1 * (__uint_as_float(rd[j + 1]) - dl[2 * e2 + 1]));
+          dso[e2] = pack_bf16(p0 * fmaf(__uint_as_float(rd[j]), p.scale, -dl[2 * e2]),
+                              p1 * fmaf(__uint_as_float(rd[j + 1]), p.scale, -dl[2 * e2 + 1]));
         }
         const int chunk = (cg & 1) * 4 + g8;
         *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[0], po[1], po[2], po[3]);
         *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
       }
       if (stage_next) { sm.lse[st ^ 1][sw * 32 + lane] = l_next; sm.dlt[st ^ 1][sw * 32 + lane] = d_next; }
+      if (threadIdx.x == 64) TRACE(6, 6 * s + 5);
       tc_fence_before();
       mbar_arrive(&sm.sdp_empty);
       fence_proxy_async_smem();
