@@ -20,6 +20,7 @@
 //   warp 1    MMA issuer:   S_e = Q K_e^T -> TMEM (double buffered);  O_e = P_e V_e -> TMEM
 //   warps 2-5 softmax:      thread = query row; tcgen05.ld S, max, exp2, bf16 P -> swizzled smem (A operand of P V);
 //                           reads O_e back and accumulates (1/n)(1/l_e) O_e in registers; writes the modality outputs
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/mmsum_b200.h"
 
@@ -437,7 +438,7 @@ struct BwdQSmem {
   float red_delta[2][4][SQ];
   uint32_t kmask[kMaxEnt][8];
   EntItem items[kMaxEnt];
-  uint64_t q_full, da_full, da_free, k_full[2], k_empty[2], v_full[2], v_empty[2], sdp_full, sdp_empty, ds_full, ds_free;
+  uint64_t q_full, da_full, da_free, k_full[2], k_empty[2], v_full[2], v_empty[2], sdp_full, s_empty, dp_empty, ds_full, ds_free;
   uint32_t tmem_slot;
   int n_items;
 };
@@ -465,7 +466,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1);
       mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1);
     }
-    mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, kSoftThreads);
+    mbar_init(&sm.sdp_full, 1); mbar_init(&sm.s_empty, kSoftThreads); mbar_init(&sm.dp_empty, kSoftThreads);
     mbar_init(&sm.ds_full, kSoftThreads); mbar_init(&sm.ds_free, 1);
     fence_barrier_init();
   }
@@ -522,14 +523,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         const EntItem it = sm.items[i];
         if (it.mod != cur_mod) { mbar_wait(&sm.da_full, n_da & 1); cur_mod = it.mod; ++n_da; }
         mbar_wait(&sm.k_full[st], (i >> 1) & 1);
-        mbar_wait(&sm.v_full[st], (i >> 1) & 1);
-        mbar_wait(&sm.sdp_empty, (i & 1) ^ 1);
+        // the S columns are handed back after pass 1 of the previous entity, the dP' columns once pass 2 has
+        // re-read them: both products of entity i+1 overlap the softmax work of entity i
+        mbar_wait(&sm.s_empty, (i & 1) ^ 1);
         tc_fence_after();
         const uint32_t idesc = umma_idesc_bf16(128, it.n16, 0, 0);
         const uint64_t kd = st ? kdesc_k[1] : kdesc_k[0], vd = st ? vdesc_k[1] : vdesc_k[0];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16_w(tmem + kColS0, desc_adv(qdesc, kk * 32), desc_adv(kd, kk * 32), idesc, kk > 0);
+        mbar_wait(&sm.v_full[st], (i >> 1) & 1);
+        mbar_wait(&sm.dp_empty, (i & 1) ^ 1);
+        tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16_w(tmem + kColDP, desc_adv(dadesc, kk * 32), desc_adv(vd, kk * 32), idesc, kk > 0);
@@ -580,61 +585,106 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       mbar_wait(&sm.sdp_full, i & 1);
       tc_fence_after();
       // pass 1: P = exp2(sc*S - LSE) (stashed as packed bf16), partial delta' = sum P o dP'
-      uint32_t pp[2][16];
-      float dl4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (has[t]) {
-          const int c = cg + 4 * t;
-          uint32_t rs[32], rd[32];
-          tmem_ld_32x32(tmem + lane_off + kColS0 + c * 32, rs);
-          tmem_ld_32x32(tmem + lane_off + kColDP + c * 32, rd);
-          tmem_ld_wait();
-          const bool full = (wd[t] == 0xffffffffu);
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float p0 = ex2(fmaf(__uint_as_float(rs[j]), sc, -lse));
-            float p1 = ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse));
-            if (!full) { p0 = ((wd[t] >> j) & 1u) ? p0 : 0.f; p1 = ((wd[t] >> (j + 1)) & 1u) ? p1 : 0.f; }
-            dl4[(j >> 1) & 3] = fmaf(p0, __uint_as_float(rd[j]), dl4[(j >> 1) & 3]);
-            dl4[(j >> 1) & 3] = fmaf(p1, __uint_as_float(rd[j + 1]), dl4[(j >> 1) & 3]);
-            pp[t][j >> 1] = pack_bf16(p0, p1);
-          }
-        }
-      }
-      sm.red_delta[par][cg][row] = (dl4[0] + dl4[1]) + (dl4[2] + dl4[3]);
-      soft_bar();
-      const float delta = (sm.red_delta[par][0][row] + sm.red_delta[par][1][row]) +
-                          (sm.red_delta[par][2][row] + sm.red_delta[par][3][row]);
-      if (cg == 0) p.DELTA[li] = delta;
-      if (i > 0) mbar_wait(&sm.ds_free, (i - 1) & 1);   // dQ MMA of the previous entity has consumed the dS tile
       // pass 2: dS = scale*inv_n * P o (dP' - delta') -> bf16 A-operand tile
+      // The S columns go back to the MMA warp after pass 1, the dP' columns as soon as pass 2 has them in registers
+      // (entities of <= 4 chunks keep dP' in registers across the delta exchange and release both after pass 1), so
+      // the next entity's Q K^T / dA V^T overlap this entity's softmax work.
       const float wgt = p.scale * inv_n;
-      const float dw = delta * wgt;   // dS = P * (wgt*dP' - wgt*delta')
+      float dl4[4] = {0.f, 0.f, 0.f, 0.f};
+      // half = 16 score columns: bits [16*half, +16) of the chunk's mask word, packed P words [8*half, +8)
+      auto pass1 = [&](const uint32_t w16, const uint32_t (&rs)[16], const uint32_t (&rd)[16], uint32_t (&pk)[8]) {
+        const bool full = (w16 == 0xffffu);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (has[t]) {
-          const int c = cg + 4 * t;
-          uint32_t rd[32];
-          tmem_ld_32x32(tmem + lane_off + kColDP + c * 32, rd);
+        for (int j = 0; j < 16; j += 2) {
+          float p0 = ex2(fmaf(__uint_as_float(rs[j]), sc, -lse));
+          float p1 = ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse));
+          if (!full) { p0 = ((w16 >> j) & 1u) ? p0 : 0.f; p1 = ((w16 >> (j + 1)) & 1u) ? p1 : 0.f; }
+          dl4[(j >> 1) & 3] = fmaf(p0, __uint_as_float(rd[j]), dl4[(j >> 1) & 3]);
+          dl4[(j >> 1) & 3] = fmaf(p1, __uint_as_float(rd[j + 1]), dl4[(j >> 1) & 3]);
+          pk[j >> 1] = pack_bf16(p0, p1);
+        }
+      };
+      auto exchange_delta = [&]() {
+        sm.red_delta[par][cg][row] = (dl4[0] + dl4[1]) + (dl4[2] + dl4[3]);
+        soft_bar();
+        const float delta = (sm.red_delta[par][0][row] + sm.red_delta[par][1][row]) +
+                            (sm.red_delta[par][2][row] + sm.red_delta[par][3][row]);
+        if (cg == 0) p.DELTA[li] = delta;
+        return delta * wgt;            // dS = P * (wgt*dP' - wgt*delta')
+      };
+      auto pass2 = [&](const int c, const int half, const float dw, const uint32_t (&rd)[16], const uint32_t (&pk)[8]) {
+        uint8_t* atom = sm.ds + row * 128 + (c >> 1) * (SQ * 128);
+#pragma unroll
+        for (int g8 = 0; g8 < 2; ++g8) {
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 pr = unpack_bf16(pk[g8 * 4 + e]);
+            const int j = g8 * 8 + 2 * e;
+            o[e] = pack_bf16(pr.x * fmaf(__uint_as_float(rd[j]), wgt, -dw), pr.y * fmaf(__uint_as_float(rd[j + 1]), wgt, -dw));
+          }
+          const int chunk = (c & 1) * 4 + half * 2 + g8;
+          *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      };
+      if (nchunk <= 4) {
+        uint32_t pk[2][8] = {}, rda[16] = {}, rdb[16] = {};
+        if (has[0]) {
+          uint32_t rs[16];
+          tmem_ld_32x16(tmem + lane_off + kColS0 + cg * 32, rs);
+          tmem_ld_32x16(tmem + lane_off + kColDP + cg * 32, rda);
           tmem_ld_wait();
-          uint8_t* atom = sm.ds + row * 128 + (c >> 1) * (SQ * 128);
+          pass1(wd[0] & 0xffffu, rs, rda, pk[0]);
+          tmem_ld_32x16(tmem + lane_off + kColS0 + cg * 32 + 16, rs);
+          tmem_ld_32x16(tmem + lane_off + kColDP + cg * 32 + 16, rdb);
+          tmem_ld_wait();
+          pass1(wd[0] >> 16, rs, rdb, pk[1]);
+        }
+        tc_fence_before();
+        mbar_arrive(&sm.s_empty);
+        mbar_arrive(&sm.dp_empty);
+        const float dw = exchange_delta();
+        if (i > 0) mbar_wait(&sm.ds_free, (i - 1) & 1);   // dQ MMA of the previous entity has consumed the dS tile
+        if (has[0]) { pass2(cg, 0, dw, rda, pk[0]); pass2(cg, 1, dw, rdb, pk[1]); }
+      } else {
+        uint32_t pk[4][8] = {};
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            uint32_t o[4];
+        for (int t = 0; t < 2; ++t) {
+          if (has[t]) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 pr = unpack_bf16(pp[t][g8 * 4 + e]);
-              const int j = g8 * 8 + 2 * e;
-              o[e] = pack_bf16(pr.x * fmaf(__uint_as_float(rd[j]), wgt, -dw), pr.y * fmaf(__uint_as_float(rd[j + 1]), wgt, -dw));
+            for (int half = 0; half < 2; ++half) {
+              uint32_t rs[16], rd[16];
+              tmem_ld_32x16(tmem + lane_off + kColS0 + (cg + 4 * t) * 32 + half * 16, rs);
+              tmem_ld_32x16(tmem + lane_off + kColDP + (cg + 4 * t) * 32 + half * 16, rd);
+              tmem_ld_wait();
+              pass1((wd[t] >> (16 * half)) & 0xffffu, rs, rd, pk[t * 2 + half]);
             }
-            const int chunk = (c & 1) * 4 + g8;
-            *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
+        tc_fence_before();
+        mbar_arrive(&sm.s_empty);
+        const float dw = exchange_delta();
+        if (i > 0) mbar_wait(&sm.ds_free, (i - 1) & 1);
+        {
+          uint32_t r0[16], r1[16];
+          tmem_ld_32x16(tmem + lane_off + kColDP + cg * 32, r0);
+          tmem_ld_32x16(tmem + lane_off + kColDP + cg * 32 + 16, r1);
+          tmem_ld_wait();
+          if (!has[1]) { tc_fence_before(); mbar_arrive(&sm.dp_empty); }
+          pass2(cg, 0, dw, r0, pk[0]);
+          pass2(cg, 1, dw, r1, pk[1]);
+        }
+        if (has[1]) {
+          uint32_t r0[16], r1[16];
+          tmem_ld_32x16(tmem + lane_off + kColDP + (cg + 4) * 32, r0);
+          tmem_ld_32x16(tmem + lane_off + kColDP + (cg + 4) * 32 + 16, r1);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&sm.dp_empty);
+          pass2(cg + 4, 0, dw, r0, pk[2]);
+          pass2(cg + 4, 1, dw, r1, pk[3]);
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&sm.sdp_empty);
       fence_proxy_async_smem();
       mbar_arrive(&sm.ds_full);
     }
@@ -859,13 +909,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
       tmem_ld_32x32(tmem + lane_off + kColST + cg * 32, rs);
       tmem_ld_32x32(tmem + lane_off + kColDPT + cg * 32, rd);
       tmem_ld_wait();
+      // S^T / dP^T now live in registers: hand the TMEM columns back so the next target's products overlap this step
+      tc_fence_before();
+      mbar_arrive(&sm.sdp_empty);
       if (threadIdx.x == 64) TRACE(6, 6 * s + 3);
-      if (s > 0) mbar_wait(&sm.pds_free, (s - 1) & 1);
-      if (threadIdx.x == 64) TRACE(6, 6 * s + 4);
       const bool full = (wd == 0xffffffffu);
+      uint32_t po[4][4], dso[4][4];
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {
-        uint32_t po[4], dso[4];
         const float4 l0 = *reinterpret_cast<const float4*>(&sm.lse[st][cg * 32 + g8 * 8]);
         const float4 l1 = *reinterpret_cast<const float4*>(&sm.lse[st][cg * 32 + g8 * 8 + 4]);
         const float4 d0 = *reinterpret_cast<const float4*>(&sm.dlt[st][cg * 32 + g8 * 8]);
@@ -878,18 +929,22 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
           float p0 = ex2(fmaf(__uint_as_float(rs[j]), sc, -ls[2 * e2]));
           float p1 = ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -ls[2 * e2 + 1]));
           if (!full) { p0 = ((wd >> j) & 1u) ? p0 : 0.f; p1 = ((wd >> (j + 1)) & 1u) ? p1 : 0.f; }
-          po[e2] = pack_bf16(p0, p1);
-          dso[e2] = pack_bf16(p0 * fmaf(__uint_as_float(rd[j]), p.scale, -dl[2 * e2]),
-                              p1 * fmaf(__uint_as_float(rd[j + 1]), p.scale, -dl[2 * e2 + 1]));
+          po[g8][e2] = pack_bf16(p0, p1);
+          dso[g8][e2] = pack_bf16(p0 * fmaf(__uint_as_float(rd[j]), p.scale, -dl[2 * e2]),
+                                  p1 * fmaf(__uint_as_float(rd[j + 1]), p.scale, -dl[2 * e2 + 1]));
         }
-        const int chunk = (cg & 1) * 4 + g8;
-        *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[0], po[1], po[2], po[3]);
-        *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
       }
       if (stage_next) { sm.lse[st ^ 1][sw * 32 + lane] = l_next; sm.dlt[st ^ 1][sw * 32 + lane] = d_next; }
+      if (threadIdx.x == 64) TRACE(6, 6 * s + 4);
+      // the P^T / dS^T tiles of the previous target must have been consumed by its dV / dK products
+      if (s > 0) mbar_wait(&sm.pds_free, (s - 1) & 1);
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {
+        const int chunk = (cg & 1) * 4 + g8;
+        *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[g8][0], po[g8][1], po[g8][2], po[g8][3]);
+        *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[g8][0], dso[g8][1], dso[g8][2], dso[g8][3]);
+      }
       if (threadIdx.x == 64) TRACE(6, 6 * s + 5);
-      tc_fence_before();
-      mbar_arrive(&sm.sdp_empty);
       fence_proxy_async_smem();
       mbar_arrive(&sm.pds_full);
     }
@@ -1018,10 +1073,16 @@ extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  attn_bwd_dq_tc_kernel<<<a->n_qseq * a->H, kAttnThreads, smem_q, stream>>>(mp, *a);
-  MMSUM_CHECK_LAUNCH();
-  attn_bwd_dkv_tc_kernel<<<n_biz * a->H * tiles, kAttnThreads, smem_kv, stream>>>(mp, kv128, *a, tiles);
-  MMSUM_CHECK_LAUNCH();
+  // profiling knob (tools/gpu_bench_attn.py): MMSUM_ATTN_BWD_PART=1 launches only dQ/DELTA, =2 only dK/dV
+  static const int part = [] { const char* e = getenv("MMSUM_ATTN_BWD_PART"); return e ? atoi(e) : 0; }();
+  if (part != 2) {
+    attn_bwd_dq_tc_kernel<<<a->n_qseq * a->H, kAttnThreads, smem_q, stream>>>(mp, *a);
+    MMSUM_CHECK_LAUNCH();
+  }
+  if (part != 1) {
+    attn_bwd_dkv_tc_kernel<<<n_biz * a->H * tiles, kAttnThreads, smem_kv, stream>>>(mp, kv128, *a, tiles);
+    MMSUM_CHECK_LAUNCH();
+  }
   return 0;
 }
 
