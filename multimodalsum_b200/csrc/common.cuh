@@ -38,11 +38,84 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 rounding of every consumer): one MUFU.RCP,
+// one MUFU.EX2 and a degree-5 Horner chain instead of libdevice erff (~3x the instructions; the GELU epilogues of the
+// fc1 GEMMs were ALU-bound on it).  E = exp(-x^2/2) = exp(-z^2) is shared with the Gaussian pdf term of GELU'.
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float erf_as(float x, float& E) {   // returns erf(x / sqrt(2)); E = exp(-x*x/2)
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.f));
+  E = fast_ex2(x * x * -0.72134752044448170f);
+  float q = fmaf(t, 1.061405429f, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  q *= t;
+  return copysignf(fmaf(-q, E, 1.f), x);
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float E;
+  const float e = erf_as(x, E);
+  const float hx = 0.5f * x;
+  return fmaf(hx, e, hx);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float E;
+  const float e = erf_as(x, E);
+  return fmaf(0.5f, e, 0.5f) + x * (0.3989422804014327f * E);
+}
+
+// Blackwell packed fp32 pairs (FFMA2 / FMUL2): one issue slot for two lanes of the same elementwise chain.
+struct f32x2 { uint64_t r; };
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 o; asm("mov.b64 %0, {%1, %2};" : "=l"(o.r) : "f"(a), "f"(b)); return o; }
+__device__ __forceinline__ f32x2 splat2(float a) { return pack2(a, a); }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v.r)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 o; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(o.r) : "l"(a.r), "l"(b.r), "l"(c.r)); return o; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 o; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(o.r) : "l"(a.r), "l"(b.r)); return o; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 o; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(o.r) : "l"(a.r), "l"(b.r)); return o; }
+
+// erf(x / sqrt(2)) for a pair; E = exp(-x*x/2)
+__device__ __forceinline__ f32x2 erf_as2(float x0, float x1, f32x2 x, f32x2& E) {
+  const f32x2 z = pack2(fabsf(x0), fabsf(x1));
+  f32x2 d = fma2(z, splat2(0.3275911f * 0.70710678118654752f), splat2(1.f));
+  float d0, d1; unpack2(d, d0, d1);
+  const f32x2 t = pack2(fast_rcp(d0), fast_rcp(d1));
+  const f32x2 a = mul2(x, mul2(x, splat2(-0.72134752044448170f)));
+  float a0, a1; unpack2(a, a0, a1);
+  E = pack2(fast_ex2(a0), fast_ex2(a1));
+  f32x2 q = fma2(t, splat2(1.061405429f), splat2(-1.453152027f));
+  q = fma2(q, t, splat2(1.421413741f));
+  q = fma2(q, t, splat2(-0.284496736f));
+  q = fma2(q, t, splat2(0.254829592f));
+  q = mul2(q, t);
+  const f32x2 e = fma2(mul2(q, splat2(-1.f)), E, splat2(1.f));
+  float e0, e1; unpack2(e, e0, e1);
+  return pack2(copysignf(e0, x0), copysignf(e1, x1));
+}
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const f32x2 x = pack2(x0, x1);
+  f32x2 E;
+  const f32x2 e = erf_as2(x0, x1, x, E);
+  const f32x2 hx = mul2(x, splat2(0.5f));
+  unpack2(fma2(hx, e, hx), x0, x1);
+}
+// (g0, g1) *= GELU'(x0), GELU'(x1)
+__device__ __forceinline__ void gelu_erf_grad_mul2(float& g0, float& g1, float x0, float x1) {
+  const f32x2 x = pack2(x0, x1);
+  f32x2 E;
+  const f32x2 e = erf_as2(x0, x1, x, E);
+  const f32x2 cdf = fma2(e, splat2(0.5f), splat2(0.5f));
+  const f32x2 d = fma2(x, mul2(E, splat2(0.3989422804014327f)), cdf);
+  unpack2(mul2(pack2(g0, g1), d), g0, g1);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -13,7 +13,7 @@
 //   warp 0     TMA producer   global -> 128B-swizzled smem ring (kStages deep), mbarrier expect_tx
 //   warp 1     MMA issuer     one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM; tcgen05.commit
 //                             releases smem stages and publishes finished accumulators
-//   warps 2-5  epilogue       tcgen05.ld TMEM -> registers, alpha/bias/GELU/ReLU/d-activation, bf16 or fp32,
+//   warps 2-9  epilogue       tcgen05.ld TMEM -> registers, alpha/bias/GELU/ReLU/d-activation, bf16 or fp32,
 //                             swizzled smem staging, TMA store (or TMA reduce-add for split-K / grad accumulation)
 // TMEM holds two accumulator stages (2 x BN fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Ragged M/N/K edges rely on TMA: out-of-bounds loads are zero-filled, out-of-bounds stores are clipped.
@@ -30,8 +30,8 @@ namespace mmsum {
 static constexpr int BM = 128;
 static constexpr int BK = 64;       // 64 bf16 = 128 B = one swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int kGemmThreads = 192;
-static constexpr int kEpiWarps = 4;
+static constexpr int kEpiWarps = 8;   // two warps per TMEM lane quarter, each owning alternate 64-column groups
+static constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 static constexpr int kEpiBufBytes = 32 * 128;  // 32 rows x 128 B per staging buffer
 
 template <int BN>
@@ -40,7 +40,7 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBufBytes;
+  static constexpr int kEpiBytes = kEpiWarps * kEpiBufBytes;     // one staging buffer per epilogue warp
   static constexpr int kBarOffset = kStages * kStageBytes + kEpiBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
 };
@@ -68,10 +68,12 @@ __device__ __forceinline__ void decode_tile(const GemmKernelArgs& g, int t, int&
   else                 { nt = r % g.n_tiles; mt = r / g.n_tiles; }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// EPI: 0 plain epilogue (alpha, bias, ReLU), 1 = GELU/ReLU with the pre-activation saved to aux, 2 = multiply by act'(aux)
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                    const __grid_constant__ CUtensorMap tmAux,
                     const GemmKernelArgs g) {
   using L = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -171,114 +173,143 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
+    // warp = (TMEM lane quarter q, column half eh): 64-column groups eh, eh+2, ... of the tile, 32 columns at a time.
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int ew = warp - 2;
-    uint8_t* stg = smem + L::kStages * L::kStageBytes + ew * 2 * kEpiBufBytes;
+    const int eh = ew >> 2;
+    uint8_t* stg = smem + L::kStages * L::kStageBytes + ew * kEpiBufBytes;
+    const bool bias_vec = (g.bias != nullptr) && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
+    constexpr int kGroupsPerWarp = BN / 128;      // 64-column groups per warp and tile
     int as = 0; uint32_t aphase = 0;
-    int buf = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int mt, nt, sp; decode_tile(g, t, mt, nt, sp);
       const int m0 = mt * BM, n0 = nt * BN;
       const int row = m0 + q * 32 + lane;
+      // activation-gradient operand (EPI 2): this warp's share of the tile is fetched before the accumulator is
+      // complete, so the global-load latency hides behind the MMAs of the tile
+      uint4 auxr[EPI == 2 ? kGroupsPerWarp : 1][2][4] = {};
+      if (EPI == 2) {
+#pragma unroll
+        for (int gi = 0; gi < kGroupsPerWarp; ++gi)
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = n0 + (eh + 2 * gi) * 64 + half * 32 + j * 8;
+              if (row < g.M && n + 8 <= g.N) auxr[gi][half][j] = *reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.ld_aux + n);
+            }
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      // accumulator chunk -> alpha, bias
+      auto load_chunk = [&](int c, float (&v)[32]) {
         const int ncol0 = n0 + c * 32;
         uint32_t r[32];
         tmem_ld_32x32(tbase + c * 32, r);
         tmem_ld_wait();
-        float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * g.alpha;
         if (g.bias != nullptr && sp == 0) {
+          if (bias_vec && ncol0 + 32 <= g.N) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { const int n = ncol0 + i; v[i] += (n < g.N) ? __ldg(g.bias + n) : 0.f; }
-        }
-        if (g.aux_mode == 1) {
-          if (row < g.M) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int n = ncol0 + j * 8;
-              if (n + 8 <= g.N) {
-                uint4 pk;
-                pk.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]); pk.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
-                pk.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]); pk.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
-                *reinterpret_cast<uint4*>(g.aux + (size_t)row * g.ld_aux + n) = pk;
-              }
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + ncol0) + j);
+              v[j * 4 + 0] += b4.x; v[j * 4 + 1] += b4.y; v[j * 4 + 2] += b4.z; v[j * 4 + 3] += b4.w;
             }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const int n = ncol0 + i; v[i] += (n < g.N) ? __ldg(g.bias + n) : 0.f; }
           }
         }
-        if (g.aux_mode != 2) {
-          if (g.act == 1) {
+      };
+      auto pack16 = [&](const float (&v)[32], uint32_t (&o)[16]) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-          } else if (g.act == 2) {
+        for (int i = 0; i < 16; ++i) o[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+      };
+      // 32 rows x 64 bf16 columns from registers into the swizzled staging tile, then one TMA store
+      auto store_group = [&](const CUtensorMap* tm, const uint32_t (&lo)[16], const uint32_t (&hi)[16], int x) {
+        if (lane == 0) tma_store_wait_read<0>();   // the previous store has finished reading the staging tile
+        __syncwarp();
+        uint8_t* b = stg + lane * 128;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-        } else {
-          // v *= act'(aux): backward through the activation fused into the dgrad epilogue
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int n = ncol0 + j * 8;
-            uint4 pk = make_uint4(0, 0, 0, 0);
-            if (row < g.M && n + 8 <= g.N) pk = *reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.ld_aux + n);
-            const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 h = unpack_bf16(w[e]);
-              if (g.act == 1) { v[j * 8 + 2 * e] *= gelu_erf_grad(h.x); v[j * 8 + 2 * e + 1] *= gelu_erf_grad(h.y); }
-              else            { v[j * 8 + 2 * e] *= (h.x > 0.f) ? 1.f : 0.f; v[j * 8 + 2 * e + 1] *= (h.y > 0.f) ? 1.f : 0.f; }
-            }
-          }
+        for (int j = 0; j < 4; ++j) {
+          *reinterpret_cast<uint4*>(b + ((j ^ (lane & 7)) << 4)) = make_uint4(lo[j * 4], lo[j * 4 + 1], lo[j * 4 + 2], lo[j * 4 + 3]);
+          *reinterpret_cast<uint4*>(b + (((4 + j) ^ (lane & 7)) << 4)) = make_uint4(hi[j * 4], hi[j * 4 + 1], hi[j * 4 + 2], hi[j * 4 + 3]);
         }
-        // ---- stage to swizzled smem and TMA-store ----
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (x < g.N && m0 + q * 32 < g.M) tma_store_2d(tm, stg, x, m0 + q * 32);
+          tma_store_commit();
+        }
+      };
+#pragma unroll
+      for (int gi = 0; gi < kGroupsPerWarp; ++gi) {
+        const int grp = eh + 2 * gi;
         if (g.out_f32) {
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
-          uint8_t* b = stg + buf * kEpiBufBytes + lane * 128;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const int c = 2 * grp + half;
+            const int ncol0 = n0 + c * 32;
+            float v[32];
+            load_chunk(c, v);
+            if (g.act == 2) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 f = make_float4(v[j * 4 + 0], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
-            *reinterpret_cast<float4*>(b + ((j ^ (lane & 7)) << 4)) = f;
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (ncol0 < g.N && m0 + q * 32 < g.M) {
-              if (g.accumulate) tma_reduce_add_2d(&tmD, stg + buf * kEpiBufBytes, ncol0, m0 + q * 32);
-              else              tma_store_2d(&tmD, stg + buf * kEpiBufBytes, ncol0, m0 + q * 32);
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            tma_store_commit();
-          }
-          buf ^= 1;
-        } else {
-          const int half = c & 1;
-          if (half == 0) {
-            if (lane == 0) tma_store_wait_read<1>();
+            if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
-          }
-          uint8_t* b = stg + buf * kEpiBufBytes + lane * 128;
+            uint8_t* b = stg + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            pk.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]); pk.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
-            pk.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]); pk.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
-            *reinterpret_cast<uint4*>(b + (((half * 4 + j) ^ (lane & 7)) << 4)) = pk;
-          }
-          if (half == 1) {
+            for (int j = 0; j < 8; ++j) {
+              float4 f = make_float4(v[j * 4 + 0], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+              *reinterpret_cast<float4*>(b + ((j ^ (lane & 7)) << 4)) = f;
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              const int x = n0 + (c >> 1) * 64;
-              if (x < g.N && m0 + q * 32 < g.M) tma_store_2d(&tmD, stg + buf * kEpiBufBytes, x, m0 + q * 32);
+              if (ncol0 < g.N && m0 + q * 32 < g.M) {
+                if (g.accumulate) tma_reduce_add_2d(&tmD, stg, ncol0, m0 + q * 32);
+                else              tma_store_2d(&tmD, stg, ncol0, m0 + q * 32);
+              }
               tma_store_commit();
             }
-            buf ^= 1;
           }
+        } else {
+          uint32_t outp[2][16], prep[EPI == 1 ? 2 : 1][16];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float v[32];
+            load_chunk(2 * grp + half, v);
+            if (EPI == 1) pack16(v, prep[EPI == 1 ? half : 0]);     // pre-activation, saved for the backward epilogue
+            if (EPI != 2) {
+              if (g.act == 1) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) gelu_erf2(v[i], v[i + 1]);
+              } else if (g.act == 2) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+              }
+            } else {
+              // v *= act'(aux): backward through the activation fused into the dgrad epilogue
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 ax = auxr[EPI == 2 ? gi : 0][half][j];
+                const uint32_t w[4] = {ax.x, ax.y, ax.z, ax.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 h = unpack_bf16(w[e]);
+                  if (g.act == 1) { gelu_erf_grad_mul2(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1], h.x, h.y); }
+                  else            { v[j * 8 + 2 * e] *= (h.x > 0.f) ? 1.f : 0.f; v[j * 8 + 2 * e + 1] *= (h.y > 0.f) ? 1.f : 0.f; }
+                }
+              }
+            }
+            pack16(v, outp[half]);
+          }
+          if (EPI == 1) store_group(&tmAux, prep[0], prep[EPI == 1 ? 1 : 0], n0 + grp * 64);
+          store_group(&tmD, outp[0], outp[1], n0 + grp * 64);
         }
       }
       // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
@@ -365,18 +396,19 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& td,
+                       const CUtensorMap& taux,
                        const GemmKernelArgs& ka, int grid, cudaStream_t stream) {
   using L = GemmSmem<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  gemm_tcgen05_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, L::kTotal, stream>>>(ta, ta2, tb, td, ka);
+  gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI><<<grid, kGemmThreads, L::kTotal, stream>>>(ta, ta2, tb, td, taux, ka);
   MMSUM_CHECK_LAUNCH();
   return 0;
 }
@@ -394,6 +426,10 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
   int bn = a->block_n;
   if (bn == 0) bn = (a->N > 128) ? 256 : 128;
   if (bn != 128 && bn != 256) return MMSUM_ERR_INVALID;
+  if (a->aux_mode != 0) {   // fused-activation epilogues exist for row-major A and 256-wide tiles
+    if (a->aux_mode < 0 || a->aux_mode > 2 || a->a_mn_major) return MMSUM_ERR_INVALID;
+    bn = 256;
+  }
 
   GemmKernelArgs ka;
   ka.M = a->M; ka.N = a->N; ka.K = a->K;
@@ -402,13 +438,21 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
   const int kblocks = (a->K + BK - 1) / BK;
   int splits = a->splits;
   if (splits <= 0) {
-    // auto split-K: only when accumulating fp32 output and the MN grid cannot fill the machine
+    // auto split-K (fp32 accumulating outputs only): pick the split count that minimises
+    //   waves * (k-blocks per split * 512 clk + ~4096 clk of unoverlapped prologue / reduce epilogue)
+    // on the persistent grid; the constants were fitted to tools/gpu_gemm_sweep.py on the step's wgrad shapes
     splits = 1;
     const int mn = ka.m_tiles * ka.n_tiles;
-    if (a->out_f32 && a->accumulate && mn < kNumSMs) {
-      splits = (2 * kNumSMs + mn - 1) / mn;
-      if (splits > kblocks / 4) splits = kblocks / 4;
-      if (splits < 1) splits = 1;
+    if (a->out_f32 && a->accumulate && a->A2 == nullptr) {
+      const int nsm = num_sms();
+      long long best = -1;
+      for (int sp = 1; sp <= 16 && sp * 8 <= kblocks; ++sp) {
+        const int kb = (kblocks + sp - 1) / sp;
+        const int eff = (kblocks + kb - 1) / kb;          // splits that actually get work
+        const long long waves = ((long long)mn * eff + nsm - 1) / nsm;
+        const long long cost = waves * ((long long)kb * 512 + 4096);
+        if (best < 0 || cost < best) { best = cost; splits = sp; }
+      }
     }
   }
   if (splits > 1 && (!(a->out_f32 && a->accumulate) || a->A2 != nullptr)) return MMSUM_ERR_INVALID;
@@ -449,22 +493,35 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
   if (a->out_f32) rc = make_tmap(&td, a->D, 1, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 4, 32, 32);
   else            rc = make_tmap(&td, a->D, 0, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 64, 32);
   if (rc) return rc;
+  CUtensorMap taux = td;   // pre-activation copy (aux_mode 1) leaves through its own map, same tiling as D
+  if (a->aux_mode == 1) {
+    rc = make_tmap(&taux, a->aux, 0, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ld_aux * 2, 64, 32);
+    if (rc) return rc;
+  }
 
   if (ka.splits > 1 && (a->act != 0 || a->aux_mode != 0)) return MMSUM_ERR_INVALID;
+  if (a->out_f32 && (a->act == 1 || a->aux_mode != 0)) return MMSUM_ERR_INVALID;   // fused activations are bf16-output only
   const int total = ka.m_tiles * ka.n_tiles * ka.splits;
   const int nsm = num_sms();
   const int grid = total < nsm ? total : nsm;
   const int am = a->a_mn_major ? 1 : 0, bm = a->b_mn_major ? 1 : 0;
-#define MMSUM_GEMM_CASE(BN_, AM_, BM_) \
-  if (bn == BN_ && am == AM_ && bm == BM_) return launch_gemm<BN_, (AM_ != 0), (BM_ != 0)>(ta, ta2, tb, td, ka, grid, stream);
-  MMSUM_GEMM_CASE(256, 0, 0)
-  MMSUM_GEMM_CASE(256, 0, 1)
-  MMSUM_GEMM_CASE(256, 1, 1)
-  MMSUM_GEMM_CASE(256, 1, 0)
-  MMSUM_GEMM_CASE(128, 0, 0)
-  MMSUM_GEMM_CASE(128, 0, 1)
-  MMSUM_GEMM_CASE(128, 1, 1)
-  MMSUM_GEMM_CASE(128, 1, 0)
+  const int epi = a->aux_mode;
+#define MMSUM_GEMM_CASE(BN_, AM_, BM_, EPI_) \
+  if (bn == BN_ && am == AM_ && bm == BM_ && epi == EPI_) \
+    return launch_gemm<BN_, (AM_ != 0), (BM_ != 0), EPI_>(ta, ta2, tb, td, taux, ka, grid, stream);
+  MMSUM_GEMM_CASE(256, 0, 0, 0)
+  MMSUM_GEMM_CASE(256, 0, 1, 0)
+  MMSUM_GEMM_CASE(256, 1, 1, 0)
+  MMSUM_GEMM_CASE(256, 1, 0, 0)
+  MMSUM_GEMM_CASE(128, 0, 0, 0)
+  MMSUM_GEMM_CASE(128, 0, 1, 0)
+  MMSUM_GEMM_CASE(128, 1, 1, 0)
+  MMSUM_GEMM_CASE(128, 1, 0, 0)
+  // fused-activation epilogues: row-major A (the Linear fprop / dgrad operands), 256-wide tiles
+  MMSUM_GEMM_CASE(256, 0, 0, 1)
+  MMSUM_GEMM_CASE(256, 0, 1, 1)
+  MMSUM_GEMM_CASE(256, 0, 0, 2)
+  MMSUM_GEMM_CASE(256, 0, 1, 2)
 #undef MMSUM_GEMM_CASE
   return MMSUM_ERR_INVALID;
 }
