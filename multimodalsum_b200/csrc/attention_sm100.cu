@@ -721,23 +721,32 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
 //   Pn^T = inv_n * exp2(sc*S^T - LSE[q]);  dS^T = scale * Pn^T o (dP'^T - delta'[q]);  both -> bf16 smem;
 //   dV += Pn^T dA,  dK += dS^T Q  (TMEM accumulators over all targets)
 // ----------------------------------------------------------------------------------------------
+// Two CTAs share an SM (256 TMEM columns, ~100 KB smem, 320 threads each): one CTA's softmax phase overlaps the other's
+// MMA / staging phases, which a single lock-stepped CTA cannot do.  A step is one (consumer target, 64-query half).
+static constexpr int QH = 64;                       // queries per step
+static constexpr int kKvSoftWarps = 8;
+static constexpr int kKvSoftThreads = kKvSoftWarps * 32;
+static constexpr int kKvThreads = 64 + kKvSoftThreads;
+__device__ __forceinline__ void kv_soft_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kKvSoftThreads) : "memory"); }
+
 struct BwdKVSmem {
   uint8_t k[SQ * 128];
   uint8_t v[SQ * 128];
-  uint8_t q[2][SQ * 128];
-  uint8_t da[2][SQ * 128];
-  uint8_t pt[2 * SQ * 128];
-  uint8_t dst[2 * SQ * 128];
-  float lse[2][SQ];
-  float dlt[2][SQ];
+  uint8_t q[2][QH * 128];      // Q / dA rows of the step's 64 queries (2-deep ring)
+  uint8_t da[2][QH * 128];
+  uint8_t pt[SQ * 128];        // Pn^T  [128 keys][64 queries] bf16, K-major A operand
+  uint8_t dst[SQ * 128];       // dS^T
+  float lse[2][QH];            // raw LSE / DELTA rows of the current and the next step (cp.async staged)
+  float dlt[2][QH];
+  float lg_invn[32];           // log2(1/n) of every target for this modality
   uint64_t kv_full, qd_full[2], qd_empty[2], sdp_full, sdp_empty, pds_full, pds_free;
   uint32_t tmem_slot;
 };
-static constexpr uint32_t kColST = 0, kColDPT = 128, kColDK = 256, kColDV = 320;
+static constexpr uint32_t kColST = 0, kColDPT = 64, kColDK = 128, kColDV = 192;
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
-attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ CUtensorMap kv128,
-                       const MmsumAttnArgs p, int tiles_per_bh) {
+__global__ void __launch_bounds__(kKvThreads, 2)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_constant__ CUtensorMap do64,
+                       const __grid_constant__ CUtensorMap kv128, const MmsumAttnArgs p, int tiles_per_bh) {
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window with pointer arithmetic on the __shared__ array so the compiler keeps the
   // shared address space (LDS/STS instead of generic LD/ST)
@@ -761,19 +770,20 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
   const bool ent_ok = (p.ent_valid == nullptr) || (p.ent_valid[(long long)biz * p.E_total + ge] != 0);
   bf16* dKV = reinterpret_cast<bf16*>(p.dKV);
 
-  // consumer targets of this entity (leave-one-out excludes target e)
-  int n_steps = 0;
-  for (int tg = 0; tg < p.R; ++tg) n_steps += (md.loo && tg == e) ? 0 : 1;
+  // consumer targets of this entity (leave-one-out excludes target e); two 64-query steps per target
+  int n_tgt = 0;
+  for (int tg = 0; tg < p.R; ++tg) n_tgt += (md.loo && tg == e) ? 0 : 1;
+  const int n_steps = 2 * n_tgt;
   if (!ent_ok || n_steps == 0) {
     // null entity: its gradient is exactly zero (the buffer is never memset)
     if (warp >= 2) {
       const int row = (warp & 3) * 32 + lane;
       const int cg = (warp - 2) >> 2;
       if (row < nkeys) {
-        bf16* dk = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dk_col + h * HD + cg * 16;
-        bf16* dv = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dv_col + h * HD + cg * 16;
+        bf16* dk = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dk_col + h * HD + cg * 32;
+        bf16* dv = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dv_col + h * HD + cg * 32;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 4; ++j) {
           *reinterpret_cast<uint4*>(dk + j * 8) = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(dv + j * 8) = make_uint4(0, 0, 0, 0);
         }
@@ -785,17 +795,17 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
   if (threadIdx.x == 0) {
     mbar_init(&sm.kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&sm.qd_full[s], 1); mbar_init(&sm.qd_empty[s], 1); }
-    mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, kSoftThreads);
-    mbar_init(&sm.pds_full, kSoftThreads); mbar_init(&sm.pds_free, 1);
+    mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, kKvSoftThreads);
+    mbar_init(&sm.pds_full, kKvSoftThreads); mbar_init(&sm.pds_free, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(&sm.tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(&sm.tmem_slot, 256); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_slot;
-  auto step_target = [&](int s) {   // s-th consumer target -> target index
-    int tg = s;
+  auto step_target = [&](int s) {   // step -> target index of its 64-query half
+    int tg = s >> 1;
     if (md.loo && tg >= e) ++tg;
     return tg;
   };
@@ -807,11 +817,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
       tma_load_2d(sm.v, &kv128, &sm.kv_full, p.v_col + h * HD, kvrow0);
       for (int s = 0; s < n_steps; ++s) {
         const int st = s & 1;
-        const int qrow0 = (biz * p.R + step_target(s)) * SQ;
+        const int qrow0 = (biz * p.R + step_target(s)) * SQ + (s & 1) * QH;
         mbar_wait(&sm.qd_empty[st], ((s >> 1) & 1) ^ 1);
-        mbar_expect_tx(&sm.qd_full[st], 2 * SQ * 128);
-        tma_load_2d(sm.q[st], &maps.q, &sm.qd_full[st], p.q_col + h * HD, qrow0);
-        tma_load_2d(sm.da[st], &maps.d_o, &sm.qd_full[st], h * HD, (int)(md.o_off / p.ldo) + qrow0);
+        mbar_expect_tx(&sm.qd_full[st], 2 * QH * 128);
+        tma_load_2d(sm.q[st], &q64, &sm.qd_full[st], p.q_col + h * HD, qrow0);
+        tma_load_2d(sm.da[st], &do64, &sm.qd_full[st], h * HD, (int)(md.o_off / p.ldo) + qrow0);
       }
     }
   } else if (warp == 1) {
@@ -822,7 +832,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
       const uint64_t qdesc_mn[2] = {umma_smem_desc_sw128(smem_u32(sm.q[0]), 8192, 1024), umma_smem_desc_sw128(smem_u32(sm.q[1]), 8192, 1024)};
       const uint64_t dadesc_k[2] = {umma_smem_desc_sw128(smem_u32(sm.da[0]), 16, 1024), umma_smem_desc_sw128(smem_u32(sm.da[1]), 16, 1024)};
       const uint64_t dadesc_mn[2] = {umma_smem_desc_sw128(smem_u32(sm.da[0]), 8192, 1024), umma_smem_desc_sw128(smem_u32(sm.da[1]), 8192, 1024)};
-      const uint32_t idesc_s = umma_idesc_bf16(128, SQ, 0, 0);
+      const uint32_t idesc_s = umma_idesc_bf16(128, QH, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
       mbar_wait(&sm.kv_full, 0);
       auto issue_sdp = [&](int s) {
@@ -850,20 +860,18 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
         tc_fence_after();
         const uint64_t qd = st ? qdesc_mn[1] : qdesc_mn[0], dd = st ? dadesc_mn[1] : dadesc_mn[0];
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)   // contraction over the 128 queries
-          umma_bf16_w(tmem + kColDV, desc_adv(ptdesc, (kk >> 2) * (SQ * 128) + (kk & 3) * 32), desc_adv(dd, kk * 2048), idesc_o,
-                    (s > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < QH / 16; ++kk)   // contraction over the step's 64 queries
+          umma_bf16_w(tmem + kColDV, desc_adv(ptdesc, kk * 32), desc_adv(dd, kk * 2048), idesc_o, (s > 0 || kk > 0) ? 1u : 0u);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16_w(tmem + kColDK, desc_adv(dstdesc, (kk >> 2) * (SQ * 128) + (kk & 3) * 32), desc_adv(qd, kk * 2048), idesc_o,
-                    (s > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < QH / 16; ++kk)
+          umma_bf16_w(tmem + kColDK, desc_adv(dstdesc, kk * 32), desc_adv(qd, kk * 2048), idesc_o, (s > 0 || kk > 0) ? 1u : 0u);
         if (lane == 0) TRACE(5, 4 * s + 3);
         umma_commit_w(&sm.qd_empty[st]);
         umma_commit_w(&sm.pds_free);
       }
     }
   } else {
-    // thread = (key row, column group cg): query chunk cg (32 of the 128 queries), dK / dV columns [16cg, 16cg+16)
+    // thread = (key row, column group cg): 32 of the step's 64 queries, dK / dV columns [32cg, 32cg+32)
     const int q4 = warp & 3;
     const int sw = warp - 2;
     const int cg = sw >> 2;
@@ -871,37 +879,36 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float sc = p.scale * kLog2e;
     const bool kvalid = (row < nkeys) && (p.key_valid == nullptr || p.key_valid[(long long)kvrow0 + row] != 0);
-    uint32_t wd = kvalid ? 0xffffffffu : 0u;
-    if (p.causal) {  // key (key0 + row) <= query (cg*32 + j)  <=>  j >= key0 + row - cg*32
-      const int lo = key0 + row - cg * 32;
-      wd &= (lo <= 0) ? 0xffffffffu : (lo >= 32 ? 0u : ~((1u << lo) - 1u));
-    }
-    uint8_t* patom = sm.pt + row * 128 + (cg >> 1) * (SQ * 128);
-    uint8_t* datom = sm.dst + row * 128 + (cg >> 1) * (SQ * 128);
+    uint8_t* patom = sm.pt + row * 128;
+    uint8_t* datom = sm.dst + row * 128;
     auto lse_index = [&](int s) {
-      return (((long long)(biz * p.R + step_target(s)) * p.H + h) * p.E_total + ge) * SQ + (sw * 32 + lane);
+      return (((long long)(biz * p.R + step_target(s)) * p.H + h) * p.E_total + ge) * SQ + (s & 1) * QH + (sw * 32 + lane);
     };
-    // staged per target: lse' = LSE - log2(inv_n)  (so P already carries 1/n) and dl' = scale * delta'
-    auto stage_vals = [&](int s, float& l, float& d) {
-      const int qs = biz * p.R + step_target(s);
-      const float inv_n = p.inv_n ? p.inv_n[(long long)qs * p.n_mod + m] : 1.f;
-      l = p.LSE[lse_index(s)] - __log2f(inv_n);
-      d = p.DELTA[lse_index(s)] * p.scale;
+    // LSE / DELTA rows of a step are staged with cp.async one step ahead (no register dependency, so the global
+    // latency never sits on the softmax critical path); P absorbs 1/n through  exp2(sc*s - (LSE - log2(1/n)))
+    auto stage_rows = [&](int s, int st) {
+      const long long i = lse_index(s);
+      cp_async_4(smem_u32(&sm.lse[st][sw * 32 + lane]), p.LSE + i);
+      cp_async_4(smem_u32(&sm.dlt[st][sw * 32 + lane]), p.DELTA + i);
     };
-    if (sw < 4) {
-      float l, d;
-      stage_vals(0, l, d);
-      sm.lse[0][sw * 32 + lane] = l;
-      sm.dlt[0][sw * 32 + lane] = d;
+    if (sw < 2) stage_rows(0, 0);
+    if (threadIdx.x - 64 < (unsigned)p.R && threadIdx.x - 64 < 32u) {
+      const int tg = threadIdx.x - 64;
+      sm.lg_invn[tg] = p.inv_n ? __log2f(p.inv_n[(long long)(biz * p.R + tg) * p.n_mod + m]) : 0.f;
     }
     for (int s = 0; s < n_steps; ++s) {
       const int st = s & 1;
+      if (sw < 2) cp_async_wait_all();   // rows of this step (issued one step ago) have landed
       if (threadIdx.x == 64) TRACE(6, 6 * s);
-      soft_bar();   // stage st is visible; everybody is done with stage st^1 (read during step s-1)
+      kv_soft_bar();   // stage st is visible; everybody is done with stage st^1 (read during step s-1)
       if (threadIdx.x == 64) TRACE(6, 6 * s + 1);
-      float l_next = 0.f, d_next = 0.f;
-      const bool stage_next = (sw < 4) && (s + 1 < n_steps);
-      if (stage_next) stage_vals(s + 1, l_next, d_next);   // loads in flight during this step
+      if ((sw < 2) && (s + 1 < n_steps)) stage_rows(s + 1, st ^ 1);
+      const float lg = sm.lg_invn[step_target(s)];
+      uint32_t wd = kvalid ? 0xffffffffu : 0u;
+      if (p.causal) {  // key (key0 + row) <= query ((s&1)*64 + cg*32 + j)  <=>  j >= key0 + row - (s&1)*64 - cg*32
+        const int lo = key0 + row - (s & 1) * QH - cg * 32;
+        wd &= (lo <= 0) ? 0xffffffffu : (lo >= 32 ? 0u : ~((1u << lo) - 1u));
+      }
       mbar_wait(&sm.sdp_full, s & 1);
       if (threadIdx.x == 64) TRACE(6, 6 * s + 2);
       tc_fence_after();
@@ -909,40 +916,43 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
       tmem_ld_32x32(tmem + lane_off + kColST + cg * 32, rs);
       tmem_ld_32x32(tmem + lane_off + kColDPT + cg * 32, rd);
       tmem_ld_wait();
-      // S^T / dP^T now live in registers: hand the TMEM columns back so the next target's products overlap this step
+      // S^T / dP^T now live in registers: hand the TMEM columns back so the next step's products overlap this one
       tc_fence_before();
       mbar_arrive(&sm.sdp_empty);
       if (threadIdx.x == 64) TRACE(6, 6 * s + 3);
       const bool full = (wd == 0xffffffffu);
-      uint32_t po[4][4], dso[4][4];
+      const f32x2 lg2 = splat2(lg), m1 = splat2(-1.f), sc2 = splat2(sc), scale2 = splat2(p.scale), nscale2 = splat2(-p.scale);
+      // the P^T / dS^T tiles of the previous step must have been consumed by its dV / dK products (they were issued
+      // while this step waited for its scores, so this wait is short; it lets every group be stored as it is formed)
+      if (s > 0) mbar_wait(&sm.pds_free, (s - 1) & 1);
+      if (threadIdx.x == 64) TRACE(6, 6 * s + 4);
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {
+        uint32_t po[4], dso[4];
         const float4 l0 = *reinterpret_cast<const float4*>(&sm.lse[st][cg * 32 + g8 * 8]);
         const float4 l1 = *reinterpret_cast<const float4*>(&sm.lse[st][cg * 32 + g8 * 8 + 4]);
         const float4 d0 = *reinterpret_cast<const float4*>(&sm.dlt[st][cg * 32 + g8 * 8]);
         const float4 d1 = *reinterpret_cast<const float4*>(&sm.dlt[st][cg * 32 + g8 * 8 + 4]);
-        const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        // packed fp32 pairs (FFMA2 / FMUL2): the softmax warps are issue-bound, so two lanes per instruction count
+        const f32x2 nl[4] = {fma2(pack2(l0.x, l0.y), m1, lg2), fma2(pack2(l0.z, l0.w), m1, lg2),
+                             fma2(pack2(l1.x, l1.y), m1, lg2), fma2(pack2(l1.z, l1.w), m1, lg2)};      // log2(1/n) - LSE
+        const f32x2 nd[4] = {mul2(pack2(d0.x, d0.y), nscale2), mul2(pack2(d0.z, d0.w), nscale2),
+                             mul2(pack2(d1.x, d1.y), nscale2), mul2(pack2(d1.z, d1.w), nscale2)};      // -scale * delta'
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
           const int j = g8 * 8 + 2 * e2;
-          float p0 = ex2(fmaf(__uint_as_float(rs[j]), sc, -ls[2 * e2]));
-          float p1 = ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -ls[2 * e2 + 1]));
+          float a0, a1;
+          unpack2(fma2(pack2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), sc2, nl[e2]), a0, a1);
+          float p0 = ex2(a0), p1 = ex2(a1);
           if (!full) { p0 = ((wd >> j) & 1u) ? p0 : 0.f; p1 = ((wd >> (j + 1)) & 1u) ? p1 : 0.f; }
-          po[g8][e2] = pack_bf16(p0, p1);
-          dso[g8][e2] = pack_bf16(p0 * fmaf(__uint_as_float(rd[j]), p.scale, -dl[2 * e2]),
-                                  p1 * fmaf(__uint_as_float(rd[j + 1]), p.scale, -dl[2 * e2 + 1]));
+          po[e2] = pack_bf16(p0, p1);
+          float s0, s1;
+          unpack2(mul2(pack2(p0, p1), fma2(pack2(__uint_as_float(rd[j]), __uint_as_float(rd[j + 1])), scale2, nd[e2])), s0, s1);
+          dso[e2] = pack_bf16(s0, s1);
         }
-      }
-      if (stage_next) { sm.lse[st ^ 1][sw * 32 + lane] = l_next; sm.dlt[st ^ 1][sw * 32 + lane] = d_next; }
-      if (threadIdx.x == 64) TRACE(6, 6 * s + 4);
-      // the P^T / dS^T tiles of the previous target must have been consumed by its dV / dK products
-      if (s > 0) mbar_wait(&sm.pds_free, (s - 1) & 1);
-#pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {
-        const int chunk = (cg & 1) * 4 + g8;
-        *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[g8][0], po[g8][1], po[g8][2], po[g8][3]);
-        *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[g8][0], dso[g8][1], dso[g8][2], dso[g8][3]);
+        const int chunk = cg * 4 + g8;
+        *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[0], po[1], po[2], po[3]);
+        *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
       }
       if (threadIdx.x == 64) TRACE(6, 6 * s + 5);
       fence_proxy_async_smem();
@@ -953,15 +963,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
     {
       // every lane issues the (.sync.aligned) TMEM loads; only lanes that own a key store
       const int srow = row < nkeys ? row : 0;
-      bf16* dk = dKV + (long long)(kvrow0 + srow) * p.lddkv + p.dk_col + h * HD + cg * 16;
-      bf16* dv = dKV + (long long)(kvrow0 + srow) * p.lddkv + p.dv_col + h * HD + cg * 16;
-      uint32_t rk[16], rv[16];
-      tmem_ld_32x16(tmem + lane_off + kColDK + cg * 16, rk);
-      tmem_ld_32x16(tmem + lane_off + kColDV + cg * 16, rv);
+      bf16* dk = dKV + (long long)(kvrow0 + srow) * p.lddkv + p.dk_col + h * HD + cg * 32;
+      bf16* dv = dKV + (long long)(kvrow0 + srow) * p.lddkv + p.dv_col + h * HD + cg * 32;
+      uint32_t rk[32], rv[32];
+      tmem_ld_32x32(tmem + lane_off + kColDK + cg * 32, rk);
+      tmem_ld_32x32(tmem + lane_off + kColDV + cg * 32, rv);
       tmem_ld_wait();
       if (row < nkeys) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 4; ++j) {
           uint4 u, w2;
           u.x = pack_bf16(__uint_as_float(rk[j * 8 + 0]), __uint_as_float(rk[j * 8 + 1]));
           u.y = pack_bf16(__uint_as_float(rk[j * 8 + 2]), __uint_as_float(rk[j * 8 + 3]));
@@ -979,13 +989,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ AttnMaps maps, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 static int validate_tc(const MmsumAttnArgs* a, bool bwd) {
   if (!a || !a->Q || !a->KV || !a->O || !a->LSE) return MMSUM_ERR_INVALID;
   if (a->n_qseq <= 0 || a->H <= 0 || a->R <= 0 || a->n_mod < 1 || a->n_mod > 3) return MMSUM_ERR_INVALID;
-  if (a->n_qseq % a->R) return MMSUM_ERR_INVALID;
+  if ((a->n_qseq % a->R) || a->R > 32) return MMSUM_ERR_INVALID;
   if ((a->ldq % 8) || (a->ldkv % 8) || (a->ldo % 8) || (a->q_col % 8) || (a->k_col % 8) || (a->v_col % 8)) return MMSUM_ERR_INVALID;
   int ents = 0;
   for (int m = 0; m < a->n_mod; ++m) {
@@ -1062,8 +1072,18 @@ extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
     if (r > kvrows) kvrows = r;
     tiles += a->mods[m].E * ((a->mods[m].Sk + SQ - 1) / SQ);
   }
-  CUtensorMap kv128;
+  CUtensorMap kv128, q64, do64;
   if (int rc = make_tmap(&kv128, a->KV, 0, (uint64_t)a->ldkv, kvrows, (uint64_t)a->ldkv * 2, 64, SQ)) return rc;
+  {   // 64-query boxes of Q and of the upstream gradient for the dK/dV kernel's steps
+    const uint64_t qrows = (uint64_t)a->n_qseq * SQ;
+    uint64_t orows = 0;
+    for (int m = 0; m < a->n_mod; ++m) {
+      const uint64_t r = (uint64_t)(a->mods[m].o_off / a->ldo) + qrows;
+      if (r > orows) orows = r;
+    }
+    if (int rc = make_tmap(&q64, a->Q, 0, (uint64_t)a->ldq, qrows, (uint64_t)a->ldq * 2, 64, QH)) return rc;
+    if (int rc = make_tmap(&do64, a->O, 0, (uint64_t)a->ldo, orows, (uint64_t)a->ldo * 2, 64, QH)) return rc;
+  }
   const int smem_q = (int)sizeof(BwdQSmem) + 1024, smem_kv = (int)sizeof(BwdKVSmem) + 1024;
   static bool attr = false;
   if (!attr) {
@@ -1080,7 +1100,7 @@ extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
     MMSUM_CHECK_LAUNCH();
   }
   if (part != 1) {
-    attn_bwd_dkv_tc_kernel<<<n_biz * a->H * tiles, kAttnThreads, smem_kv, stream>>>(mp, kv128, *a, tiles);
+    attn_bwd_dkv_tc_kernel<<<n_biz * a->H * tiles, kKvThreads, smem_kv, stream>>>(q64, do64, kv128, *a, tiles);
     MMSUM_CHECK_LAUNCH();
   }
   return 0;
