@@ -367,7 +367,8 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       }
       while (cur_mod < it.mod) { flush(cur_mod); ++cur_mod; }
       // exp pass: P = exp2(s*sc - m) -> bf16 into the swizzled A-operand tile; partial row sum
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      f32x2 l2[2] = {splat2(0.f), splat2(0.f)};     // packed fp32 pairs (FFMA2 / FADD2): issue slots are the limit
+      const f32x2 sc2 = splat2(sc), nmsc2 = splat2(-msc);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const bool has = t == 0 ? has0 : has1;
@@ -377,15 +378,15 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
           uint32_t r[32];
           tmem_ld_32x32(scol + c * 32, r);
           tmem_ld_wait();
-          if (wd == 0xffffffffu) {
+          const bool full = (wd == 0xffffffffu);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { const float e = ex2(fmaf(__uint_as_float(r[j]), sc, -msc)); l4[j & 3] += e; r[j] = __float_as_uint(e); }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float e = ((wd >> j) & 1u) ? ex2(fmaf(__uint_as_float(r[j]), sc, -msc)) : 0.f;
-              l4[j & 3] += e; r[j] = __float_as_uint(e);
-            }
+          for (int j = 0; j < 32; j += 2) {
+            float a0, a1;
+            unpack2(fma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, nmsc2), a0, a1);
+            float e0 = ex2(a0), e1 = ex2(a1);
+            if (!full) { e0 = ((wd >> j) & 1u) ? e0 : 0.f; e1 = ((wd >> (j + 1)) & 1u) ? e1 : 0.f; }
+            l2[(j >> 1) & 1] = add2(l2[(j >> 1) & 1], pack2(e0, e1));
+            r[j] = __float_as_uint(e0); r[j + 1] = __float_as_uint(e1);
           }
           uint8_t* atom = sm.p + row * 128 + (c >> 1) * (SQ * 128);
 #pragma unroll
@@ -400,6 +401,9 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
           }
         }
       }
+      float l4[4];
+      unpack2(l2[0], l4[0], l4[1]);
+      unpack2(l2[1], l4[2], l4[3]);
       sm.red_sum[par][cg][row] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       if (threadIdx.x == 64) TRACE(3, 6 * i + 5);
       tc_fence_before();
