@@ -21,6 +21,7 @@
 //   warps 2-5 softmax:      thread = query row; tcgen05.ld S, max, exp2, bf16 P -> swizzled smem (A operand of P V);
 //                           reads O_e back and accumulates (1/n)(1/l_e) O_e in registers; writes the modality outputs
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "../../include/mmsum_b200.h"
 
@@ -378,16 +379,20 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
           uint32_t r[32];
           tmem_ld_32x32(scol + c * 32, r);
           tmem_ld_wait();
-          const bool full = (wd == 0xffffffffu);
+          // two copies of the loop (warp-uniform choice): predicated-off mask code would still take issue slots
+          auto exp_body = [&](auto tag) {
+            constexpr bool kFull = decltype(tag)::value;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float a0, a1;
-            unpack2(fma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, nmsc2), a0, a1);
-            float e0 = ex2(a0), e1 = ex2(a1);
-            if (!full) { e0 = ((wd >> j) & 1u) ? e0 : 0.f; e1 = ((wd >> (j + 1)) & 1u) ? e1 : 0.f; }
-            l2[(j >> 1) & 1] = add2(l2[(j >> 1) & 1], pack2(e0, e1));
-            r[j] = __float_as_uint(e0); r[j + 1] = __float_as_uint(e1);
-          }
+            for (int j = 0; j < 32; j += 2) {
+              float a0, a1;
+              unpack2(fma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, nmsc2), a0, a1);
+              float e0 = ex2(a0), e1 = ex2(a1);
+              if constexpr (!kFull) { e0 = ((wd >> j) & 1u) ? e0 : 0.f; e1 = ((wd >> (j + 1)) & 1u) ? e1 : 0.f; }
+              l2[(j >> 1) & 1] = add2(l2[(j >> 1) & 1], pack2(e0, e1));
+              r[j] = __float_as_uint(e0); r[j + 1] = __float_as_uint(e1);
+            }
+          };
+          if (__all_sync(0xffffffffu, wd == 0xffffffffu)) exp_body(std::true_type{}); else exp_body(std::false_type{});
           uint8_t* atom = sm.p + row * 128 + (c >> 1) * (SQ * 128);
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
@@ -597,16 +602,20 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       float dl4[4] = {0.f, 0.f, 0.f, 0.f};
       // half = 16 score columns: bits [16*half, +16) of the chunk's mask word, packed P words [8*half, +8)
       auto pass1 = [&](const uint32_t w16, const uint32_t (&rs)[16], const uint32_t (&rd)[16], uint32_t (&pk)[8]) {
-        const bool full = (w16 == 0xffffu);
+        // two copies of the loop (warp-uniform choice): predicated-off mask code would still take issue slots
+        auto body = [&](auto tag) {
+          constexpr bool kFull = decltype(tag)::value;
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          float p0 = ex2(fmaf(__uint_as_float(rs[j]), sc, -lse));
-          float p1 = ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse));
-          if (!full) { p0 = ((w16 >> j) & 1u) ? p0 : 0.f; p1 = ((w16 >> (j + 1)) & 1u) ? p1 : 0.f; }
-          dl4[(j >> 1) & 3] = fmaf(p0, __uint_as_float(rd[j]), dl4[(j >> 1) & 3]);
-          dl4[(j >> 1) & 3] = fmaf(p1, __uint_as_float(rd[j + 1]), dl4[(j >> 1) & 3]);
-          pk[j >> 1] = pack_bf16(p0, p1);
-        }
+          for (int j = 0; j < 16; j += 2) {
+            float p0 = ex2(fmaf(__uint_as_float(rs[j]), sc, -lse));
+            float p1 = ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse));
+            if constexpr (!kFull) { p0 = ((w16 >> j) & 1u) ? p0 : 0.f; p1 = ((w16 >> (j + 1)) & 1u) ? p1 : 0.f; }
+            dl4[(j >> 1) & 3] = fmaf(p0, __uint_as_float(rd[j]), dl4[(j >> 1) & 3]);
+            dl4[(j >> 1) & 3] = fmaf(p1, __uint_as_float(rd[j + 1]), dl4[(j >> 1) & 3]);
+            pk[j >> 1] = pack_bf16(p0, p1);
+          }
+        };
+        if (__all_sync(0xffffffffu, w16 == 0xffffu)) body(std::true_type{}); else body(std::false_type{});
       };
       auto exchange_delta = [&]() {
         sm.red_delta[par][cg][row] = (dl4[0] + dl4[1]) + (dl4[2] + dl4[3]);
@@ -924,12 +933,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
       tc_fence_before();
       mbar_arrive(&sm.sdp_empty);
       if (threadIdx.x == 64) TRACE(6, 6 * s + 3);
-      const bool full = (wd == 0xffffffffu);
       const f32x2 lg2 = splat2(lg), m1 = splat2(-1.f), sc2 = splat2(sc), scale2 = splat2(p.scale), nscale2 = splat2(-p.scale);
       // the P^T / dS^T tiles of the previous step must have been consumed by its dV / dK products (they were issued
       // while this step waited for its scores, so this wait is short; it lets every group be stored as it is formed)
       if (s > 0) mbar_wait(&sm.pds_free, (s - 1) & 1);
       if (threadIdx.x == 64) TRACE(6, 6 * s + 4);
+      // two copies of the loop (warp-uniform choice): predicated-off mask code would still take issue slots
+      auto body = [&](auto tag) {
+      constexpr bool kFull = decltype(tag)::value;
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {
         uint32_t po[4], dso[4];
@@ -948,7 +959,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
           float a0, a1;
           unpack2(fma2(pack2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), sc2, nl[e2]), a0, a1);
           float p0 = ex2(a0), p1 = ex2(a1);
-          if (!full) { p0 = ((wd >> j) & 1u) ? p0 : 0.f; p1 = ((wd >> (j + 1)) & 1u) ? p1 : 0.f; }
+          if constexpr (!kFull) { p0 = ((wd >> j) & 1u) ? p0 : 0.f; p1 = ((wd >> (j + 1)) & 1u) ? p1 : 0.f; }
           po[e2] = pack_bf16(p0, p1);
           float s0, s1;
           unpack2(mul2(pack2(p0, p1), fma2(pack2(__uint_as_float(rd[j]), __uint_as_float(rd[j + 1])), scale2, nd[e2])), s0, s1);
@@ -958,6 +969,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
         *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[0], po[1], po[2], po[3]);
         *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
       }
+      };
+      if (__all_sync(0xffffffffu, wd == 0xffffffffu)) body(std::true_type{}); else body(std::false_type{});
       if (threadIdx.x == 64) TRACE(6, 6 * s + 5);
       fence_proxy_async_smem();
       mbar_arrive(&sm.pds_full);
