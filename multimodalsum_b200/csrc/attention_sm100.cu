@@ -149,7 +149,7 @@ __device__ __forceinline__ void key_bitmask(const MmsumAttnArgs& p, const EntIte
 }
 
 struct FwdSmem {
-  uint8_t q[SQ * 128];
+  uint8_t q[2][SQ * 128];      // 2-deep only in head mode (one Q tile per item); otherwise stage 0 holds the CTA's Q
   uint8_t k[2][kKVStageBytes];
   uint8_t v[2][kKVStageBytes];
   uint8_t p[kPBytes];
@@ -157,30 +157,43 @@ struct FwdSmem {
   float red_sum[2][4][SQ];
   uint32_t kmask[kMaxEnt][8];
   EntItem items[kMaxEnt];
-  uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], p_full, mma2_done;
+  uint64_t q_full[2], q_empty[2], k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], s_empty[2], p_full, mma2_done;
   uint32_t tmem_slot;
   int n_items;
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p) {
+attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p, const int head_mode) {
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window with pointer arithmetic on the __shared__ array so the compiler keeps the
   // shared address space (LDS/STS instead of generic LD/ST)
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tgt = blockIdx.x % p.R;
-  const int h = (blockIdx.x / p.R) % p.H;
-  const int biz = blockIdx.x / (p.R * p.H);
+  // head mode (self-attention: one modality, one entity): the CTA owns a whole sequence and its items are the H heads,
+  // so the per-CTA set-up and the load / MMA / softmax latencies are amortised and overlapped over 16 items instead of
+  // being paid by 16 single-item CTAs.  Otherwise the CTA owns one (sequence, head) and its items are the entities.
+  const int tgt = head_mode ? (int)(blockIdx.x % p.R) : (int)(blockIdx.x % p.R);
+  const int h = head_mode ? 0 : (int)((blockIdx.x / p.R) % p.H);
+  const int biz = head_mode ? (int)(blockIdx.x / p.R) : (int)(blockIdx.x / (p.R * p.H));
   const int qseq = biz * p.R + tgt;
   const int qrow0 = qseq * SQ;
+  auto item_head = [&](int i) { return head_mode ? i : h; };
 
   if (warp == 0) {
-    const int n = build_ent_items(p, qseq, sm.items, lane);
+    int n = build_ent_items(p, qseq, sm.items, lane);
+    if (head_mode) {                       // replicate the single entity once per head
+      __syncwarp();
+      if (n > 0) {
+        const EntItem it0 = sm.items[0];
+        __syncwarp();
+        if (lane < p.H) sm.items[lane] = it0;
+        n = p.H;
+      }
+    }
     if (lane == 0) sm.n_items = n;
   }
   if (threadIdx.x == 32) {
-    mbar_init(&sm.q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&sm.q_full[s], 1); mbar_init(&sm.q_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1);
       mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1);
@@ -204,16 +217,23 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(&sm.q_full, SQ * 128);
-      tma_load_2d(sm.q, &maps.q, &sm.q_full, p.q_col + h * HD, qrow0);
+      if (!head_mode) {
+        mbar_expect_tx(&sm.q_full[0], SQ * 128);
+        tma_load_2d(sm.q[0], &maps.q, &sm.q_full[0], p.q_col + h * HD, qrow0);
+      }
       // K stages are released as soon as S = Q K^T has retired, V stages only after P V: two independent rings
       for (int i = 0; i < n_items; ++i) {
         const int st = i & 1;
+        if (head_mode) {                   // this item's Q tile (released by the same commit as its K stage)
+          mbar_wait(&sm.q_empty[st], ((i >> 1) & 1) ^ 1);
+          mbar_expect_tx(&sm.q_full[st], SQ * 128);
+          tma_load_2d(sm.q[st], &maps.q, &sm.q_full[st], p.q_col + i * HD, qrow0);
+        }
         mbar_wait(&sm.k_empty[st], ((i >> 1) & 1) ^ 1);
         const EntItem it = sm.items[i];
         mbar_expect_tx(&sm.k_full[st], it.nkeys * 128);
         TRACE(0, i);
-        tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.k_full[st], p.k_col + h * HD, it.kv_row0);
+        tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.k_full[st], p.k_col + item_head(i) * HD, it.kv_row0);
       }
     } else if (lane == 1) {
       for (int i = 0; i < n_items; ++i) {
@@ -221,20 +241,22 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
         mbar_wait(&sm.v_empty[st], ((i >> 1) & 1) ^ 1);
         const EntItem it = sm.items[i];
         mbar_expect_tx(&sm.v_full[st], it.nkeys * 128);
-        tma_load_2d(sm.v[st], &maps.kv[it.mod], &sm.v_full[st], p.v_col + h * HD, it.kv_row0);
+        tma_load_2d(sm.v[st], &maps.kv[it.mod], &sm.v_full[st], p.v_col + item_head(i) * HD, it.kv_row0);
       }
     }
   } else if (warp == 1) {
     build_masks(p, sm.items, n_items, sm.kmask, 0, lane);
     if (n_items > 0) {   // whole warp runs the issue loop; elect.sync picks the issuing lane per instruction
-      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sm.q), 16, 1024);
+      const uint64_t qdesc0 = umma_smem_desc_sw128(smem_u32(sm.q[0]), 16, 1024), qdesc1 = umma_smem_desc_sw128(smem_u32(sm.q[1]), 16, 1024);
       const uint64_t kdesc0 = umma_smem_desc_sw128(smem_u32(sm.k[0]), 16, 1024), kdesc1 = umma_smem_desc_sw128(smem_u32(sm.k[1]), 16, 1024);
       const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sm.p), 16, 1024);
       const uint64_t vdesc0 = umma_smem_desc_sw128(smem_u32(sm.v[0]), 8192, 1024), vdesc1 = umma_smem_desc_sw128(smem_u32(sm.v[1]), 8192, 1024);
-      mbar_wait(&sm.q_full, 0);
+      if (!head_mode) mbar_wait(&sm.q_full[0], 0);
       auto issue_s = [&](int i) {
         const int st = i & 1;
         const EntItem it = sm.items[i];
+        if (head_mode) mbar_wait(&sm.q_full[st], (i >> 1) & 1);
+        const uint64_t qdesc = (head_mode && st) ? qdesc1 : qdesc0;
         mbar_wait(&sm.k_full[st], (i >> 1) & 1);
         if (lane == 0) TRACE(1, 2 * i);
         mbar_wait(&sm.s_empty[st], ((i >> 1) & 1) ^ 1);
@@ -248,6 +270,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
           umma_bf16_w(dcol, desc_adv(qdesc, kk * 32), desc_adv(kdesc, kk * 32), idesc, kk > 0);
         umma_commit_w(&sm.s_full[st]);
         umma_commit_w(&sm.k_empty[st]);
+        if (head_mode) umma_commit_w(&sm.q_empty[st]);
       };
       issue_s(0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
@@ -287,8 +310,8 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
     bf16* Og = reinterpret_cast<bf16*>(p.O);
-    auto flush = [&](int m) {
-      bf16* dst = Og + p.mods[m].o_off + (long long)(qrow0 + row) * p.ldo + h * HD + cg * 16;
+    auto flush = [&](int m, int head) {
+      bf16* dst = Og + p.mods[m].o_off + (long long)(qrow0 + row) * p.ldo + head * HD + cg * 16;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         uint4 u;
@@ -308,12 +331,12 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
     };
     // finish the bookkeeping of the previous entity once all four column groups have published their partial sums
     float msc_prev = 0.f, invn_prev = 0.f;
-    int ent_prev = 0;
+    int ent_prev = 0, head_prev = h;
     auto close_prev = [&](int par_prev) {
       const float l = (sm.red_sum[par_prev][0][row] + sm.red_sum[par_prev][1][row]) +
                       (sm.red_sum[par_prev][2][row] + sm.red_sum[par_prev][3][row]);
       if (cg == 0)
-        p.LSE[(((long long)qseq * p.H + h) * p.E_total + ent_prev) * SQ + row] = (l > 0.f) ? (msc_prev + __log2f(l)) : INFINITY;
+        p.LSE[(((long long)qseq * p.H + head_prev) * p.E_total + ent_prev) * SQ + row] = (l > 0.f) ? (msc_prev + __log2f(l)) : INFINITY;
       return (l > 0.f) ? __fdividef(invn_prev, l) : 0.f;
     };
     int cur_mod = 0;
@@ -365,8 +388,9 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
         if (threadIdx.x == 64) TRACE(3, 6 * i + 4);
         tc_fence_after();
         add_o(w_prev);
+        if (head_mode) flush(0, i - 1);    // previous head's output is complete
       }
-      while (cur_mod < it.mod) { flush(cur_mod); ++cur_mod; }
+      while (cur_mod < it.mod) { flush(cur_mod, h); ++cur_mod; }
       // exp pass: P = exp2(s*sc - m) -> bf16 into the swizzled A-operand tile; partial row sum
       f32x2 l2[2] = {splat2(0.f), splat2(0.f)};     // packed fp32 pairs (FFMA2 / FADD2): issue slots are the limit
       const f32x2 sc2 = splat2(sc), nmsc2 = splat2(-msc);
@@ -415,7 +439,7 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       mbar_arrive(&sm.s_empty[st]);
       fence_proxy_async_smem();
       mbar_arrive(&sm.p_full);
-      msc_prev = msc; invn_prev = inv_n; ent_prev = it.ent;
+      msc_prev = msc; invn_prev = inv_n; ent_prev = it.ent; head_prev = item_head(i);
     }
     if (n_items > 0) {
       soft_bar();                                   // partial sums of the last entity are visible
@@ -424,7 +448,12 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p)
       tc_fence_after();
       add_o(w_prev);
     }
-    while (cur_mod < p.n_mod) { flush(cur_mod); ++cur_mod; }
+    if (head_mode) {
+      if (n_items > 0) flush(0, n_items - 1);
+      else for (int hh = 0; hh < p.H; ++hh) flush(0, hh);      // null entity: zero rows for every head
+    } else {
+      while (cur_mod < p.n_mod) { flush(cur_mod, h); ++cur_mod; }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -447,30 +476,46 @@ struct BwdQSmem {
   float red_delta[2][4][SQ];
   uint32_t kmask[kMaxEnt][8];
   EntItem items[kMaxEnt];
-  uint64_t q_full, da_full, da_free, k_full[2], k_empty[2], v_full[2], v_empty[2], sdp_full, s_empty, dp_empty, ds_full, ds_free;
+  uint64_t q_full, da_full, da_free, qd_full[2], qd_empty[2], k_full[2], k_empty[2], v_full[2], v_empty[2], sdp_full, s_empty, dp_empty, ds_full, ds_free;
   uint32_t tmem_slot;
   int n_items;
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p) {
+attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p, const int head_mode) {
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window with pointer arithmetic on the __shared__ array so the compiler keeps the
   // shared address space (LDS/STS instead of generic LD/ST)
   BwdQSmem& sm = *reinterpret_cast<BwdQSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // head mode (self-attention, <= 128 keys): the CTA owns a whole sequence and its items are the H heads (see the forward
+  // kernel); each item then has its own Q / dA tiles (2-deep ring: stage 1 lives in the unused upper half of the dS
+  // region) and its own dQ, read out of TMEM one item later.
   const int tgt = blockIdx.x % p.R;
-  const int h = (blockIdx.x / p.R) % p.H;
-  const int biz = blockIdx.x / (p.R * p.H);
+  const int h = head_mode ? 0 : (int)((blockIdx.x / p.R) % p.H);
+  const int biz = head_mode ? (int)(blockIdx.x / p.R) : (int)(blockIdx.x / (p.R * p.H));
   const int qseq = biz * p.R + tgt;
   const int qrow0 = qseq * SQ;
+  auto item_head = [&](int i) { return head_mode ? i : h; };
+  uint8_t* const q_stage1 = sm.ds + 2 * SQ * 128;
+  uint8_t* const da_stage1 = sm.ds + 3 * SQ * 128;
 
   if (warp == 0) {
-    const int n = build_ent_items(p, qseq, sm.items, lane);
+    int n = build_ent_items(p, qseq, sm.items, lane);
+    if (head_mode) {                       // replicate the single entity once per head
+      __syncwarp();
+      if (n > 0) {
+        const EntItem it0 = sm.items[0];
+        __syncwarp();
+        if (lane < p.H) sm.items[lane] = it0;
+        n = p.H;
+      }
+    }
     if (lane == 0) sm.n_items = n;
   }
   if (threadIdx.x == 32) {
     mbar_init(&sm.q_full, 1); mbar_init(&sm.da_full, 1); mbar_init(&sm.da_free, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&sm.qd_full[s], 1); mbar_init(&sm.qd_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1);
       mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1);
@@ -491,13 +536,20 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(&sm.q_full, SQ * 128);
-      tma_load_2d(sm.q, &maps.q, &sm.q_full, p.q_col + h * HD, qrow0);
+      if (!head_mode) {
+        mbar_expect_tx(&sm.q_full, SQ * 128);
+        tma_load_2d(sm.q, &maps.q, &sm.q_full, p.q_col + h * HD, qrow0);
+      }
       int cur_mod = -1, n_da = 0;
       for (int i = 0; i < n_items; ++i) {
         const int st = i & 1;
         const EntItem it = sm.items[i];
-        if (it.mod != cur_mod) {
+        if (head_mode) {                   // this head's Q and dA tiles
+          mbar_wait(&sm.qd_empty[st], ((i >> 1) & 1) ^ 1);
+          mbar_expect_tx(&sm.qd_full[st], 2 * SQ * 128);
+          tma_load_2d(st ? q_stage1 : sm.q, &maps.q, &sm.qd_full[st], p.q_col + i * HD, qrow0);
+          tma_load_2d(st ? da_stage1 : sm.da, &maps.d_o, &sm.qd_full[st], i * HD, (int)(p.mods[it.mod].o_off / p.ldo) + qrow0);
+        } else if (it.mod != cur_mod) {
           mbar_wait(&sm.da_free, (n_da & 1) ^ 1);      // previous modality's dP MMAs have retired
           mbar_expect_tx(&sm.da_full, SQ * 128);
           tma_load_2d(sm.da, &maps.d_o, &sm.da_full, h * HD, (int)(p.mods[it.mod].o_off / p.ldo) + qrow0);
@@ -506,7 +558,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         // V is only read by dP' = dA V^T (released early); K also feeds dQ += dS K (released late): two rings
         mbar_wait(&sm.v_empty[st], ((i >> 1) & 1) ^ 1);
         mbar_expect_tx(&sm.v_full[st], it.nkeys * 128);
-        tma_load_2d(sm.v[st], &maps.kv[it.mod], &sm.v_full[st], p.v_col + h * HD, it.kv_row0);
+        tma_load_2d(sm.v[st], &maps.kv[it.mod], &sm.v_full[st], p.v_col + item_head(i) * HD, it.kv_row0);
       }
     } else if (lane == 1) {
       for (int i = 0; i < n_items; ++i) {
@@ -514,23 +566,27 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         const EntItem it = sm.items[i];
         mbar_wait(&sm.k_empty[st], ((i >> 1) & 1) ^ 1);
         mbar_expect_tx(&sm.k_full[st], it.nkeys * 128);
-        tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.k_full[st], p.k_col + h * HD, it.kv_row0);
+        tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.k_full[st], p.k_col + item_head(i) * HD, it.kv_row0);
       }
     }
   } else if (warp == 1) {
     build_masks(p, sm.items, n_items, sm.kmask, 0, lane);
     if (n_items > 0) {   // whole warp runs the issue loop; elect.sync picks the issuing lane per instruction
-      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sm.q), 16, 1024), dadesc = umma_smem_desc_sw128(smem_u32(sm.da), 16, 1024);
+      const uint64_t qdesc0 = umma_smem_desc_sw128(smem_u32(sm.q), 16, 1024), dadesc0 = umma_smem_desc_sw128(smem_u32(sm.da), 16, 1024);
+      const uint64_t qdesc1 = umma_smem_desc_sw128(smem_u32(q_stage1), 16, 1024), dadesc1 = umma_smem_desc_sw128(smem_u32(da_stage1), 16, 1024);
       const uint64_t dsdesc = umma_smem_desc_sw128(smem_u32(sm.ds), 16, 1024);
       const uint64_t kdesc_k[2] = {umma_smem_desc_sw128(smem_u32(sm.k[0]), 16, 1024), umma_smem_desc_sw128(smem_u32(sm.k[1]), 16, 1024)};
       const uint64_t kdesc_mn[2] = {umma_smem_desc_sw128(smem_u32(sm.k[0]), 8192, 1024), umma_smem_desc_sw128(smem_u32(sm.k[1]), 8192, 1024)};
       const uint64_t vdesc_k[2] = {umma_smem_desc_sw128(smem_u32(sm.v[0]), 16, 1024), umma_smem_desc_sw128(smem_u32(sm.v[1]), 16, 1024)};
-      mbar_wait(&sm.q_full, 0);
+      if (!head_mode) mbar_wait(&sm.q_full, 0);
       int cur_mod = -1, n_da = 0;
       auto issue_sdp = [&](int i) {
         const int st = i & 1;
         const EntItem it = sm.items[i];
-        if (it.mod != cur_mod) { mbar_wait(&sm.da_full, n_da & 1); cur_mod = it.mod; ++n_da; }
+        const uint64_t qdesc = (head_mode && st) ? qdesc1 : qdesc0, dadesc = (head_mode && st) ? dadesc1 : dadesc0;
+        if (head_mode) {
+          mbar_wait(&sm.qd_full[st], (i >> 1) & 1);
+        } else if (it.mod != cur_mod) { mbar_wait(&sm.da_full, n_da & 1); cur_mod = it.mod; ++n_da; }
         mbar_wait(&sm.k_full[st], (i >> 1) & 1);
         // the S columns are handed back after pass 1 of the previous entity, the dP' columns once pass 2 has
         // re-read them: both products of entity i+1 overlap the softmax work of entity i
@@ -550,7 +606,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         umma_commit_w(&sm.sdp_full);
         umma_commit_w(&sm.v_empty[st]);
         // last item of its modality: the dA tile may be replaced once these MMAs retire
-        if (i + 1 >= n_items || sm.items[i + 1].mod != it.mod) umma_commit_w(&sm.da_free);
+        if (head_mode) umma_commit_w(&sm.qd_empty[st]);
+        else if (i + 1 >= n_items || sm.items[i + 1].mod != it.mod) umma_commit_w(&sm.da_free);
       };
       issue_sdp(0);
       const uint32_t idesc_q = umma_idesc_bf16(128, HD, 0, 1);
@@ -566,7 +623,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         for (int kk = 0; kk < kMaxKeys / 16; ++kk)
           if (kk < nk)
             umma_bf16_w(tmem + kColDQ, desc_adv(dsdesc, (kk >> 2) * (SQ * 128) + (kk & 3) * 32), desc_adv(kd, kk * 2048), idesc_q,
-                      (i > 0 || kk > 0) ? 1u : 0u);
+                      ((i > 0 && !head_mode) || kk > 0) ? 1u : 0u);
         umma_commit_w(&sm.k_empty[st]);
         umma_commit_w(&sm.ds_free);
       }
@@ -579,6 +636,22 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float sc = p.scale * kLog2e;
     build_masks(p, sm.items, n_items, sm.kmask, warp - 1, lane);
+    // dQ columns [16cg, 16cg+16) of this row out of TMEM (caller has waited for the dQ MMAs) -> global, for one head
+    auto store_dq = [&](int head) {
+      bf16* dQg = reinterpret_cast<bf16*>(p.dQ) + (long long)(qrow0 + row) * p.lddq + p.dq_col + head * HD + cg * 16;
+      uint32_t r[16];
+      tmem_ld_32x16(tmem + lane_off + kColDQ + cg * 16, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint4 u;
+        u.x = pack_bf16(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
+        u.y = pack_bf16(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
+        u.z = pack_bf16(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
+        u.w = pack_bf16(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
+        *reinterpret_cast<uint4*>(dQg + j * 8) = u;
+      }
+    };
     for (int i = 0; i < n_items; ++i) {
       const EntItem it = sm.items[i];
       const int par = i & 1;
@@ -588,7 +661,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       wd[0] = has[0] ? sm.kmask[i][cg] : 0u;
       wd[1] = has[1] ? sm.kmask[i][cg + 4] : 0u;
       if (p.causal) { wd[0] = causal_word(wd[0], row, cg); wd[1] = causal_word(wd[1], row, cg + 4); }
-      const long long li = (((long long)qseq * p.H + h) * p.E_total + it.ent) * SQ + row;
+      const long long li = (((long long)qseq * p.H + item_head(i)) * p.E_total + it.ent) * SQ + row;
       const float lse = p.LSE[li];
       const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
       mbar_wait(&sm.sdp_full, i & 1);
@@ -657,7 +730,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         mbar_arrive(&sm.s_empty);
         mbar_arrive(&sm.dp_empty);
         const float dw = exchange_delta();
-        if (i > 0) mbar_wait(&sm.ds_free, (i - 1) & 1);   // dQ MMA of the previous entity has consumed the dS tile
+        if (i > 0) {                                       // dQ MMA of the previous entity has consumed the dS tile
+          mbar_wait(&sm.ds_free, (i - 1) & 1);
+          if (head_mode) { tc_fence_after(); store_dq(i - 1); tc_fence_before(); }   // ... and the previous head's dQ is final
+        }
         if (has[0]) { pass2(cg, 0, dw, rda, pk[0]); pass2(cg, 1, dw, rdb, pk[1]); }
       } else {
         uint32_t pk[4][8] = {};
@@ -677,7 +753,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         tc_fence_before();
         mbar_arrive(&sm.s_empty);
         const float dw = exchange_delta();
-        if (i > 0) mbar_wait(&sm.ds_free, (i - 1) & 1);
+        if (i > 0) {
+          mbar_wait(&sm.ds_free, (i - 1) & 1);
+          if (head_mode) { tc_fence_after(); store_dq(i - 1); tc_fence_before(); }
+        }
         {
           uint32_t r0[16], r1[16];
           tmem_ld_32x16(tmem + lane_off + kColDP + cg * 32, r0);
@@ -701,26 +780,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       fence_proxy_async_smem();
       mbar_arrive(&sm.ds_full);
     }
-    // dQ: read the accumulator once every entity has been folded in
-    bf16* dQg = reinterpret_cast<bf16*>(p.dQ) + (long long)(qrow0 + row) * p.lddq + p.dq_col + h * HD + cg * 16;
+    // dQ: read the accumulator once every entity has been folded in (head mode: the last head's)
     if (n_items > 0) {
       mbar_wait(&sm.ds_free, (n_items - 1) & 1);
       tc_fence_after();
-      uint32_t r[16];
-      tmem_ld_32x16(tmem + lane_off + kColDQ + cg * 16, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
-        u.y = pack_bf16(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
-        u.z = pack_bf16(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
-        u.w = pack_bf16(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
-        *reinterpret_cast<uint4*>(dQg + j * 8) = u;
-      }
+      store_dq(head_mode ? n_items - 1 : h);
     } else {
-      *reinterpret_cast<uint4*>(dQg) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(dQg + 8) = make_uint4(0, 0, 0, 0);
+      for (int hh = head_mode ? 0 : h; hh < (head_mode ? p.H : h + 1); ++hh) {
+        bf16* dQg = reinterpret_cast<bf16*>(p.dQ) + (long long)(qrow0 + row) * p.lddq + p.dq_col + hh * HD + cg * 16;
+        *reinterpret_cast<uint4*>(dQg) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dQg + 8) = make_uint4(0, 0, 0, 0);
+      }
     }
   }
   tc_fence_before();
@@ -752,14 +822,15 @@ struct BwdKVSmem {
   float lse[2][QH];            // raw LSE / DELTA rows of the current and the next step (cp.async staged)
   float dlt[2][QH];
   float lg_invn[32];           // log2(1/n) of every target for this modality
-  uint64_t kv_full, qd_full[2], qd_empty[2], sdp_full, sdp_empty, pds_full, pds_free;
+  uint64_t kv_full, kv_free, qd_full[2], qd_empty[2], sdp_full, sdp_empty, pds_full, pds_free;
   uint32_t tmem_slot;
 };
 static constexpr uint32_t kColST = 0, kColDPT = 64, kColDK = 128, kColDV = 192;
 
 __global__ void __launch_bounds__(kKvThreads, 2)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_constant__ CUtensorMap do64,
-                       const __grid_constant__ CUtensorMap kv128, const MmsumAttnArgs p, int tiles_per_bh) {
+                       const __grid_constant__ CUtensorMap kv128, const MmsumAttnArgs p, int tiles_per_bh,
+                       const int head_mode) {
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window with pointer arithmetic on the __shared__ array so the compiler keeps the
   // shared address space (LDS/STS instead of generic LD/ST)
@@ -767,7 +838,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int rem = blockIdx.x % tiles_per_bh;
   const int bh = blockIdx.x / tiles_per_bh;
-  const int h = bh % p.H, biz = bh / p.H;
+  // head mode (self-attention): the CTA owns one (sequence, key tile) and walks a group of heads, so the set-up is paid once
+  // and every mbarrier simply keeps counting steps across heads (g = head index * n_steps + step)
+  // head_mode = heads per CTA (1 = one head per CTA)
+  const int hgroups = p.H / head_mode;
+  const int biz = bh / hgroups;
+  const int h_begin = (bh % hgroups) * head_mode, h_end = h_begin + head_mode;
   int m = 0, e = 0, tile = 0;
   for (m = 0; m < p.n_mod; ++m) {
     const int nt = (p.mods[m].Sk + SQ - 1) / SQ;
@@ -793,12 +869,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
       const int row = (warp & 3) * 32 + lane;
       const int cg = (warp - 2) >> 2;
       if (row < nkeys) {
-        bf16* dk = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dk_col + h * HD + cg * 32;
-        bf16* dv = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dv_col + h * HD + cg * 32;
+        for (int h = h_begin; h < h_end; ++h) {
+          bf16* dk = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dk_col + h * HD + cg * 32;
+          bf16* dv = dKV + (long long)(kvrow0 + row) * p.lddkv + p.dv_col + h * HD + cg * 32;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          *reinterpret_cast<uint4*>(dk + j * 8) = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(dv + j * 8) = make_uint4(0, 0, 0, 0);
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<uint4*>(dk + j * 8) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(dv + j * 8) = make_uint4(0, 0, 0, 0);
+          }
         }
       }
     }
@@ -806,7 +884,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
   }
 
   if (threadIdx.x == 0) {
-    mbar_init(&sm.kv_full, 1);
+    mbar_init(&sm.kv_full, 1); mbar_init(&sm.kv_free, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&sm.qd_full[s], 1); mbar_init(&sm.qd_empty[s], 1); }
     mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, kKvSoftThreads);
     mbar_init(&sm.pds_full, kKvSoftThreads); mbar_init(&sm.pds_free, 1);
@@ -825,16 +903,21 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(&sm.kv_full, 2 * SQ * 128);
-      tma_load_2d(sm.k, &kv128, &sm.kv_full, p.k_col + h * HD, kvrow0);
-      tma_load_2d(sm.v, &kv128, &sm.kv_full, p.v_col + h * HD, kvrow0);
-      for (int s = 0; s < n_steps; ++s) {
-        const int st = s & 1;
-        const int qrow0 = (biz * p.R + step_target(s)) * SQ + (s & 1) * QH;
-        mbar_wait(&sm.qd_empty[st], ((s >> 1) & 1) ^ 1);
-        mbar_expect_tx(&sm.qd_full[st], 2 * QH * 128);
-        tma_load_2d(sm.q[st], &q64, &sm.qd_full[st], p.q_col + h * HD, qrow0);
-        tma_load_2d(sm.da[st], &do64, &sm.qd_full[st], h * HD, (int)(md.o_off / p.ldo) + qrow0);
+      for (int h = h_begin; h < h_end; ++h) {
+        const int g0 = (h - h_begin) * n_steps;
+        // the K / V tiles are read by the S^T / dP^T products only: the previous head's last pair has retired
+        if (h > h_begin) mbar_wait(&sm.kv_free, (h - h_begin - 1) & 1);
+        mbar_expect_tx(&sm.kv_full, 2 * SQ * 128);
+        tma_load_2d(sm.k, &kv128, &sm.kv_full, p.k_col + h * HD, kvrow0);
+        tma_load_2d(sm.v, &kv128, &sm.kv_full, p.v_col + h * HD, kvrow0);
+        for (int s = 0; s < n_steps; ++s) {
+          const int g = g0 + s, st = g & 1;
+          const int qrow0 = (biz * p.R + step_target(s)) * SQ + (s & 1) * QH;
+          mbar_wait(&sm.qd_empty[st], ((g >> 1) & 1) ^ 1);
+          mbar_expect_tx(&sm.qd_full[st], 2 * QH * 128);
+          tma_load_2d(sm.q[st], &q64, &sm.qd_full[st], p.q_col + h * HD, qrow0);
+          tma_load_2d(sm.da[st], &do64, &sm.qd_full[st], h * HD, (int)(md.o_off / p.ldo) + qrow0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -847,9 +930,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
       const uint64_t dadesc_mn[2] = {umma_smem_desc_sw128(smem_u32(sm.da[0]), 8192, 1024), umma_smem_desc_sw128(smem_u32(sm.da[1]), 8192, 1024)};
       const uint32_t idesc_s = umma_idesc_bf16(128, QH, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
-      mbar_wait(&sm.kv_full, 0);
-      auto issue_sdp = [&](int s) {
+      const int g_total = (h_end - h_begin) * n_steps;
+      auto issue_sdp = [&](int s) {        // s = global step; the first step of a head waits for that head's K / V
         const int st = s & 1;
+        if (s % n_steps == 0) mbar_wait(&sm.kv_full, (s / n_steps) & 1);
         mbar_wait(&sm.qd_full[st], (s >> 1) & 1);
         if (lane == 0) TRACE(5, 4 * s);
         mbar_wait(&sm.sdp_empty, (s & 1) ^ 1);
@@ -863,21 +947,23 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16_w(tmem + kColDPT, desc_adv(vdesc, kk * 32), desc_adv(dd, kk * 32), idesc_s, kk > 0);
         umma_commit_w(&sm.sdp_full);
+        if (s % n_steps == n_steps - 1) umma_commit_w(&sm.kv_free);   // last reader of this head's K / V tiles
       };
       issue_sdp(0);
-      for (int s = 0; s < n_steps; ++s) {
-        if (s + 1 < n_steps) issue_sdp(s + 1);
+      for (int s = 0; s < g_total; ++s) {
+        if (s + 1 < g_total) issue_sdp(s + 1);
         const int st = s & 1;
+        const uint32_t first = (s % n_steps == 0) ? 0u : 1u;     // first step of a head starts fresh dK / dV accumulators
         mbar_wait(&sm.pds_full, s & 1);
         if (lane == 0) TRACE(5, 4 * s + 2);
         tc_fence_after();
         const uint64_t qd = st ? qdesc_mn[1] : qdesc_mn[0], dd = st ? dadesc_mn[1] : dadesc_mn[0];
 #pragma unroll
         for (int kk = 0; kk < QH / 16; ++kk)   // contraction over the step's 64 queries
-          umma_bf16_w(tmem + kColDV, desc_adv(ptdesc, kk * 32), desc_adv(dd, kk * 2048), idesc_o, (s > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_w(tmem + kColDV, desc_adv(ptdesc, kk * 32), desc_adv(dd, kk * 2048), idesc_o, (kk > 0) ? 1u : first);
 #pragma unroll
         for (int kk = 0; kk < QH / 16; ++kk)
-          umma_bf16_w(tmem + kColDK, desc_adv(dstdesc, kk * 32), desc_adv(qd, kk * 2048), idesc_o, (s > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_w(tmem + kColDK, desc_adv(dstdesc, kk * 32), desc_adv(qd, kk * 2048), idesc_o, (kk > 0) ? 1u : first);
         if (lane == 0) TRACE(5, 4 * s + 3);
         umma_commit_w(&sm.qd_empty[st]);
         umma_commit_w(&sm.pds_free);
@@ -894,35 +980,40 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
     const bool kvalid = (row < nkeys) && (p.key_valid == nullptr || p.key_valid[(long long)kvrow0 + row] != 0);
     uint8_t* patom = sm.pt + row * 128;
     uint8_t* datom = sm.dst + row * 128;
-    auto lse_index = [&](int s) {
+    auto lse_index = [&](int h, int s) {
       return (((long long)(biz * p.R + step_target(s)) * p.H + h) * p.E_total + ge) * SQ + (s & 1) * QH + (sw * 32 + lane);
     };
     // LSE / DELTA rows of a step are staged with cp.async one step ahead (no register dependency, so the global
     // latency never sits on the softmax critical path); P absorbs 1/n through  exp2(sc*s - (LSE - log2(1/n)))
-    auto stage_rows = [&](int s, int st) {
-      const long long i = lse_index(s);
+    auto stage_rows = [&](int h, int s, int st) {
+      const long long i = lse_index(h, s);
       cp_async_4(smem_u32(&sm.lse[st][sw * 32 + lane]), p.LSE + i);
       cp_async_4(smem_u32(&sm.dlt[st][sw * 32 + lane]), p.DELTA + i);
     };
-    if (sw < 2) stage_rows(0, 0);
+    if (sw < 2) stage_rows(h_begin, 0, 0);
     if (threadIdx.x - 64 < (unsigned)p.R && threadIdx.x - 64 < 32u) {
       const int tg = threadIdx.x - 64;
       sm.lg_invn[tg] = p.inv_n ? __log2f(p.inv_n[(long long)(biz * p.R + tg) * p.n_mod + m]) : 0.f;
     }
+    for (int h = h_begin; h < h_end; ++h) {
+    const int g0 = (h - h_begin) * n_steps;
     for (int s = 0; s < n_steps; ++s) {
-      const int st = s & 1;
+      const int g = g0 + s, st = g & 1;
       if (sw < 2) cp_async_wait_all();   // rows of this step (issued one step ago) have landed
       if (threadIdx.x == 64) TRACE(6, 6 * s);
       kv_soft_bar();   // stage st is visible; everybody is done with stage st^1 (read during step s-1)
       if (threadIdx.x == 64) TRACE(6, 6 * s + 1);
-      if ((sw < 2) && (s + 1 < n_steps)) stage_rows(s + 1, st ^ 1);
+      if (sw < 2) {
+        if (s + 1 < n_steps) stage_rows(h, s + 1, st ^ 1);
+        else if (h + 1 < h_end) stage_rows(h + 1, 0, st ^ 1);
+      }
       const float lg = sm.lg_invn[step_target(s)];
       uint32_t wd = kvalid ? 0xffffffffu : 0u;
       if (p.causal) {  // key (key0 + row) <= query ((s&1)*64 + cg*32 + j)  <=>  j >= key0 + row - (s&1)*64 - cg*32
         const int lo = key0 + row - (s & 1) * QH - cg * 32;
         wd &= (lo <= 0) ? 0xffffffffu : (lo >= 32 ? 0u : ~((1u << lo) - 1u));
       }
-      mbar_wait(&sm.sdp_full, s & 1);
+      mbar_wait(&sm.sdp_full, g & 1);
       if (threadIdx.x == 64) TRACE(6, 6 * s + 2);
       tc_fence_after();
       uint32_t rs[32], rd[32];
@@ -936,7 +1027,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
       const f32x2 lg2 = splat2(lg), m1 = splat2(-1.f), sc2 = splat2(sc), scale2 = splat2(p.scale), nscale2 = splat2(-p.scale);
       // the P^T / dS^T tiles of the previous step must have been consumed by its dV / dK products (they were issued
       // while this step waited for its scores, so this wait is short; it lets every group be stored as it is formed)
-      if (s > 0) mbar_wait(&sm.pds_free, (s - 1) & 1);
+      if (g > 0) mbar_wait(&sm.pds_free, (g - 1) & 1);
       if (threadIdx.x == 64) TRACE(6, 6 * s + 4);
       // two copies of the loop (warp-uniform choice): predicated-off mask code would still take issue slots
       auto body = [&](auto tag) {
@@ -975,7 +1066,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
       fence_proxy_async_smem();
       mbar_arrive(&sm.pds_full);
     }
-    mbar_wait(&sm.pds_free, (n_steps - 1) & 1);
+    mbar_wait(&sm.pds_free, (g0 + n_steps - 1) & 1);
     tc_fence_after();
     {
       // every lane issues the (.sync.aligned) TMEM loads; only lanes that own a key store
@@ -1002,6 +1093,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
           *reinterpret_cast<uint4*>(dv + j * 8) = w2;
         }
       }
+      tc_fence_before();   // the next head's first dV / dK products overwrite these accumulators
+    }
     }
   }
   tc_fence_before();
@@ -1071,7 +1164,9 @@ extern "C" int mmsum_attn_fwd(const MmsumAttnArgs* a, void* stream_v) {
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  attn_fwd_tc_kernel<<<a->n_qseq * a->H, kAttnThreads, smem, stream>>>(mp, *a);
+  // self-attention shape (one modality, one entity per sequence, no leave-one-out): heads become the CTA's items
+  const int head_mode = (a->n_mod == 1 && a->mods[0].E == 1 && !a->mods[0].loo && a->H <= kMaxEnt && a->n_qseq >= 64) ? 1 : 0;
+  attn_fwd_tc_kernel<<<head_mode ? a->n_qseq : a->n_qseq * a->H, kAttnThreads, smem, stream>>>(mp, *a, head_mode);
   MMSUM_CHECK_LAUNCH();
   return 0;
 }
@@ -1113,11 +1208,17 @@ extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
   // profiling knob (tools/gpu_bench_attn.py): MMSUM_ATTN_BWD_PART=1 launches only dQ/DELTA, =2 only dK/dV
   static const int part = [] { const char* e = getenv("MMSUM_ATTN_BWD_PART"); return e ? atoi(e) : 0; }();
   if (part != 2) {
-    attn_bwd_dq_tc_kernel<<<a->n_qseq * a->H, kAttnThreads, smem_q, stream>>>(mp, *a);
+    // self-attention shape: heads become the CTA's items (needs <= 128 keys: the Q / dA ring borrows the dS upper half)
+    const int head_mode = (a->n_mod == 1 && a->mods[0].E == 1 && !a->mods[0].loo && a->mods[0].Sk <= SQ && a->H <= kMaxEnt &&
+                           a->n_qseq >= 64) ? 1 : 0;
+    attn_bwd_dq_tc_kernel<<<head_mode ? a->n_qseq : a->n_qseq * a->H, kAttnThreads, smem_q, stream>>>(mp, *a, head_mode);
     MMSUM_CHECK_LAUNCH();
   }
   if (part != 1) {
-    attn_bwd_dkv_tc_kernel<<<n_biz * a->H * tiles, kKvThreads, smem_kv, stream>>>(q64, do64, kv128, *a, tiles);
+    // self-attention shape: 4 heads per CTA (amortises the set-up, still ~2 waves of 2 CTAs/SM at 144 sequences)
+    const int heads_per_cta = (a->n_mod == 1 && a->mods[0].E == 1 && !a->mods[0].loo && n_biz >= 64 && a->H % 4 == 0) ? 4 : 1;
+    attn_bwd_dkv_tc_kernel<<<n_biz * (a->H / heads_per_cta) * tiles, kKvThreads, smem_kv, stream>>>(q64, do64, kv128, *a, tiles,
+                                                                                              heads_per_cta);
     MMSUM_CHECK_LAUNCH();
   }
   return 0;

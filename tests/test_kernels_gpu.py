@@ -222,11 +222,12 @@ def _ref_attention(q, k, v, valid, causal, scale):
     return torch.softmax(w, -1) @ v
 
 
+@pytest.mark.parametrize("n_seq", [6, 72])   # 72 sequences: the kernels switch to one CTA per sequence with heads as items
 @pytest.mark.parametrize("causal", [False, True])
-def test_self_attention_fwd_bwd(causal):
+def test_self_attention_fwd_bwd(causal, n_seq):
     ops = _ops()
     torch.manual_seed(7)
-    N, H, S, hd = 6, 16, 128, 64
+    N, H, S, hd = n_seq, 16, 128, 64
     T = N * S
     qkv = (torch.randn(T, 3 * D, device=_dev()) * 1.0).to(torch.bfloat16)
     lens = torch.randint(20, S + 1, (N,), device=_dev())
