@@ -165,6 +165,8 @@ struct FwdSmem {
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p, const int head_mode) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();   // launched with programmatic stream serialization: nothing global is touched before this point
   // align inside the shared window with pointer arithmetic on the __shared__ array so the compiler keeps the
   // shared address space (LDS/STS instead of generic LD/ST)
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -484,6 +486,8 @@ struct BwdQSmem {
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p, const int head_mode) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();   // launched with programmatic stream serialization: nothing global is touched before this point
   // align inside the shared window with pointer arithmetic on the __shared__ array so the compiler keeps the
   // shared address space (LDS/STS instead of generic LD/ST)
   BwdQSmem& sm = *reinterpret_cast<BwdQSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -832,6 +836,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
                        const __grid_constant__ CUtensorMap kv128, const MmsumAttnArgs p, int tiles_per_bh,
                        const int head_mode) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();   // launched with programmatic stream serialization: nothing global is touched before this point
   // align inside the shared window with pointer arithmetic on the __shared__ array so the compiler keeps the
   // shared address space (LDS/STS instead of generic LD/ST)
   BwdKVSmem& sm = *reinterpret_cast<BwdKVSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -1166,7 +1172,7 @@ extern "C" int mmsum_attn_fwd(const MmsumAttnArgs* a, void* stream_v) {
   }
   // self-attention shape (one modality, one entity per sequence, no leave-one-out): heads become the CTA's items
   const int head_mode = (a->n_mod == 1 && a->mods[0].E == 1 && !a->mods[0].loo && a->H <= kMaxEnt && a->n_qseq >= 64) ? 1 : 0;
-  attn_fwd_tc_kernel<<<head_mode ? a->n_qseq : a->n_qseq * a->H, kAttnThreads, smem, stream>>>(mp, *a, head_mode);
+  MMSUM_LAUNCH_PDL(attn_fwd_tc_kernel, head_mode ? a->n_qseq : a->n_qseq * a->H, kAttnThreads, smem, stream, mp, *a, head_mode);
   MMSUM_CHECK_LAUNCH();
   return 0;
 }
@@ -1211,14 +1217,14 @@ extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
     // self-attention shape: heads become the CTA's items (needs <= 128 keys: the Q / dA ring borrows the dS upper half)
     const int head_mode = (a->n_mod == 1 && a->mods[0].E == 1 && !a->mods[0].loo && a->mods[0].Sk <= SQ && a->H <= kMaxEnt &&
                            a->n_qseq >= 64) ? 1 : 0;
-    attn_bwd_dq_tc_kernel<<<head_mode ? a->n_qseq : a->n_qseq * a->H, kAttnThreads, smem_q, stream>>>(mp, *a, head_mode);
+    MMSUM_LAUNCH_PDL(attn_bwd_dq_tc_kernel, head_mode ? a->n_qseq : a->n_qseq * a->H, kAttnThreads, smem_q, stream, mp, *a, head_mode);
     MMSUM_CHECK_LAUNCH();
   }
   if (part != 1) {
     // self-attention shape: 4 heads per CTA (amortises the set-up, still ~2 waves of 2 CTAs/SM at 144 sequences)
     const int heads_per_cta = (a->n_mod == 1 && a->mods[0].E == 1 && !a->mods[0].loo && n_biz >= 64 && a->H % 4 == 0) ? 4 : 1;
-    attn_bwd_dkv_tc_kernel<<<n_biz * (a->H / heads_per_cta) * tiles, kKvThreads, smem_kv, stream>>>(q64, do64, kv128, *a, tiles,
-                                                                                              heads_per_cta);
+    MMSUM_LAUNCH_PDL(attn_bwd_dkv_tc_kernel, n_biz * (a->H / heads_per_cta) * tiles, kKvThreads, smem_kv, stream, q64, do64, kv128, *a,
+                     tiles, heads_per_cta);
     MMSUM_CHECK_LAUNCH();
   }
   return 0;

@@ -2,6 +2,7 @@
 // PTX wrappers for mbarrier / TMA / tcgen05, bf16 packing, a counter-based RNG
 // for dropout, and warp reductions.  No torch types anywhere in csrc/.
 #pragma once
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -11,6 +12,27 @@
 #define MMSUM_OK 0
 #define MMSUM_ERR_INVALID (-1)
 #define MMSUM_ERR_DRIVER (-2)
+
+// host: launch with the programmatic-stream-serialization attribute (the kernel must call pdl_wait() before touching
+// global memory)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool off = (getenv("MMSUM_NO_PDL") != nullptr);   // A/B switch for measurements
+  cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#define MMSUM_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                          \
+  do {                                                                                                   \
+    cudaError_t _le = launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__);  \
+    if (_le != cudaSuccess) return (int)_le;                                                             \
+  } while (0)
 
 #define MMSUM_CHECK_LAUNCH()                         \
   do {                                               \
@@ -117,6 +139,12 @@ __device__ __forceinline__ void gelu_erf_grad_mul2(float& g0, float& g1, float x
   const f32x2 d = fma2(x, mul2(E, splat2(0.3989422804014327f)), cdf);
   unpack2(mul2(pack2(g0, g1), d), g0, g1);
 }
+
+// Programmatic dependent launch: a kernel launched with launch_pdl() may begin (set-up only) while its predecessor on the
+// stream is still draining; pdl_wait() blocks until the predecessor grid has completed and its writes are visible, so it
+// must precede every global-memory access.  pdl_launch_dependents() lets the successor's CTAs be scheduled as SMs free up.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -106,6 +106,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();            // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop; lane 0 issues) =====================
@@ -408,7 +410,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI><<<grid, kGemmThreads, L::kTotal, stream>>>(ta, ta2, tb, td, taux, ka);
+  cudaError_t le = launch_pdl(gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>, dim3(grid), dim3(kGemmThreads), (size_t)L::kTotal, stream,
+                              ta, ta2, tb, td, taux, ka);
+  if (le != cudaSuccess) return (int)le;
   MMSUM_CHECK_LAUNCH();
   return 0;
 }

@@ -222,6 +222,8 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const bf16* __restrict_
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          bf16* __restrict__ out, float* __restrict__ mean_o,
                                                          float* __restrict__ rstd_o, int rows, DropCfg dc) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -255,6 +257,8 @@ __global__ void __launch_bounds__(128, 3) add_ln_bwd_kernel(const bf16* __restri
                                                             const float* __restrict__ rstd_i, bf16* __restrict__ dres,
                                                             bf16* __restrict__ dy_out, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int rows, DropCfg dc) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sacc[];                      // [4 warps][2][VPL][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float* sg = sacc + warp * (2 * VPL * 32);
@@ -327,6 +331,8 @@ __global__ void __launch_bounds__(128, 3) add_ln_bwd_kernel(const bf16* __restri
 // out[n] += sum_r x[r, n]   x bf16 [rows, ld]; N multiple of 8
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long ld, int rows, int N,
                                                      float* __restrict__ out, int rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sm[8][256];
   const int cg = threadIdx.x & 31;        // column group of 8
   const int rl = threadIdx.x >> 5;        // row lane 0..7
@@ -359,6 +365,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 __global__ void __launch_bounds__(256) gate_fwd_kernel(const bf16* __restrict__ o3, const bf16* __restrict__ u,
                                                        const uint8_t* __restrict__ pres, bf16* __restrict__ y,
                                                        bf16* __restrict__ ab, long long n, int rows_per_biz) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     const long long row = i / D;
@@ -389,6 +397,8 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(const bf16* __restrict__ 
 // du_a = dy*table*(alpha>0)*(1-alpha^2), du_b likewise with img / beta
 __global__ void __launch_bounds__(256) gate_bwd_u_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ o3,
                                                          const bf16* __restrict__ ab, bf16* __restrict__ du, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     const uint4 d4 = *reinterpret_cast<const uint4*>(dy + i);
@@ -414,6 +424,8 @@ __global__ void __launch_bounds__(256) gate_bwd_u_kernel(const bf16* __restrict_
 __global__ void __launch_bounds__(256) gate_bwd_o_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab,
                                                          const bf16* __restrict__ dca, const bf16* __restrict__ dcb,
                                                          bf16* __restrict__ do3, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     const long long row = i / D; const int c = (int)(i - row * D);
@@ -813,7 +825,7 @@ extern "C" int mmsum_add_ln_fwd(const void* res, const void* y, const float* gam
                                 float* mean, float* rstd, int32_t rows, int32_t d_model, float p_drop, uint64_t seed,
                                 uint32_t stream_id, void* stream) {
   if (d_model != D || rows <= 0 || !res || !y || !out) return MMSUM_ERR_INVALID;
-  add_ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(reinterpret_cast<const bf16*>(res),
+  MMSUM_LAUNCH_PDL(add_ln_fwd_kernel, (rows + 7) / 8, 256, 0, STREAM(stream), reinterpret_cast<const bf16*>(res),
                                                                  reinterpret_cast<const bf16*>(y), gamma, beta,
                                                                  reinterpret_cast<bf16*>(out), mean, rstd, rows,
                                                                  make_drop(p_drop, seed, stream_id));
@@ -832,7 +844,7 @@ extern "C" int mmsum_add_ln_bwd(const void* d1, const void* d2, const void* res,
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  add_ln_bwd_kernel<<<nblocks(rows, 4 * 4, 148 * 3), 128, 4 * 2 * VPL * 32 * 4, STREAM(stream)>>>(
+  MMSUM_LAUNCH_PDL(add_ln_bwd_kernel, nblocks(rows, 4 * 4, 148 * 3), 128, 4 * 2 * VPL * 32 * 4, STREAM(stream), 
       reinterpret_cast<const bf16*>(d1), reinterpret_cast<const bf16*>(d2), reinterpret_cast<const bf16*>(res),
       reinterpret_cast<const bf16*>(y), gamma, mean, rstd, reinterpret_cast<bf16*>(dres), reinterpret_cast<bf16*>(dy),
       dgamma, dbeta, rows, make_drop(p_drop, seed, stream_id));
@@ -845,7 +857,7 @@ extern "C" int mmsum_colsum(const void* x, int64_t ld, int32_t rows, int32_t N, 
   const int gx = (N + 255) / 256;
   int gy = (148 * 4) / gx; if (gy < 1) gy = 1; if (gy > (rows + 63) / 64) gy = (rows + 63) / 64;
   const int rpb = (rows + gy - 1) / gy;
-  colsum_kernel<<<dim3(gx, gy), 256, 0, STREAM(stream)>>>(reinterpret_cast<const bf16*>(x), ld, rows, N, out, rpb);
+  MMSUM_LAUNCH_PDL(colsum_kernel, dim3(gx, gy), 256, 0, STREAM(stream), reinterpret_cast<const bf16*>(x), ld, rows, N, out, rpb);
   MMSUM_CHECK_LAUNCH();
   return 0;
 }
@@ -854,7 +866,7 @@ extern "C" int mmsum_gate_fwd(const void* o3, const void* u, const uint8_t* pres
                               int32_t rows_per_biz, int32_t d_model, void* stream) {
   if (d_model != D || rows <= 0 || rows_per_biz <= 0) return MMSUM_ERR_INVALID;
   const long long n = (long long)rows * D;
-  gate_fwd_kernel<<<nblocks(n, 2048, 148 * 8), 256, 0, STREAM(stream)>>>(
+  MMSUM_LAUNCH_PDL(gate_fwd_kernel, nblocks(n, 2048, 148 * 8), 256, 0, STREAM(stream), 
       reinterpret_cast<const bf16*>(o3), reinterpret_cast<const bf16*>(u), pres, reinterpret_cast<bf16*>(y),
       reinterpret_cast<bf16*>(ab), n, rows_per_biz);
   MMSUM_CHECK_LAUNCH();
@@ -863,7 +875,7 @@ extern "C" int mmsum_gate_fwd(const void* o3, const void* u, const uint8_t* pres
 extern "C" int mmsum_gate_bwd_u(const void* dy, const void* o3, const void* ab, void* du, int32_t rows, int32_t d_model, void* stream) {
   if (d_model != D || rows <= 0) return MMSUM_ERR_INVALID;
   const long long n = (long long)rows * D;
-  gate_bwd_u_kernel<<<nblocks(n, 2048, 148 * 8), 256, 0, STREAM(stream)>>>(
+  MMSUM_LAUNCH_PDL(gate_bwd_u_kernel, nblocks(n, 2048, 148 * 8), 256, 0, STREAM(stream), 
       reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(o3), reinterpret_cast<const bf16*>(ab),
       reinterpret_cast<bf16*>(du), n);
   MMSUM_CHECK_LAUNCH();
@@ -873,7 +885,7 @@ extern "C" int mmsum_gate_bwd_o(const void* dy, const void* ab, const void* dca,
                                 int32_t d_model, void* stream) {
   if (d_model != D || rows <= 0) return MMSUM_ERR_INVALID;
   const long long n = (long long)rows * D;
-  gate_bwd_o_kernel<<<nblocks(n, 2048, 148 * 8), 256, 0, STREAM(stream)>>>(
+  MMSUM_LAUNCH_PDL(gate_bwd_o_kernel, nblocks(n, 2048, 148 * 8), 256, 0, STREAM(stream), 
       reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(ab), reinterpret_cast<const bf16*>(dca),
       reinterpret_cast<const bf16*>(dcb), reinterpret_cast<bf16*>(do3), n);
   MMSUM_CHECK_LAUNCH();
