@@ -73,29 +73,6 @@ __device__ __forceinline__ float fast_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float erf_as(float x, float& E) {   // returns erf(x / sqrt(2)); E = exp(-x*x/2)
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = fast_rcp(fmaf(0.3275911f, z, 1.f));
-  E = fast_ex2(x * x * -0.72134752044448170f);
-  float q = fmaf(t, 1.061405429f, -1.453152027f);
-  q = fmaf(q, t, 1.421413741f);
-  q = fmaf(q, t, -0.284496736f);
-  q = fmaf(q, t, 0.254829592f);
-  q *= t;
-  return copysignf(fmaf(-q, E, 1.f), x);
-}
-__device__ __forceinline__ float gelu_erf(float x) {
-  float E;
-  const float e = erf_as(x, E);
-  const float hx = 0.5f * x;
-  return fmaf(hx, e, hx);
-}
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  float E;
-  const float e = erf_as(x, E);
-  return fmaf(0.5f, e, 0.5f) + x * (0.3989422804014327f * E);
-}
-
 // Blackwell packed fp32 pairs (FFMA2 / FMUL2): one issue slot for two lanes of the same elementwise chain.
 struct f32x2 { uint64_t r; };
 __device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 o; asm("mov.b64 %0, {%1, %2};" : "=l"(o.r) : "f"(a), "f"(b)); return o; }
@@ -364,41 +341,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 }
 
 // ----------------------------------------------------------------------------
-// legacy warp-level MMA (m16n8k16 bf16) + ldmatrix — used by the attention kernels
+// cp.async (per-thread global -> shared copies with no register dependency)
 // ----------------------------------------------------------------------------
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(saddr));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(saddr));
-}
-__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(saddr));
-}
-__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(saddr));
-}
-__device__ __forceinline__ void cp_async_16(uint32_t saddr, const void* gptr, bool pred) {
-  int sz = pred ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gptr), "r"(sz) : "memory");
-}
 __device__ __forceinline__ void cp_async_4(uint32_t saddr, const void* gptr) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // 32 lanes x 16 columns of fp32
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
