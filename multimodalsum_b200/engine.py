@@ -14,6 +14,7 @@ B200-first design decisions:
 torch is used for memory (arenas, workspaces), streams and torch.distributed only.
 """
 import math
+import os
 
 import torch
 
@@ -66,16 +67,19 @@ def _arena_order(cfg: ModelConfig):
 
 
 class _Pool:
-    """Free-list of equally shaped scratch tensors.  Everything runs on one stream, so a buffer may be handed out
-    again as soon as its last consumer has been enqueued."""
+    """Free-list of equally shaped scratch tensors.  The step runs on one stream (plus the bias-gradient side stream,
+    which `before_put` joins), so a buffer may be handed out again as soon as its last consumer has been enqueued."""
 
     def __init__(self, n, shape, device):
         self.free = [torch.empty(shape, device=device, dtype=torch.bfloat16) for _ in range(n)]
+        self.before_put = None
 
     def get(self):
         return self.free.pop()
 
     def put(self, *ts):
+        if self.before_put is not None:
+            self.before_put()
         for t in ts:
             if t is not None and all(t is not f for f in self.free):
                 self.free.append(t)
@@ -100,6 +104,13 @@ class StepEngine:
         self.grad_ready_hook = None      # callable(lo, hi): gradient arena range [lo, hi) is final (data-parallel buckets)
         self._w16_version = -1
         self.anchor = None
+        # bias-gradient side stream (see _bias_grad); MMSUM_BIAS_SIDE_STREAM=0 keeps everything on one stream
+        self.side_stream = None
+        self._side_pending = False
+        if self.device.type == "cuda" and os.environ.get("MMSUM_BIAS_SIDE_STREAM", "1") != "0":
+            self.side_stream = torch.cuda.Stream(device=self.device)
+            self._ev_main = torch.cuda.Event()
+            self._ev_side = torch.cuda.Event()
 
     # ------------------------------------------------------------------ parameters
     def bind(self, named_params):
@@ -203,6 +214,7 @@ class StepEngine:
         w["loss"] = f32(1)
         # backward scratch
         w["pool"] = _Pool(5, (T, D), dev)
+        w["pool"].before_put = self._side_join
         w["dH"] = bf(T, FF)
         w["dqkv"] = bf(T, 3 * D)
         w["dkv"] = bf(Tm, 2 * D)
@@ -389,7 +401,29 @@ class StepEngine:
             out = out[:, col_slice[0]:col_slice[1]]
         ops.gemm(dy, x, out, a_t=True, b_t=True, accumulate=True)
 
+    # Bias gradients (column sums of an upstream-gradient matrix) are short, launch-latency-dominated kernels that sit
+    # off the critical dgrad chain: they run on a side stream and overlap the GEMMs that consume the same matrix.  The main
+    # stream joins the side stream before any scratch buffer is recycled, before a gradient range is declared final and
+    # at the end of backward.
+    def _bias_grad(self, x, out):
+        if self.side_stream is None:
+            ops.colsum(x, out)
+            return
+        main = torch.cuda.current_stream()
+        self._ev_main.record(main)
+        self.side_stream.wait_event(self._ev_main)
+        with torch.cuda.stream(self.side_stream):
+            ops.colsum(x, out)
+            self._ev_side.record(self.side_stream)
+        self._side_pending = True
+
+    def _side_join(self):
+        if self._side_pending:
+            torch.cuda.current_stream().wait_event(self._ev_side)
+            self._side_pending = False
+
     def _ready(self, name_last):
+        self._side_join()
         if self.grad_ready_hook is not None:
             hi = self.offsets[name_last] + (math.prod(self.shapes[name_last]) + ALIGN - 1) // ALIGN * ALIGN
             self.grad_ready_hook(hi)
@@ -403,13 +437,13 @@ class StepEngine:
                        self.g32(lp + "final_layer_norm.weight"), self.g32(lp + "final_layer_norm.bias"), pd, self.seed,
                        self._sid(kind, l))
         pool.put(d1, d2)
-        ops.colsum(df, self.g32(lp + "fc2.bias"))
+        self._bias_grad(df, self.g32(lp + "fc2.bias"))
         self._wgrad(df, a["a"], lp + "fc2.weight")
         dH = w["dH"]
         ops.gemm(df, self.w16(lp + "fc2.weight"), dH, b_t=True, act=ops.ACT_GELU, aux=a["h"], aux_mode=ops.AUX_MUL_DACT)
         if df is not dres:
             pool.put(df)
-        ops.colsum(dH, self.g32(lp + "fc1.bias"))
+        self._bias_grad(dH, self.g32(lp + "fc1.bias"))
         self._wgrad(dH, xin, lp + "fc1.weight")
         dx = pool.get()
         ops.gemm(dH, self.w16(lp + "fc1.weight"), dx, b_t=True)
@@ -425,7 +459,7 @@ class StepEngine:
                        self.g32(lp + "self_attn_layer_norm.weight"), self.g32(lp + "self_attn_layer_norm.bias"), pd, self.seed,
                        self._sid(kind, l))
         pool.put(d1, d2)
-        ops.colsum(do, self.g32(s + "out_proj.bias"))
+        self._bias_grad(do, self.g32(s + "out_proj.bias"))
         self._wgrad(do, a["ctx"], s + "out_proj.weight")
         dctx = pool.get()
         ops.gemm(do, self.w16(s + "out_proj.weight"), dctx, b_t=True)
@@ -434,7 +468,7 @@ class StepEngine:
         dqkv = w["dqkv"]
         ops.attn_bwd(self._self_attn_args(w, a["qkv"], dctx, a["lse"], key_valid, causal, bwd=dqkv))
         pool.put(dctx)
-        ops.colsum(dqkv, self.g32(s + "q_proj.bias", s + "v_proj.bias"))
+        self._bias_grad(dqkv, self.g32(s + "q_proj.bias", s + "v_proj.bias"))
         self._wgrad(dqkv, a["x"], s + "q_proj.weight", s + "v_proj.weight")
         dx = pool.get()
         ops.gemm(dqkv, self.w16(s + "q_proj.weight", s + "v_proj.weight"), dx, b_t=True)
@@ -484,8 +518,8 @@ class StepEngine:
             if multimodal:
                 dU, dO3 = w["dU"], w["dO3"]
                 ops.gate_bwd_u(dyc, a["O3"], a["AB"], dU, T, D)
-                ops.colsum(dU[0], self.g32(c + "alpha_proj.bias"))
-                ops.colsum(dU[1], self.g32(c + "beta_proj.bias"))
+                self._bias_grad(dU[0], self.g32(c + "alpha_proj.bias"))
+                self._bias_grad(dU[1], self.g32(c + "beta_proj.bias"))
                 self._wgrad(dU[0], a["O3"][0], c + "alpha_proj.weight", col_slice=(0, D))
                 self._wgrad(dU[0], a["O3"][1], c + "alpha_proj.weight", col_slice=(D, 2 * D))
                 self._wgrad(dU[1], a["O3"][0], c + "beta_proj.weight", col_slice=(0, D))
@@ -496,7 +530,7 @@ class StepEngine:
                 dO3f = dO3.view(nm * T, D)
             else:
                 dO3f = dyc
-            ops.colsum(dO3f, self.g32(c + "out_proj.bias"))
+            self._bias_grad(dO3f, self.g32(c + "out_proj.bias"))
             self._wgrad(dO3f, a["A3"].view(nm * T, D), c + "out_proj.weight")
             dA3 = w["dA3"]
             g(dO3f, self.w16(c + "out_proj.weight"), dA3.view(nm * T, D), b_t=True)
@@ -505,12 +539,12 @@ class StepEngine:
             dqc = pool.get()
             dkv = w["dkv"]
             ops.attn_bwd(self._cross_attn_args(w, a["qc"], a["kv"], dA3, a["lse_c"], bwd=(dqc, dkv)))
-            ops.colsum(dqc, self.g32(c + "q_proj.bias"))
+            self._bias_grad(dqc, self.g32(c + "q_proj.bias"))
             self._wgrad(dqc, a["x1"], c + "q_proj.weight")
             dx1 = pool.get()
             g(dqc, self.w16(c + "q_proj.weight"), dx1, b_t=True)
             pool.put(dqc)
-            ops.colsum(dkv, self.g32(c + "k_proj.bias", c + "v_proj.bias"))
+            self._bias_grad(dkv, self.g32(c + "k_proj.bias", c + "v_proj.bias"))
             self._wgrad(dkv, w["MEM"], c + "k_proj.weight", c + "v_proj.weight")
             g(dkv, self.w16(c + "k_proj.weight", c + "v_proj.weight"), w["dMEM32"], b_t=True, accumulate=True)
             # self block
@@ -533,7 +567,7 @@ class StepEngine:
             dtab = dMEM[T:T + B * F]
             self._wgrad(dtab, w["tab_h"], t + "linear.weight")
             g(dtab, self.w16(t + "linear.weight"), w["dtab_h"], b_t=True, act=ops.ACT_RELU, aux=w["tab_h"], aux_mode=ops.AUX_MUL_DACT)
-            ops.colsum(w["dtab_h"], self.g32(t + "fc.bias"))
+            self._bias_grad(w["dtab_h"], self.g32(t + "fc.bias"))
             self._wgrad(w["dtab_h"], w["tabX"], t + "fc.weight")
             g(w["dtab_h"], self.w16(t + "fc.weight"), w["dtabX"], b_t=True)
             batch = self._batch
