@@ -162,7 +162,8 @@ class Generator:
             kv.append(g(MEM, eng.w16(c + "k_proj.weight", c + "v_proj.weight"), bf(Tm, 2 * D),
                         bias=eng.w32(c + "k_proj.bias", c + "v_proj.bias")))
         return dict(B=B, R=R, Sp=Sp, Sk=Sk, F=F, n_img=n_img, ik=ik, T=T, Tm=Tm, kv=kv, mem_valid=mem_valid, ent_valid=ent_valid,
-                    inv_n=inv_n_biz.repeat_interleave(num_beams, dim=0).contiguous(), pres=pres, beams=num_beams, ws=None)
+                    inv_n=inv_n_biz.repeat_interleave(num_beams, dim=0).contiguous(), inv_n_biz=inv_n_biz.contiguous(), pres=pres,
+                    beams=num_beams, ws=None, cws=None)
 
     # ------------------------------------------------------------------ one decode step (all beams)
     @torch.no_grad()
@@ -228,23 +229,132 @@ class Generator:
         g(last, eng.w16(bm + "shared.weight"), w["logits"], bias=eng.w32_flb())
         return w["logits"]
 
+    # ------------------------------------------------------------------ one cached decode step (all beams)
+    @torch.no_grad()
+    def step_logits(self, st, input_ids, rating_diff):
+        """Incremental decoding (`_use_saved_state` / cached branch of `get_head_output`, modeling_multimodalsum.py:774-815,
+        889-920): only the newest token of every hypothesis goes through the decoder.  Self-attention K|V of all earlier
+        positions live in per-layer caches [N, 128, 2D] (the new row is written in place by the K|V GEMM), cross-attention
+        K|V are the static per-business projections from `encode`.  Call `reorder_cache(st, beam_idx)` after every beam
+        re-ranking (`_reorder_cache`, :3103-3115).  input_ids [N, cur_len] -> fp32 logits [N, V] of the last position.
+
+        The attention kernels work on 128-row query tiles: the self-attention query of hypothesis n sits in row t of its own
+        causal frame (rows != t are ignored), and the `beams` cross-attention queries of a business share one frame (rows
+        0..beams-1) because they attend to the same memory."""
+        eng, cfg = self.eng, self.eng.cfg
+        dev = input_ids.device
+        D, H, V, FF = cfg.d_model, cfg.heads, cfg.vocab_size, cfg.ffn_dim
+        N, cur = input_ids.shape
+        S = 128
+        if cur > S:
+            raise ValueError("decoder frames up to 128 tokens")
+        if st["beams"] > S:
+            raise ValueError("at most 128 beams")
+        t = cur - 1
+        beams, B = st["beams"], st["B"]
+        Et = st["R"] + 1 + st["n_img"]
+        if st["cws"] is None:
+            bf = lambda *s: torch.empty(s, device=dev, dtype=torch.bfloat16)
+            zbf = lambda *s: torch.zeros(s, device=dev, dtype=torch.bfloat16)
+            f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+            L = cfg.decoder_layers
+            st["cws"] = dict(x=bf(N, D), x1=bf(N, D), x2=bf(N, D), nxt=bf(N, D), o=bf(N, D), qc=bf(N, D), a=bf(N, FF), f=bf(N, D),
+                             qf=zbf(N * S, D), ctx=zbf(N * S, D),                 # self-attention query / context frames
+                             kvs=[zbf(N, S, 2 * D) for _ in range(L)],            # self-attention K|V caches (finite everywhere)
+                             kvs_alt=[zbf(N, S, 2 * D) for _ in range(L)],
+                             qcf=zbf(B * S, D), A3f=zbf(3, B * S, D),             # cross-attention frames: one per business
+                             A3=bf(3, N, D), O3=bf(3, N, D), U=bf(2, N, D), AB=bf(2, N, D), yc=bf(N, D),
+                             mean=f32(N), rstd=f32(N), lse=f32(N, H, 1, S), lse_c=f32(B, H, Et, S),
+                             ids=torch.empty(N, device=dev, dtype=torch.int32),
+                             logits=f32(N, (V + 3) // 4 * 4)[:, :V], pos=-1)
+        w = st["cws"]
+        if t != w["pos"] + 1:
+            raise ValueError("step_logits must be called with consecutive lengths (got position %d after %d)" % (t, w["pos"]))
+        w["pos"] = t
+        g = ops.gemm
+        bm = "bart_model.model."
+        pre = bm + "decoder."
+        w["ids"].copy_(input_ids[:, t])
+        x = w["x"]
+        # position t for every row: the kernel adds P[(row % S) + 2], so pass S = 1 and the table shifted by t rows
+        ops.embed_ln_fwd(w["ids"], eng.w32(bm + "shared.weight"), eng.w32(pre + "embed_positions.weight")[t:],
+                         rating_diff.reshape(-1).float().contiguous(), eng.w32(pre + "rating_embeddings"),
+                         eng.w32(pre + "layernorm_embedding.weight"), eng.w32(pre + "layernorm_embedding.bias"), x, w["mean"], w["rstd"],
+                         N, 1, 0.0, 0, 0)
+        R, Sp, Sk, F, n_img, ik, Tt = st["R"], st["Sp"], st["Sk"], st["F"], st["n_img"], st["ik"], st["T"]
+        Tf = B * S
+        mods = [(0, 0, R, Sk, 0, 0, Sp), (Tt, Tf * D, 1, F, 0, R, 0), (Tt + B * F, 2 * Tf * D, n_img, ik, 0, R + 1, 0)]
+        q_row = w["qf"].view(N, S, D)[:, t]          # strided [N, D] views: the GEMMs read / write them in place
+        ctx_row = w["ctx"].view(N, S, D)[:, t]
+        nxt = w["nxt"]
+        for l in range(cfg.decoder_layers):
+            lp = pre + "layers.%d." % l
+            s_, c = lp + "self_attn.", lp + "encoder_attn."
+            wqkv, bqkv = eng.w16(s_ + "q_proj.weight", s_ + "v_proj.weight"), eng.w32(s_ + "q_proj.bias", s_ + "v_proj.bias")
+            cache = w["kvs"][l]
+            g(x, wqkv[:D], q_row, bias=bqkv[:D])
+            g(x, wqkv[D:], cache[:, t], bias=bqkv[D:])                      # appends this position's K|V to the cache
+            ops.attn_fwd(ops.attn_args(Q=w["qf"], ldq=D, q_col=0, KV=cache.view(N * S, 2 * D), ldkv=2 * D, k_col=0, v_col=D, O=w["ctx"],
+                                       ldo=D, LSE=w["lse"], key_valid=None, ent_valid=None, inv_n=None, n_qseq=N, H=H, R=1, causal=1,
+                                       E_total=1, scale=cfg.head_dim ** -0.5, mods=[(0, 0, 1, S, 0, 0)]))
+            g(ctx_row, eng.w16(s_ + "out_proj.weight"), w["o"], bias=eng.w32(s_ + "out_proj.bias"))
+            ops.add_ln_fwd(x, w["o"], eng.w32(lp + "self_attn_layer_norm.weight"), eng.w32(lp + "self_attn_layer_norm.bias"), w["x1"],
+                           w["mean"], w["rstd"], 0.0, 0, 0)
+            g(w["x1"], eng.w16(c + "q_proj.weight"), w["qc"], bias=eng.w32(c + "q_proj.bias"))
+            w["qcf"].view(B, S, D)[:, :beams].copy_(w["qc"].view(B, beams, D))
+            ops.attn_fwd(ops.attn_args(Q=w["qcf"], ldq=D, q_col=0, KV=st["kv"][l], ldkv=2 * D, k_col=0, v_col=D, O=w["A3f"], ldo=D,
+                                       LSE=w["lse_c"], key_valid=st["mem_valid"], ent_valid=st["ent_valid"], inv_n=st["inv_n_biz"], n_qseq=B,
+                                       H=H, R=1, causal=0, E_total=Et, scale=cfg.head_dim ** -0.5, mods=mods))
+            w["A3"].view(3, B, beams, D).copy_(w["A3f"].view(3, B, S, D)[:, :, :beams])
+            g(w["A3"].view(3 * N, D), eng.w16(c + "out_proj.weight"), w["O3"].view(3 * N, D), bias=eng.w32(c + "out_proj.bias"))
+            ops.gemm_cat(w["O3"][0], w["O3"][1], eng.w16(c + "alpha_proj.weight"), w["U"][0], bias=eng.w32(c + "alpha_proj.bias"))
+            ops.gemm_cat(w["O3"][0], w["O3"][2], eng.w16(c + "beta_proj.weight"), w["U"][1], bias=eng.w32(c + "beta_proj.bias"))
+            ops.gate_fwd(w["O3"], w["U"], st["pres"], w["yc"], w["AB"], N, beams, D)
+            ops.add_ln_fwd(w["x1"], w["yc"], eng.w32(lp + "encoder_attn_layer_norm.weight"), eng.w32(lp + "encoder_attn_layer_norm.bias"),
+                           w["x2"], w["mean"], w["rstd"], 0.0, 0, 0)
+            g(w["x2"], eng.w16(lp + "fc1.weight"), w["a"], bias=eng.w32(lp + "fc1.bias"), act=ops.ACT_GELU)
+            g(w["a"], eng.w16(lp + "fc2.weight"), w["f"], bias=eng.w32(lp + "fc2.bias"))
+            ops.add_ln_fwd(w["x2"], w["f"], eng.w32(lp + "final_layer_norm.weight"), eng.w32(lp + "final_layer_norm.bias"), nxt,
+                           w["mean"], w["rstd"], 0.0, 0, 0)
+            x, nxt = nxt, x
+        w["x"], w["nxt"] = x, nxt
+        g(x, eng.w16(bm + "shared.weight"), w["logits"], bias=eng.w32_flb())
+        return w["logits"]
+
+    @torch.no_grad()
+    def reorder_cache(self, st, beam_idx):
+        """`_reorder_cache` (:3103-3115): hypothesis i continues hypothesis beam_idx[i]; only the self-attention caches move
+        (the cross-attention K|V are per business and beam_idx never crosses businesses)."""
+        w = st["cws"]
+        if w is None:
+            return
+        for l in range(len(w["kvs"])):
+            torch.index_select(w["kvs"][l], 0, beam_idx, out=w["kvs_alt"][l])
+            w["kvs"][l], w["kvs_alt"][l] = w["kvs_alt"][l], w["kvs"][l]
+
     # ------------------------------------------------------------------ public entry point (src/test.py:152-158)
     @torch.no_grad()
     def generate(self, reviews, reviews_mask, field, field_value, img, img_mask, rating_diff=None, num_beams=4, max_length=20,
-                 min_length=0, length_penalty=1.0, no_repeat_ngram_size=3, early_stopping=True):
+                 min_length=0, length_penalty=1.0, no_repeat_ngram_size=3, early_stopping=True, use_cache=True):
+        """use_cache=True: incremental decoding with self-attention K|V caches (`step_logits`); False: recompute the whole
+        prefix every step (`last_logits`, kept as the cross-check of the cached path)."""
         cfg = self.model.cfg
         B = reviews.shape[0]
         st = self.encode(reviews, reviews_mask, field, field_value, img, img_mask, num_beams)
         rd = torch.zeros(B, device=reviews.device) if rating_diff is None else rating_diff.reshape(B).float()
         rd = rd.repeat_interleave(num_beams).contiguous()
-        return beam_search(lambda ids: self.last_logits(st, ids, rd), B, cfg.vocab_size, reviews.device, num_beams=num_beams,
+        if use_cache:
+            logits_fn, reorder_fn = (lambda ids: self.step_logits(st, ids, rd)), (lambda beam_idx: self.reorder_cache(st, beam_idx))
+        else:
+            logits_fn, reorder_fn = (lambda ids: self.last_logits(st, ids, rd)), None
+        return beam_search(logits_fn, B, cfg.vocab_size, reviews.device, num_beams=num_beams,
                            max_length=max_length, min_length=min_length, length_penalty=length_penalty,
                            no_repeat_ngram_size=no_repeat_ngram_size, early_stopping=early_stopping, pad=cfg.pad_token_id,
-                           bos=cfg.bos_token_id, eos=cfg.eos_token_id)
+                           bos=cfg.bos_token_id, eos=cfg.eos_token_id, reorder_fn=reorder_fn)
 
 
 def beam_search(logits_fn, B, V, dev, num_beams=4, max_length=20, min_length=0, length_penalty=1.0, no_repeat_ngram_size=3,
-                early_stopping=True, pad=1, bos=0, eos=2):
+                early_stopping=True, pad=1, bos=0, eos=2, reorder_fn=None):
     """_generate_beam_search (modeling_multimodalsum.py:2803-3067), do_sample=False.  `logits_fn(input_ids[N, cur_len])`
     returns the fp32 next-token logits [N, V] of the last position (N = B*num_beams, beams of a business adjacent)."""
     N = B * num_beams
@@ -302,8 +412,10 @@ def beam_search(logits_fn, B, V, dev, num_beams=4, max_length=20, min_length=0, 
         beam_idx = torch.tensor([x[2] for x in next_batch_beam], device=dev, dtype=torch.long)
         input_ids = torch.cat([input_ids[beam_idx, :], beam_tokens.unsqueeze(1)], dim=-1)
         cur_len += 1
-        # (the reference re-gathers memories / caches with beam_idx here; the un-expanded per-business memory and the
-        #  prefix recompute make that unnecessary: beam_idx never crosses businesses, :2957)
+        # the reference re-gathers memories and caches with beam_idx here (:2957, _reorder_cache); the per-business memory is
+        # un-expanded (beam_idx never crosses businesses), so only an incremental decoder's self-attention caches move
+        if reorder_fn is not None:
+            reorder_fn(beam_idx)
     ids_host = input_ids.tolist()
     bs_host = beam_scores.tolist()
     for b in range(B):

@@ -28,11 +28,44 @@ def _setup(name):
     return Generator(model), cfg, sd, batch, case["gen"], torch.from_numpy(z["tokens"])
 
 
-def test_beam_search_exact_ids_on_tie_free_case():
-    """Wide logit bias -> candidates separated by far more than bf16 noise: generated ids must equal the reference's."""
+@pytest.mark.parametrize("use_cache", [True, False])
+def test_beam_search_exact_ids_on_tie_free_case(use_cache):
+    """Wide logit bias -> candidates separated by far more than bf16 noise: generated ids must equal the reference's, both
+    with incremental decoding (self-attention K|V caches, beam re-ordering) and with the prefix recomputed every step."""
     gen, cfg, sd, batch, gk, ref = _setup("gen_small_yelp_biased")
-    out = gen.generate(batch.reviews, batch.reviews_mask, batch.field, batch.field_value, batch.img, batch.img_mask, **gk)
+    out = gen.generate(batch.reviews, batch.reviews_mask, batch.field, batch.field_value, batch.img, batch.img_mask,
+                       use_cache=use_cache, **gk)
     assert torch.equal(out.cpu(), ref), (out.cpu().tolist(), ref.tolist())
+
+
+def test_cached_decode_matches_prefix_recompute():
+    """`step_logits` (one token per hypothesis, caches permuted by `reorder_cache` after every step) against `last_logits`
+    (whole prefix recomputed) on the same token histories, 4 beams per business, including beam permutations inside a
+    business: same bf16 kernels on the same values -> log-probabilities agree to 2e-2 nats and the arg-max is identical
+    wherever the top-2 margin exceeds 0.1 nats."""
+    gen, cfg, sd, batch, gk, ref = _setup("gen_small_yelp_s128")
+    beams = 4
+    B = batch.reviews.shape[0]
+    N = B * beams
+    st_c = gen.encode(batch.reviews, batch.reviews_mask, batch.field, batch.field_value, batch.img, batch.img_mask, beams)
+    st_r = gen.encode(batch.reviews, batch.reviews_mask, batch.field, batch.field_value, batch.img, batch.img_mask, beams)
+    rd = torch.zeros(N, device="cuda")
+    g = torch.Generator().manual_seed(5)
+    ids = torch.full((N, 1), cfg.eos_token_id, dtype=torch.long, device="cuda")
+    worst = 0.0
+    for step in range(10):
+        lc = torch.log_softmax(gen.step_logits(st_c, ids, rd).float(), -1)
+        lr = torch.log_softmax(gen.last_logits(st_r, ids, rd).float(), -1)
+        worst = max(worst, (lc - lr).abs().max().item())
+        top2 = lr.topk(2, dim=-1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 0.1
+        assert torch.equal(lc.argmax(-1)[clear], lr.argmax(-1)[clear])
+        # continue every hypothesis from a random beam of the same business with a random token (what beam search does)
+        src = (torch.arange(N) // beams) * beams + torch.randint(0, beams, (N,), generator=g)
+        tok = torch.randint(3, cfg.vocab_size, (N, 1), generator=g)
+        ids = torch.cat([ids[src.cuda()], tok.cuda()], dim=1)
+        gen.reorder_cache(st_c, src.cuda())
+    assert worst <= 2e-2, worst
 
 
 @pytest.mark.parametrize("name", ["gen_small_yelp_s128", "gen_small_yelp_s150"])
