@@ -816,6 +816,16 @@ static constexpr int kKvSoftThreads = kKvSoftWarps * 32;
 static constexpr int kKvThreads = 64 + kKvSoftThreads;
 __device__ __forceinline__ void kv_soft_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kKvSoftThreads) : "memory"); }
 
+// Key tiling of a modality for the dK/dV kernel.  Entities whose key count is not a multiple of 128 (196-key images) are
+// tiled as ONE contiguous key range per business (tiles may straddle two entities; every row carries its own entity), so
+// 10 x 196 keys cost 16 tiles instead of 20 half-empty ones.  Needs contiguous entities, no leave-one-out, Sk >= 128.
+__host__ __device__ inline bool mod_packed(const MmsumAttnMod& md) {
+  return md.E > 1 && !md.loo && (md.ent_stride == 0 || md.ent_stride == md.Sk) && md.Sk >= SQ && (md.Sk % SQ) != 0;
+}
+__host__ __device__ inline int mod_tiles(const MmsumAttnMod& md) {
+  return mod_packed(md) ? (md.E * md.Sk + SQ - 1) / SQ : md.E * ((md.Sk + SQ - 1) / SQ);
+}
+
 struct BwdKVSmem {
   uint8_t k[SQ * 128];
   uint8_t v[SQ * 128];
@@ -823,8 +833,8 @@ struct BwdKVSmem {
   uint8_t da[2][QH * 128];
   uint8_t pt[SQ * 128];        // Pn^T  [128 keys][64 queries] bf16, K-major A operand
   uint8_t dst[SQ * 128];       // dS^T
-  float lse[2][QH];            // raw LSE / DELTA rows of the current and the next step (cp.async staged)
-  float dlt[2][QH];
+  float lse[2][2][QH];         // raw LSE / DELTA rows of the current and the next step (cp.async staged), for the (up to)
+  float dlt[2][2][QH];         // two entities a packed tile straddles
   float lg_invn[32];           // log2(1/n) of every target for this modality
   uint64_t kv_full, kv_free, qd_full[2], qd_empty[2], sdp_full, sdp_empty, pds_full, pds_free;
   uint32_t tmem_slot;
@@ -850,19 +860,33 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
   const int hgroups = p.H / head_mode;
   const int biz = bh / hgroups;
   const int h_begin = (bh % hgroups) * head_mode, h_end = h_begin + head_mode;
-  int m = 0, e = 0, tile = 0;
+  int m = 0;
   for (m = 0; m < p.n_mod; ++m) {
-    const int nt = (p.mods[m].Sk + SQ - 1) / SQ;
-    const int cnt = p.mods[m].E * nt;
-    if (rem < cnt) { e = rem / nt; tile = rem % nt; break; }
+    const int cnt = mod_tiles(p.mods[m]);
+    if (rem < cnt) break;
     rem -= cnt;
   }
   const MmsumAttnMod& md = p.mods[m];
+  const bool packed = mod_packed(md);
+  int e, key0, nkeys, kvrow0;
+  if (packed) {            // tile `rem` of the business' contiguous key range; rows belong to entity e or e + 1
+    const int gk0 = rem * SQ;
+    e = gk0 / md.Sk;
+    key0 = gk0 - e * md.Sk;
+    nkeys = min(SQ, md.E * md.Sk - gk0);
+    kvrow0 = (int)(md.kv_row_base + (long long)biz * md.E * md.Sk) + gk0;
+  } else {
+    const int nt = (md.Sk + SQ - 1) / SQ;
+    e = rem / nt;
+    key0 = (rem % nt) * SQ;
+    nkeys = min(SQ, md.Sk - key0);
+    kvrow0 = (int)(md.kv_row_base + ((long long)biz * md.E + e) * (md.ent_stride > 0 ? md.ent_stride : md.Sk)) + key0;
+  }
+  const int e_hi = min(e + 1, md.E - 1);                       // second entity of a packed tile (== e when there is none)
   const int ge = md.ent_base + e;
-  const int key0 = tile * SQ;
-  const int nkeys = min(SQ, md.Sk - key0);
-  const int kvrow0 = (int)(md.kv_row_base + ((long long)biz * md.E + e) * (md.ent_stride > 0 ? md.ent_stride : md.Sk)) + key0;
-  const bool ent_ok = (p.ent_valid == nullptr) || (p.ent_valid[(long long)biz * p.E_total + ge] != 0);
+  auto ent_valid_at = [&](int ee) { return (p.ent_valid == nullptr) || (p.ent_valid[(long long)biz * p.E_total + md.ent_base + ee] != 0); };
+  const bool ok_lo = ent_valid_at(e), ok_hi = packed && (key0 + SQ > md.Sk) && (e + 1 < md.E) && ent_valid_at(e + 1);
+  const bool ent_ok = ok_lo || ok_hi;
   bf16* dKV = reinterpret_cast<bf16*>(p.dKV);
 
   // consumer targets of this entity (leave-one-out excludes target e); two 64-query steps per target
@@ -983,18 +1007,24 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
     const int row = q4 * 32 + lane;            // key within the tile
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const float sc = p.scale * kLog2e;
-    const bool kvalid = (row < nkeys) && (p.key_valid == nullptr || p.key_valid[(long long)kvrow0 + row] != 0);
+    const int slot = (packed && key0 + row >= md.Sk) ? 1 : 0;  // which of the tile's two entities owns this key row
+    const bool kvalid = (row < nkeys) && (slot ? ok_hi : ok_lo) && (p.key_valid == nullptr || p.key_valid[(long long)kvrow0 + row] != 0);
     uint8_t* patom = sm.pt + row * 128;
     uint8_t* datom = sm.dst + row * 128;
-    auto lse_index = [&](int h, int s) {
-      return (((long long)(biz * p.R + step_target(s)) * p.H + h) * p.E_total + ge) * SQ + (s & 1) * QH + (sw * 32 + lane);
+    auto lse_index = [&](int h, int s, int ent) {
+      return (((long long)(biz * p.R + step_target(s)) * p.H + h) * p.E_total + md.ent_base + ent) * SQ + (s & 1) * QH + (sw * 32 + lane);
     };
     // LSE / DELTA rows of a step are staged with cp.async one step ahead (no register dependency, so the global
     // latency never sits on the softmax critical path); P absorbs 1/n through  exp2(sc*s - (LSE - log2(1/n)))
     auto stage_rows = [&](int h, int s, int st) {
-      const long long i = lse_index(h, s);
-      cp_async_4(smem_u32(&sm.lse[st][sw * 32 + lane]), p.LSE + i);
-      cp_async_4(smem_u32(&sm.dlt[st][sw * 32 + lane]), p.DELTA + i);
+      const long long i = lse_index(h, s, e);
+      cp_async_4(smem_u32(&sm.lse[st][0][sw * 32 + lane]), p.LSE + i);
+      cp_async_4(smem_u32(&sm.dlt[st][0][sw * 32 + lane]), p.DELTA + i);
+      if (packed) {
+        const long long i2 = lse_index(h, s, e_hi);
+        cp_async_4(smem_u32(&sm.lse[st][1][sw * 32 + lane]), p.LSE + i2);
+        cp_async_4(smem_u32(&sm.dlt[st][1][sw * 32 + lane]), p.DELTA + i2);
+      }
     };
     if (sw < 2) stage_rows(h_begin, 0, 0);
     if (threadIdx.x - 64 < (unsigned)p.R && threadIdx.x - 64 < 32u) {
@@ -1041,10 +1071,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {
         uint32_t po[4], dso[4];
-        const float4 l0 = *reinterpret_cast<const float4*>(&sm.lse[st][cg * 32 + g8 * 8]);
-        const float4 l1 = *reinterpret_cast<const float4*>(&sm.lse[st][cg * 32 + g8 * 8 + 4]);
-        const float4 d0 = *reinterpret_cast<const float4*>(&sm.dlt[st][cg * 32 + g8 * 8]);
-        const float4 d1 = *reinterpret_cast<const float4*>(&sm.dlt[st][cg * 32 + g8 * 8 + 4]);
+        const float4 l0 = *reinterpret_cast<const float4*>(&sm.lse[st][slot][cg * 32 + g8 * 8]);
+        const float4 l1 = *reinterpret_cast<const float4*>(&sm.lse[st][slot][cg * 32 + g8 * 8 + 4]);
+        const float4 d0 = *reinterpret_cast<const float4*>(&sm.dlt[st][slot][cg * 32 + g8 * 8]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&sm.dlt[st][slot][cg * 32 + g8 * 8 + 4]);
         // packed fp32 pairs (FFMA2 / FMUL2): the softmax warps are issue-bound, so two lanes per instruction count
         const f32x2 nl[4] = {fma2(pack2(l0.x, l0.y), m1, lg2), fma2(pack2(l0.z, l0.w), m1, lg2),
                              fma2(pack2(l1.x, l1.y), m1, lg2), fma2(pack2(l1.z, l1.w), m1, lg2)};      // log2(1/n) - LSE
@@ -1188,7 +1218,7 @@ extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
   for (int m = 0; m < a->n_mod; ++m) {
     const uint64_t r = (uint64_t)a->mods[m].kv_row_base + (uint64_t)n_biz * a->mods[m].E * (a->mods[m].ent_stride > 0 ? a->mods[m].ent_stride : a->mods[m].Sk);
     if (r > kvrows) kvrows = r;
-    tiles += a->mods[m].E * ((a->mods[m].Sk + SQ - 1) / SQ);
+    tiles += mod_tiles(a->mods[m]);
   }
   CUtensorMap kv128, q64, do64;
   if (int rc = make_tmap(&kv128, a->KV, 0, (uint64_t)a->ldkv, kvrows, (uint64_t)a->ldkv * 2, 64, SQ)) return rc;
