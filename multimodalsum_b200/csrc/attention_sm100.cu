@@ -463,6 +463,310 @@ attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p,
 }
 
 // ----------------------------------------------------------------------------------------------
+// forward, version 2 — one thread per query row, two softmax groups ping-pong over the items, P never leaves TMEM
+//   * warps 2-5 own the even items, warps 6-9 the odd ones; a thread owns a whole score row, so row max / sum need no
+//     cross-warp exchange and there is no CTA-level barrier in the item loop — the two groups drift half an item apart and
+//     one group's exp2 (MUFU) phase overlaps the other's TMEM loads, max pass and MMA hand-offs;
+//   * P = exp2(.) is written back over its own score row in tensor memory as packed bf16 (tcgen05.st) and P V is issued with
+//     the A operand in TMEM (no 64 KB P tile, no smem store traffic, no proxy fence);
+//   * outputs: per-entity O is read out of TMEM by the owning thread and folded into 64 register accumulators; the two
+//     groups' partial sums of a modality are combined through smem at the (at most three) modality boundaries.
+// ----------------------------------------------------------------------------------------------
+static constexpr int kF2Threads = 64 + 8 * 32;
+struct Fwd2Smem {
+  uint8_t q[2][SQ * 128];
+  uint8_t k[2][kKVStageBytes];
+  uint8_t v[2][kKVStageBytes];
+  float oacc[HD][SQ];          // group B's partial output of the current modality (column-major: conflict-free)
+  uint32_t kmask[kMaxEnt][8];
+  EntItem items[kMaxEnt];
+  uint64_t q_full[2], q_empty[2], k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], o_full[2], o_free;
+  uint32_t tmem_slot;
+  int n_items;
+};
+__device__ __forceinline__ void f2_mask_bar() { asm volatile("bar.sync 2, 288;" ::: "memory"); }   // warps 1..9
+__device__ __forceinline__ void f2_group_bar() { asm volatile("bar.sync 3, 256;" ::: "memory"); }  // warps 2..9
+__device__ __forceinline__ void f2_build_masks(const MmsumAttnArgs& p, EntItem* items, int n_items, uint32_t (*kmask)[8],
+                                               int w, int lane) {   // w = warp - 1 in [0, 9)
+  for (int idx = w; idx < n_items * 7; idx += 9) {
+    const int i = idx / 7, c = idx - i * 7;
+    const uint32_t wd = chunk_word(p, items[i], c, lane);
+    if (lane == 0) kmask[i][c] = wd;
+  }
+  f2_mask_bar();
+  const int i = w * 32 + lane;
+  if (i < n_items) {
+    int last = 0;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) { const uint32_t wd = kmask[i][c]; if (wd) last = c * 32 + 32 - __clz(wd); }
+    const int n16 = (last + 15) & ~15;
+    items[i].n16 = n16 < 16 ? 16 : n16;
+  }
+  f2_mask_bar();
+}
+
+__global__ void __launch_bounds__(kF2Threads, 1)
+attn_fwd_tc2_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p, const int head_mode) {
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();   // launched with programmatic stream serialization: nothing global is touched before this point
+  Fwd2Smem& sm = *reinterpret_cast<Fwd2Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tgt = blockIdx.x % p.R;
+  const int h = head_mode ? 0 : (int)((blockIdx.x / p.R) % p.H);
+  const int biz = head_mode ? (int)(blockIdx.x / p.R) : (int)(blockIdx.x / (p.R * p.H));
+  const int qseq = biz * p.R + tgt;
+  const int qrow0 = qseq * SQ;
+  auto item_head = [&](int i) { return head_mode ? i : h; };
+
+  if (warp == 0) {
+    int n = build_ent_items(p, qseq, sm.items, lane);
+    if (head_mode) {                       // replicate the single entity once per head
+      __syncwarp();
+      if (n > 0) {
+        const EntItem it0 = sm.items[0];
+        __syncwarp();
+        if (lane < p.H) sm.items[lane] = it0;
+        n = p.H;
+      }
+    }
+    if (lane == 0) sm.n_items = n;
+  }
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.q_full[s], 1); mbar_init(&sm.q_empty[s], 1);
+      mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1);
+      mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1);
+      mbar_init(&sm.s_full[s], 1); mbar_init(&sm.p_full[s], 128); mbar_init(&sm.o_full[s], 1);
+    }
+    mbar_init(&sm.o_free, 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.q);
+  }
+  // V rows beyond an entity's key count are multiplied by P = 0: they must hold finite values, never stale NaN bits
+  for (int i = threadIdx.x; i < 2 * kKVStageBytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sm.v[0])[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 1) { tmem_alloc(&sm.tmem_slot, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_slot;
+  const int n_items = sm.n_items;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (!head_mode) {
+        mbar_expect_tx(&sm.q_full[0], SQ * 128);
+        tma_load_2d(sm.q[0], &maps.q, &sm.q_full[0], p.q_col + h * HD, qrow0);
+      }
+      for (int i = 0; i < n_items; ++i) {
+        const int st = i & 1;
+        if (head_mode) {
+          mbar_wait(&sm.q_empty[st], ((i >> 1) & 1) ^ 1);
+          mbar_expect_tx(&sm.q_full[st], SQ * 128);
+          tma_load_2d(sm.q[st], &maps.q, &sm.q_full[st], p.q_col + i * HD, qrow0);
+        }
+        mbar_wait(&sm.k_empty[st], ((i >> 1) & 1) ^ 1);
+        const EntItem it = sm.items[i];
+        mbar_expect_tx(&sm.k_full[st], it.nkeys * 128);
+        tma_load_2d(sm.k[st], &maps.kv[it.mod], &sm.k_full[st], p.k_col + item_head(i) * HD, it.kv_row0);
+      }
+    } else if (lane == 1) {
+      for (int i = 0; i < n_items; ++i) {
+        const int st = i & 1;
+        mbar_wait(&sm.v_empty[st], ((i >> 1) & 1) ^ 1);
+        const EntItem it = sm.items[i];
+        mbar_expect_tx(&sm.v_full[st], it.nkeys * 128);
+        tma_load_2d(sm.v[st], &maps.kv[it.mod], &sm.v_full[st], p.v_col + item_head(i) * HD, it.kv_row0);
+      }
+    }
+  } else if (warp == 1) {
+    f2_build_masks(p, sm.items, n_items, sm.kmask, 0, lane);
+    if (n_items > 0) {   // whole warp runs the issue loop; elect.sync picks the issuing lane per instruction
+      const uint64_t qdesc0 = umma_smem_desc_sw128(smem_u32(sm.q[0]), 16, 1024), qdesc1 = umma_smem_desc_sw128(smem_u32(sm.q[1]), 16, 1024);
+      const uint64_t kdesc0 = umma_smem_desc_sw128(smem_u32(sm.k[0]), 16, 1024), kdesc1 = umma_smem_desc_sw128(smem_u32(sm.k[1]), 16, 1024);
+      const uint64_t vdesc0 = umma_smem_desc_sw128(smem_u32(sm.v[0]), 8192, 1024), vdesc1 = umma_smem_desc_sw128(smem_u32(sm.v[1]), 8192, 1024);
+      if (!head_mode) mbar_wait(&sm.q_full[0], 0);
+      auto issue_s = [&](int i) {
+        const int st = i & 1;
+        const EntItem it = sm.items[i];
+        if (head_mode) mbar_wait(&sm.q_full[st], (i >> 1) & 1);
+        mbar_wait(&sm.k_full[st], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, it.n16, 0, 0);
+        const uint64_t qdesc = (head_mode && st) ? qdesc1 : qdesc0, kdesc = st ? kdesc1 : kdesc0;
+        const uint32_t dcol = tmem + (st ? kColS1 : kColS0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_w(dcol, desc_adv(qdesc, kk * 32), desc_adv(kdesc, kk * 32), idesc, kk > 0);
+        umma_commit_w(&sm.s_full[st]);
+        umma_commit_w(&sm.k_empty[st]);
+        if (head_mode) umma_commit_w(&sm.q_empty[st]);
+      };
+      issue_s(0);
+      if (n_items > 1) issue_s(1);
+      const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+      for (int i = 0; i < n_items; ++i) {
+        const int st = i & 1;
+        const EntItem it = sm.items[i];
+        mbar_wait(&sm.v_full[st], (i >> 1) & 1);
+        mbar_wait(&sm.p_full[st], (i >> 1) & 1);            // P (bf16) now sits where the scores were
+        if (lane == 0) TRACE(1, 3 * i);
+        if (i > 0) mbar_wait(&sm.o_free, (i - 1) & 1);      // the previous entity's O has been read out
+        if (lane == 0) TRACE(1, 3 * i + 1);
+        tc_fence_after();
+        const uint64_t vdesc = st ? vdesc1 : vdesc0;
+        const uint32_t pcol = tmem + (st ? kColS1 : kColS0);
+        const int nk = it.n16 >> 4;
+#pragma unroll
+        for (int kk = 0; kk < kMaxKeys / 16; ++kk)
+          if (kk < nk) umma_bf16_ts_w(tmem + kColO, pcol + kk * 8, desc_adv(vdesc, kk * 2048), idesc_o, kk > 0);
+        if (lane == 0) TRACE(1, 3 * i + 2);
+        umma_commit_w(&sm.v_empty[st]);
+        umma_commit_w(&sm.o_full[st]);
+        if (i + 2 < n_items) issue_s(i + 2);                 // overwrites this score buffer: ordered after P V above
+      }
+    }
+  } else {
+    // ===================== softmax groups: thread = one query row of every second item =====================
+    const int g = (warp - 2) >> 2;
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const float sc = p.scale * kLog2e;
+    float acc[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    bf16* Og = reinterpret_cast<bf16*>(p.O);
+    auto store_out = [&](int m, int head) {        // acc -> bf16 output row, then reset
+      bf16* dst = Og + p.mods[m].o_off + (long long)(qrow0 + row) * p.ldo + head * HD;
+#pragma unroll
+      for (int j = 0; j < HD / 8; ++j) {
+        uint4 u;
+        u.x = pack_bf16(acc[j * 8 + 0], acc[j * 8 + 1]); u.y = pack_bf16(acc[j * 8 + 2], acc[j * 8 + 3]);
+        u.z = pack_bf16(acc[j * 8 + 4], acc[j * 8 + 5]); u.w = pack_bf16(acc[j * 8 + 6], acc[j * 8 + 7]);
+        *reinterpret_cast<uint4*>(dst + j * 8) = u;
+      }
+#pragma unroll
+      for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    };
+    // modality boundary (entity mode): group B hands its partial sums to group A through smem
+    auto flush = [&](int m) {
+      if (g == 1) {
+#pragma unroll
+        for (int j = 0; j < HD; ++j) sm.oacc[j][row] = acc[j];
+#pragma unroll
+        for (int j = 0; j < HD; ++j) acc[j] = 0.f;
+      }
+      f2_group_bar();
+      if (g == 0) {
+#pragma unroll
+        for (int j = 0; j < HD; ++j) acc[j] += sm.oacc[j][row];
+        store_out(m, h);
+      }
+      f2_group_bar();
+    };
+    int cur_mod = 0;
+    f2_build_masks(p, sm.items, n_items, sm.kmask, warp - 1, lane);
+    for (int i = g; i < n_items; i += 2) {
+      const EntItem it = sm.items[i];
+      const int head = item_head(i);
+      const int nchunk = (it.n16 + 31) >> 5;
+      const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
+      if (!head_mode) { while (cur_mod < it.mod) { flush(cur_mod); ++cur_mod; } }
+      const uint32_t scol = tmem + lane_off + (g ? kColS1 : kColS0);
+      const bool tr = (lane == 0 && q4 == 2);   // warps 2 and 6
+      if (tr) TRACE(3 + g, 6 * (i >> 1));
+      mbar_wait(&sm.s_full[g], (i >> 1) & 1);
+      if (tr) TRACE(3 + g, 6 * (i >> 1) + 1);
+      tc_fence_after();
+      // (Tried and measured slower: 16-column pieces with the next tcgen05.ld in flight, and strictly alternating the two
+      //  groups' exp2 phases with a token — the ~200-clock TMEM load round trip, not MUFU contention, bounds a lone warp.)
+      // ---- row max ----
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+      for (int c = 0; c < nchunk; ++c) {
+        uint32_t wd = sm.kmask[i][c];
+        if (p.causal) wd = causal_word(wd, row, c);
+        uint32_t r[32];
+        tmem_ld_32x32(scol + c * 32, r);
+        tmem_ld_wait();
+        if (__all_sync(0xffffffffu, wd == 0xffffffffu)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx4[j & 3] = ((wd >> j) & 1u) ? fmaxf(mx4[j & 3], __uint_as_float(r[j])) : mx4[j & 3];
+        }
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float msc = (mx == -INFINITY) ? 0.f : mx * sc;
+      if (tr) TRACE(3 + g, 6 * (i >> 1) + 2);
+      // ---- P = exp2(s*sc - m) written back over the scores as packed bf16; row sum ----
+      f32x2 l2[2] = {splat2(0.f), splat2(0.f)};
+      const f32x2 sc2 = splat2(sc), nmsc2 = splat2(-msc);
+#pragma unroll 1
+      for (int c = 0; c < nchunk; ++c) {
+        uint32_t wd = sm.kmask[i][c];
+        if (p.causal) wd = causal_word(wd, row, c);
+        uint32_t r[32], pk[16];
+        tmem_ld_32x32(scol + c * 32, r);
+        tmem_ld_wait();
+        auto body = [&](auto tag) {
+          constexpr bool kFull = decltype(tag)::value;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float a0, a1;
+            unpack2(fma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, nmsc2), a0, a1);
+            float e0 = ex2(a0), e1 = ex2(a1);
+            if constexpr (!kFull) { e0 = ((wd >> j) & 1u) ? e0 : 0.f; e1 = ((wd >> (j + 1)) & 1u) ? e1 : 0.f; }
+            l2[(j >> 1) & 1] = add2(l2[(j >> 1) & 1], pack2(e0, e1));
+            pk[j >> 1] = pack_bf16(e0, e1);
+          }
+        };
+        if (__all_sync(0xffffffffu, wd == 0xffffffffu)) body(std::true_type{}); else body(std::false_type{});
+        tmem_st_32x16(scol + c * 16, pk);          // columns [16c, 16c+16) lie inside score chunks this thread has consumed
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&sm.p_full[g]);
+      if (tr) TRACE(3 + g, 6 * (i >> 1) + 3);
+      float l4[4];
+      unpack2(l2[0], l4[0], l4[1]);
+      unpack2(l2[1], l4[2], l4[3]);
+      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      p.LSE[(((long long)qseq * p.H + head) * p.E_total + it.ent) * SQ + row] = (l > 0.f) ? (msc + __log2f(l)) : INFINITY;
+      const float wgt = (l > 0.f) ? __fdividef(inv_n, l) : 0.f;
+      // ---- this entity's O = P V: fold into the register accumulators ----
+      mbar_wait(&sm.o_full[g], (i >> 1) & 1);
+      if (tr) TRACE(3 + g, 6 * (i >> 1) + 4);
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + lane_off + kColO + hh * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[hh * 32 + j] = fmaf(wgt, __uint_as_float(r[j]), acc[hh * 32 + j]);
+      }
+      tc_fence_before();
+      mbar_arrive(&sm.o_free);
+      if (tr) TRACE(3 + g, 6 * (i >> 1) + 5);
+      if (head_mode) store_out(0, head);
+    }
+    if (head_mode) {
+      if (n_items == 0 && g == 0) for (int hh = 0; hh < p.H; ++hh) store_out(0, hh);   // null entity: zero rows for every head
+    } else {
+      while (cur_mod < p.n_mod) { flush(cur_mod); ++cur_mod; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ----------------------------------------------------------------------------------------------
 // backward, part 1 — one CTA per (sequence, head): dQ and DELTA
 //   per entity:  S = Q K^T and dP' = dA V^T into TMEM;  P = exp2(sc*S - LSE) (kept in registers as bf16),
 //   delta' = rowsum(P o dP');  dS = scale*inv_n * P o (dP' - delta') -> bf16 smem;  dQ += dS K  (TMEM, all entities)
@@ -1202,7 +1506,19 @@ extern "C" int mmsum_attn_fwd(const MmsumAttnArgs* a, void* stream_v) {
   }
   // self-attention shape (one modality, one entity per sequence, no leave-one-out): heads become the CTA's items
   const int head_mode = (a->n_mod == 1 && a->mods[0].E == 1 && !a->mods[0].loo && a->H <= kMaxEnt && a->n_qseq >= 64) ? 1 : 0;
-  MMSUM_LAUNCH_PDL(attn_fwd_tc_kernel, head_mode ? a->n_qseq : a->n_qseq * a->H, kAttnThreads, smem, stream, mp, *a, head_mode);
+  static const bool use_v1 = (getenv("MMSUM_ATTN_FWD_V1") != nullptr);   // A/B switch: the first forward kernel
+  if (use_v1) {
+    MMSUM_LAUNCH_PDL(attn_fwd_tc_kernel, head_mode ? a->n_qseq : a->n_qseq * a->H, kAttnThreads, smem, stream, mp, *a, head_mode);
+  } else {
+    const int smem2 = (int)sizeof(Fwd2Smem) + 1024;
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      if (e != cudaSuccess) return (int)e;
+      attr2 = true;
+    }
+    MMSUM_LAUNCH_PDL(attn_fwd_tc2_kernel, head_mode ? a->n_qseq : a->n_qseq * a->H, kF2Threads, smem2, stream, mp, *a, head_mode);
+  }
   MMSUM_CHECK_LAUNCH();
   return 0;
 }
