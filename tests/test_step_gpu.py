@@ -90,6 +90,27 @@ def test_step_matches_reference_full_bart_large():
     _check(gold, loss, grads, ograds)
 
 
+def test_step_matches_oracle_at_72_sequences():
+    """8 businesses x 9 reviews = 72 sequences: the shape at which the self-attention kernels switch to one CTA per sequence
+    with the heads as pipeline items (and dK/dV to 4 heads per CTA), ragged review lengths, random image counts (null
+    entities, image tiles straddling two entities).  BART-large widths, 2 + 2 layers; reference = the fp32 oracle on the GPU
+    (pinned to the reference by tests/test_oracle_golden.py)."""
+    from oracle import mmsum_oracle as OR
+    from multimodalsum_b200.synth import ModelConfig, make_batch, make_state_dict
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = ModelConfig(dataset="yelp", encoder_layers=2, decoder_layers=2, dropout=0.0)
+    sd = make_state_dict(cfg, seed=3, perturb=True, gates_open=True)
+    batch = make_batch(cfg, 8, seed=11)
+    oloss, ograds, _ = OR.step_loss_and_grads(sd, cfg, batch, 0.1, dtype=torch.float32, device="cuda")
+    names = [n for n in ograds if not n.endswith("final_logits_bias")]
+    gold = dict(cfg=cfg, sd=sd, batch=batch, loss=float(oloss), names=names,
+                norms={n: ograds[n].double().norm().item() for n in names})
+    loss, grads, _ = _run_cuda_step(gold)
+    assert all(n in grads for n in names)
+    _check(gold, loss, grads, ograds)
+
+
 def test_step_full_text_only_config1():
     gold = load_golden("full_text_b1")
     loss, grads, _ = _run_cuda_step(gold)
