@@ -923,7 +923,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         if (i + 1 < n_items) issue_sdp(i + 1);
         const int st = i & 1;
         const EntItem it = sm.items[i];
+        if (lane == 0) TRACE(1, 3 * i);
         mbar_wait(&sm.ds_full, i & 1);
+        if (lane == 0) TRACE(1, 3 * i + 1);
         tc_fence_after();
         const uint64_t kd = st ? kdesc_mn[1] : kdesc_mn[0];
         const int nk = it.n16 >> 4;
@@ -932,6 +934,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           if (kk < nk)
             umma_bf16_w(tmem + kColDQ, desc_adv(dsdesc, (kk >> 2) * (SQ * 128) + (kk & 3) * 32), desc_adv(kd, kk * 2048), idesc_q,
                       ((i > 0 && !head_mode) || kk > 0) ? 1u : 0u);
+        if (lane == 0) TRACE(1, 3 * i + 2);
         umma_commit_w(&sm.k_empty[st]);
         umma_commit_w(&sm.ds_free);
       }
@@ -972,7 +975,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       const long long li = (((long long)qseq * p.H + item_head(i)) * p.E_total + it.ent) * SQ + row;
       const float lse = p.LSE[li];
       const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
+      if (threadIdx.x == 64) TRACE(3, 5 * i);
       mbar_wait(&sm.sdp_full, i & 1);
+      if (threadIdx.x == 64) TRACE(3, 5 * i + 1);
       tc_fence_after();
       // pass 1: P = exp2(sc*S - LSE) (stashed as packed bf16), partial delta' = sum P o dP'
       // pass 2: dS = scale*inv_n * P o (dP' - delta') -> bf16 A-operand tile
@@ -1000,7 +1005,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       };
       auto exchange_delta = [&]() {
         sm.red_delta[par][cg][row] = (dl4[0] + dl4[1]) + (dl4[2] + dl4[3]);
+        if (threadIdx.x == 64) TRACE(3, 5 * i + 2);
         soft_bar();
+        if (threadIdx.x == 64) TRACE(3, 5 * i + 3);
         const float delta = (sm.red_delta[par][0][row] + sm.red_delta[par][1][row]) +
                             (sm.red_delta[par][2][row] + sm.red_delta[par][3][row]);
         if (cg == 0) p.DELTA[li] = delta;
@@ -1085,6 +1092,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           pass2(cg + 4, 1, dw, r1, pk[3]);
         }
       }
+      if (threadIdx.x == 64) TRACE(3, 5 * i + 4);
       fence_proxy_async_smem();
       mbar_arrive(&sm.ds_full);
     }
