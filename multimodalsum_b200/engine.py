@@ -108,7 +108,8 @@ class StepEngine:
         self.side_stream = None
         self._side_pending = False
         if self.device.type == "cuda" and os.environ.get("MMSUM_BIAS_SIDE_STREAM", "1") != "0":
-            self.side_stream = torch.cuda.Stream(device=self.device)
+            prio = int(os.environ.get("MMSUM_SIDE_PRIORITY", "-1"))   # high priority: its short kernels slot in at once
+            self.side_stream = torch.cuda.Stream(device=self.device, priority=prio)
             self._ev_main = torch.cuda.Event()
             self._ev_side = torch.cuda.Event()
 
