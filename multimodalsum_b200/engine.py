@@ -75,6 +75,8 @@ class _Pool:
         self.before_put = None
 
     def get(self):
+        if not self.free:
+            raise RuntimeError("scratch pool exhausted (a buffer was not returned with put())")
         return self.free.pop()
 
     def put(self, *ts):
@@ -98,11 +100,15 @@ class StepEngine:
         self.bound = False
         self.ws = None
         self.ws_key = None
-        self.seed = 0x5EED
+        # dropout stream = f(seed, step_count, layer, element): the seed follows torch.manual_seed / torch.initial_seed and
+        # differs per data-parallel rank; `seed` and `step_count` are plain attributes so a resume can restore them
+        self.seed = self._default_seed()
         self.step_count = 0
+        self.fwd_generation = 0          # bumped by every forward; backward refuses to run on a stale workspace
         self.dropout = cfg.dropout
         self.grad_ready_hook = None      # callable(lo, hi): gradient arena range [lo, hi) is final (data-parallel buckets)
-        self._w16_version = -1
+        self._w16_fresh = False          # True only right after a fused optimizer wrote W16 itself
+        self._w16_versions = -1
         self.anchor = None
         # bias-gradient side stream (see _bias_grad); MMSUM_BIAS_SIDE_STREAM=0 keeps everything on one stream
         self.side_stream = None
@@ -142,7 +148,7 @@ class StepEngine:
                 self.params[n] = p
         self.anchor = torch.zeros(1, device=dev, requires_grad=True)
         self.bound = True
-        self._w16_version = -1
+        self._w16_fresh = False
 
     def _view(self, arena, n, n2=None):
         o = self.offsets[n]
@@ -162,16 +168,46 @@ class StepEngine:
     def g32(self, n, n2=None):
         return self._view(self.G32, n, n2)
 
+    @staticmethod
+    def _default_seed():
+        rank = 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank = dist.get_rank()
+            else:
+                rank = int(os.environ.get("RANK", "0"))
+        except Exception:
+            rank = 0
+        return (torch.initial_seed() ^ (0x5EED + rank * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
+
+    def _param_versions(self):
+        return sum(p._version for p in self.params.values())
+
     def refresh_bf16_weights(self, force=False):
-        if force or self.W32._version != self._w16_version:
+        """Re-cast the fp32 masters into the bf16 compute copy.  The masters are updated through the Parameters
+        (`p.data.addcdiv_` in transformers' AdamW, torch.optim, load_state_dict, ...), which the arena's own version counter
+        never sees, so the cast runs on EVERY call (2.8 GB of traffic, < 0.5 ms) unless a fused optimizer that writes W16
+        itself has just declared it fresh (`mark_w16_fresh`) and no Parameter has been written in place since."""
+        vs = self._param_versions()
+        if force or not self._w16_fresh or vs != self._w16_versions:
             ops.cast_bf16(self.W32, self.W16)
-            self._w16_version = self.W32._version
+        self._w16_fresh = False
+        self._w16_versions = vs
+
+    def mark_w16_fresh(self):
+        self._w16_fresh = True
+        self._w16_versions = self._param_versions()
+
+    def mark_weights_dirty(self):
+        self._w16_fresh = False
 
     # ------------------------------------------------------------------ workspaces
     def _alloc(self, B, R, S, F, n_img, img_keys):
         key = (B, R, S, F, n_img, img_keys)
         if self.ws_key == key:
             return self.ws
+        self.ws, self.ws_key = None, None       # drop the old workspace before allocating the new one
         cfg, dev = self.cfg, self.device
         D, FF, H = cfg.d_model, cfg.ffn_dim, cfg.heads
         T = B * R * S
@@ -280,6 +316,7 @@ class StepEngine:
         w = self._alloc(B, R, S, F, n_img, img_keys)
         T, Tm = w["T"], w["Tm"]
         self.step_count += 1
+        self.fwd_generation += 1
         self.training = training
         pd = self.dropout if training else 0.0
         self.pd = pd
@@ -478,6 +515,8 @@ class StepEngine:
     def backward(self, grad_out=None):
         """Writes every parameter gradient into the fp32 gradient arena (+=) and points `.grad` at it."""
         cfg, w = self.cfg, self.ws
+        if w is None:
+            raise RuntimeError("backward() without a forward()")
         D, V = cfg.d_model, cfg.vocab_size
         T, Tm, B, R, S, F = w["T"], w["Tm"], w["B"], w["R"], w["S"], w["F"]
         n_img, img_keys = w["n_img"], w["img_keys"]

@@ -76,7 +76,7 @@ class FusedAdamW:
                                        ops._ptr(self.flags), C.c_int64(eng.numel), C.c_float(lr), C.c_float(b1), C.c_float(b2),
                                        C.c_float(self.eps), C.c_float(self.weight_decay), C.c_float(step_size), ops._ptr(sumsq),
                                        C.c_float(self.max_grad_norm or 0.0), s), "mmsum_adamw_step")
-        eng._w16_version = eng.W32._version   # W16 was refreshed by the kernel itself
+        eng.mark_w16_fresh()                  # W16 was refreshed by the kernel itself
 
     def grad_norm(self):
         return self.sumsq.sqrt()
