@@ -44,7 +44,7 @@ def _arena_order(cfg: ModelConfig):
         lp = bm + "decoder.layers.%d." % i
         names += ffn(lp)
         c = lp + "encoder_attn."
-        if cfg.dataset != "text":
+        if cfg.multimodal:
             names += [c + "alpha_proj.weight", c + "alpha_proj.bias", c + "beta_proj.weight", c + "beta_proj.bias"]
         names += [c + "out_proj.weight", c + "out_proj.bias", c + "q_proj.weight", c + "q_proj.bias",
                   c + "k_proj.weight", c + "v_proj.weight", c + "k_proj.bias", c + "v_proj.bias",
@@ -52,10 +52,11 @@ def _arena_order(cfg: ModelConfig):
         names += self_attn(lp)
     names += [bm + "decoder.layernorm_embedding.weight", bm + "decoder.layernorm_embedding.bias",
               bm + "decoder.rating_embeddings", bm + "decoder.embed_positions.weight"]
-    if cfg.dataset != "text":
+    if cfg.table is not None:
         t = "table_encoder."
         names += [t + "linear.weight", t + "fc.weight", t + "fc.bias"]
-        names += [t + "rating_embedding.weight", t + ("hours_embedding.weight" if cfg.dataset == "yelp" else "price_embedding.weight")]
+        names += [t + "rating_embedding.weight", t + ("hours_embedding.weight" if cfg.table == "yelp" else "price_embedding.weight")]
+    if cfg.image:
         names += ["img_encoder.linear.weight"]
     for i in reversed(range(cfg.encoder_layers)):
         lp = bm + "encoder.layers.%d." % i
@@ -124,6 +125,8 @@ class StepEngine:
         """Move the parameters into the flat arenas and re-point `.data` at the arena views."""
         named = dict(named_params)
         off = 0
+        # a stand-alone BartFor*ConditionalGeneration owns no table / image encoder: those arena entries are dropped
+        self.names = [n for n in self.names if n in named or not n.startswith(("table_encoder.", "img_encoder."))]
         for n in self.names:
             if n not in named:
                 raise KeyError("parameter %s missing" % n)
@@ -204,6 +207,8 @@ class StepEngine:
 
     # ------------------------------------------------------------------ workspaces
     def _alloc(self, B, R, S, F, n_img, img_keys):
+        """Workspaces of one step shape.  B businesses, R decoder sequences per business (the leave-one-out targets; 1 in
+        the img / table stages), S = 128; memory rows = [text B*R*S (when the model has a text memory) | table B*F | image]."""
         key = (B, R, S, F, n_img, img_keys)
         if self.ws_key == key:
             return self.ws
@@ -211,35 +216,40 @@ class StepEngine:
         cfg, dev = self.cfg, self.device
         D, FF, H = cfg.d_model, cfg.ffn_dim, cfg.heads
         T = B * R * S
-        Tm = T + B * F + B * n_img * img_keys
+        has_text = cfg.text_memory
+        Tt = T if has_text else 0
+        Tm = Tt + B * F + B * n_img * img_keys
         N = B * R
-        Et = R + (1 if F > 0 else 0) + n_img
+        Et = (R if has_text else 0) + (1 if F > 0 else 0) + n_img
+        nm = int(has_text) + int(F > 0) + int(n_img > 0)
         bf = lambda *s: torch.empty(s, device=dev, dtype=torch.bfloat16)
         f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
         u8 = lambda *s: torch.zeros(s, device=dev, dtype=torch.uint8)
         i32 = lambda *s: torch.zeros(s, device=dev, dtype=torch.int32)
-        w = dict(B=B, R=R, S=S, F=F, n_img=n_img, img_keys=img_keys, T=T, Tm=Tm, N=N, Et=Et)
+        w = dict(B=B, R=R, S=S, F=F, n_img=n_img, img_keys=img_keys, T=T, Tt=Tt, Tm=Tm, N=N, Et=Et, nm=nm)
         w.update(enc_ids=i32(T), dec_ids=i32(T), labels=i32(T), enc_valid=u8(T), dec_valid=u8(T), mem_valid=u8(Tm),
-                 ent_valid=u8(B, Et), pres=u8(B, 2), rating_diff=f32(N), inv_n=f32(N, 3 if F > 0 else 1))
+                 ent_valid=u8(B, Et), pres=u8(B, 2), rating_diff=f32(N), inv_n=f32(N, nm))
         w["MEM"] = bf(Tm, D)
         if F > 0:
-            w.update(tabX=bf(B * F, 2 * D), tab_valid=u8(B, F), tab_h=bf(B * F, D), img16=bf(B * n_img * img_keys, 1024))
-        L_e, L_d = cfg.encoder_layers, cfg.decoder_layers
+            w.update(tabX=bf(B * F, 2 * D), tab_valid=u8(B, F), tab_h=bf(B * F, D))
+        if n_img > 0:
+            w.update(img16=bf(B * n_img * img_keys, 1024))
+        L_e, L_d = (cfg.encoder_layers if has_text else 0), cfg.decoder_layers
         enc = []
         for l in range(L_e):
             enc.append(dict(x=bf(T, D) if l > 0 else None, qkv=bf(T, 3 * D), ctx=bf(T, D), o=bf(T, D), x1=bf(T, D), h=bf(T, FF),
                             a=bf(T, FF), f=bf(T, D), lse=f32(N, H, 1, S), m1=f32(T), r1=f32(T), m2=f32(T), r2=f32(T)))
         w["enc"] = enc
-        w["enc_x0"] = bf(T, D)
-        w["enc_m0"], w["enc_r0"] = f32(T), f32(T)
+        if has_text:
+            w["enc_x0"] = bf(T, D)
+            w["enc_m0"], w["enc_r0"] = f32(T), f32(T)
         dec = []
-        nm = 3 if F > 0 else 1
         for l in range(L_d):
             d = dict(x=bf(T, D), qkv=bf(T, 3 * D), ctx=bf(T, D), o=bf(T, D), x1=bf(T, D), qc=bf(T, D), kv=bf(Tm, 2 * D),
                      A3=bf(nm, T, D), O3=bf(nm, T, D), x2=bf(T, D), h=bf(T, FF), a=bf(T, FF), f=bf(T, D),
                      lse=f32(N, H, 1, S), lse_c=f32(N, H, Et, S),
                      m1=f32(T), r1=f32(T), m2=f32(T), r2=f32(T), m3=f32(T), r3=f32(T))
-            if nm == 3:
+            if cfg.multimodal:
                 d.update(AB=bf(2, T, D), yc=bf(T, D))
             dec.append(d)
         w["dec"] = dec
@@ -261,7 +271,7 @@ class StepEngine:
         w["dz32"] = f32(T, D)
         w["dA3"] = bf(nm, T, D)
         w["dO3"] = bf(nm, T, D)
-        if nm == 3:
+        if cfg.multimodal:
             w.update(U=bf(2, T, D), dU=bf(2, T, D), dca=bf(T, 2 * D), dcb=bf(T, 2 * D))
         if F > 0:
             w.update(dtab_h=bf(B * F, D), dtabX=bf(B * F, 2 * D))
@@ -284,11 +294,16 @@ class StepEngine:
 
     def _cross_attn_args(self, w, qc, kv, out3, lse, bwd=None):
         D, H, S, T = self.cfg.d_model, self.cfg.heads, w["S"], w["T"]
-        B, R, F, n_img, ik = w["B"], w["R"], w["F"], w["n_img"], w["img_keys"]
-        mods = [(0, 0, R, S, 1, 0)]
+        B, R, F, n_img, ik, Tt = w["B"], w["R"], w["F"], w["n_img"], w["img_keys"], w["Tt"]
+        mods, eb = [], 0
+        if Tt > 0:
+            mods.append((0, 0, R, S, 1, 0))          # text: leave-one-out over the R reviews of the business
+            eb = R
         if F > 0:
-            mods.append((T, T * D, 1, F, 0, R))
-            mods.append((T + B * F, 2 * T * D, n_img, ik, 0, R + 1))
+            mods.append((Tt, len(mods) * T * D, 1, F, 0, eb))
+            eb += 1
+        if n_img > 0:
+            mods.append((Tt + B * F, len(mods) * T * D, n_img, ik, 0, eb))
         kw = dict(Q=qc, ldq=D, q_col=0, KV=kv, ldkv=2 * D, k_col=0, v_col=D, O=out3, ldo=D, LSE=lse,
                   key_valid=w["mem_valid"], ent_valid=w["ent_valid"], inv_n=w["inv_n"], n_qseq=w["N"], H=H, R=R, causal=0,
                   E_total=w["Et"], scale=self.cfg.head_dim ** -0.5, mods=mods)
@@ -298,23 +313,46 @@ class StepEngine:
         return ops.attn_args(**kw)
 
     # ------------------------------------------------------------------ forward
+    def _stage_bookkeeping(self, w, batch, img_mask_u8):
+        """Integer bookkeeping of the img / table pretraining stages (src/img_pretrain.py:85-141, src/table_pretrain.py:84-129):
+        one target per business given as `labels`, rating_diff = 0, one memory modality.  Small tensors; torch on the device."""
+        from .inference import shift_tokens_right
+        cfg = self.cfg
+        B, F, n_img, ik = w["B"], w["F"], w["n_img"], w["img_keys"]
+        lab = batch.labels.to(torch.int64)
+        dec = shift_tokens_right(lab, cfg.pad_token_id, cfg.bos_token_id, cfg.eos_token_id)
+        w["labels"].copy_(lab.reshape(-1))
+        w["dec_ids"].copy_(dec.reshape(-1))
+        w["dec_valid"].copy_(dec.ne(cfg.pad_token_id).reshape(-1))
+        w["rating_diff"].zero_()
+        if F > 0:
+            w["mem_valid"].copy_(w["tab_valid"].reshape(-1))
+            ent = w["tab_valid"].max(dim=1, keepdim=True).values
+        else:
+            w["mem_valid"].copy_(img_mask_u8.ne(0).to(torch.uint8)[:, :, None].expand(B, n_img, ik).reshape(-1))
+            ent = img_mask_u8.ne(0).to(torch.uint8)
+        w["ent_valid"].copy_(ent)
+        cnt = ent.sum(dim=1).float()
+        w["inv_n"].copy_(torch.where(cnt > 0, 1.0 / cnt.clamp(min=1), torch.zeros_like(cnt))[:, None])
+
     def forward(self, batch, label_smoothing=0.1, training=True):
         """batch: synth.Batch on the device.  Returns the scalar loss tensor (fp32, device)."""
         if not self.bound:
             raise RuntimeError("engine.bind(named_parameters) first")
         cfg = self.cfg
         D, FF, V = cfg.d_model, cfg.ffn_dim, cfg.vocab_size
-        B, R, S = batch.reviews.shape
-        multimodal = cfg.dataset != "text"
-        if multimodal:
-            F = 47 if cfg.dataset == "yelp" else 133
-            n_img, img_keys = batch.img.shape[1], batch.img.shape[2]
+        has_text, gates = cfg.text_memory, cfg.multimodal
+        if has_text:
+            B, R, S = batch.reviews.shape
         else:
-            F, n_img, img_keys = 0, 0, 0
+            (B, S), R = batch.labels.shape, 1
+        F = {None: 0, "yelp": 47, "amazon": 133}[cfg.table]
+        n_img, img_keys = (batch.img.shape[1], batch.img.shape[2]) if cfg.image else (0, 0)
         if S != 128:
             raise ValueError("the attention kernels are specialised to 128-token frames")
         w = self._alloc(B, R, S, F, n_img, img_keys)
-        T, Tm = w["T"], w["Tm"]
+        T, Tt, Tm = w["T"], w["Tt"], w["Tm"]
+        w["batch"] = batch                 # backward re-reads the bit-code table fields
         self.step_count += 1
         self.fwd_generation += 1
         self.training = training
@@ -327,50 +365,57 @@ class StepEngine:
         g = ops.gemm
 
         # ---- table front end + step bookkeeping (integer work, bit-exact)
-        if multimodal:
+        img_mask_u8 = None
+        if F > 0:
             t = "table_encoder."
-            W1name = t + ("hours_embedding.weight" if cfg.dataset == "yelp" else "price_embedding.weight")
-            if cfg.dataset == "yelp":
+            W1name = t + ("hours_embedding.weight" if cfg.table == "yelp" else "price_embedding.weight")
+            if cfg.table == "yelp":
                 W0, W1 = self.w32(t + "rating_embedding.weight"), self.w32(W1name)
             else:
                 W0, W1 = self.w32(W1name), self.w32(t + "rating_embedding.weight")
-            ops.table_fwd(cfg.dataset, B, self.w32(bm + "shared.weight"), batch.field, batch.field_value, W0, W1,
+            ops.table_fwd(cfg.table, B, self.w32(bm + "shared.weight"), batch.field, batch.field_value, W0, W1,
                           w["tabX"], w["tab_valid"])
+        if n_img > 0:
             img_mask_u8 = batch.img_mask.view(torch.uint8) if batch.img_mask.dtype == torch.bool else batch.img_mask
-        ops.prep_step(batch.reviews, batch.reviews_mask, batch.reviews_rating,
-                      w["tab_valid"] if multimodal else None, img_mask_u8 if multimodal else None,
-                      B=B, R=R, S=S, F=F, n_img=n_img, img_keys=img_keys, n_mod=3 if multimodal else 1,
-                      pad_id=cfg.pad_token_id, bos_id=cfg.bos_token_id, eos_id=cfg.eos_token_id,
-                      enc_ids=w["enc_ids"], dec_ids=w["dec_ids"], labels=w["labels"], enc_valid=w["enc_valid"],
-                      dec_valid=w["dec_valid"], mem_valid=w["mem_valid"], ent_valid=w["ent_valid"],
-                      pres=w["pres"] if multimodal else None, rating_diff=w["rating_diff"], inv_n=w["inv_n"])
+        if has_text:
+            ops.prep_step(batch.reviews, batch.reviews_mask, batch.reviews_rating,
+                          w["tab_valid"] if gates else None, img_mask_u8 if gates else None,
+                          B=B, R=R, S=S, F=F, n_img=n_img, img_keys=img_keys, n_mod=3 if gates else 1,
+                          pad_id=cfg.pad_token_id, bos_id=cfg.bos_token_id, eos_id=cfg.eos_token_id,
+                          enc_ids=w["enc_ids"], dec_ids=w["dec_ids"], labels=w["labels"], enc_valid=w["enc_valid"],
+                          dec_valid=w["dec_valid"], mem_valid=w["mem_valid"], ent_valid=w["ent_valid"],
+                          pres=w["pres"] if gates else None, rating_diff=w["rating_diff"], inv_n=w["inv_n"])
+        else:
+            self._stage_bookkeeping(w, batch, img_mask_u8)
         MEM = w["MEM"]
-        if multimodal:
+        if F > 0:
             t = "table_encoder."
             g(w["tabX"], self.w16(t + "fc.weight"), w["tab_h"], bias=self.w32(t + "fc.bias"), act=ops.ACT_RELU)
-            g(w["tab_h"], self.w16(t + "linear.weight"), MEM[T:T + B * F])
+            g(w["tab_h"], self.w16(t + "linear.weight"), MEM[Tt:Tt + B * F])
+        if n_img > 0:
             img = batch.img.reshape(B * n_img * img_keys, 1024)
             if img.dtype == torch.float32:
                 ops.cast_bf16(img.contiguous(), w["img16"])
                 img = w["img16"]
             w["img_in"] = img
-            g(img, self.w16("img_encoder.linear.weight"), MEM[T + B * F:])
+            g(img, self.w16("img_encoder.linear.weight"), MEM[Tt + B * F:])
 
         # ---- encoder (BartEncoder.forward :346-404)
-        pre = bm + "encoder."
-        x = w["enc_x0"]
-        ops.embed_ln_fwd(w["enc_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"), None, None,
-                         self.w32(pre + "layernorm_embedding.weight"), self.w32(pre + "layernorm_embedding.bias"),
-                         x, w["enc_m0"], w["enc_r0"], T, S, pd, seed, self._sid(0, 0))
-        L_e = cfg.encoder_layers
-        for l in range(L_e):
-            a = w["enc"][l]
-            a["x"] = x
-            lp = pre + "layers.%d." % l
-            out = MEM[:T] if l == L_e - 1 else w["enc"][l + 1]["x"]
-            self._self_block_fwd(w, a, lp, x, w["enc_valid"], False, l, 1)
-            self._ffn_block_fwd(a, lp, a["x1"], out, "m2", "r2", l, 2)
-            x = out
+        if has_text:
+            pre = bm + "encoder."
+            x = w["enc_x0"]
+            ops.embed_ln_fwd(w["enc_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"), None, None,
+                             self.w32(pre + "layernorm_embedding.weight"), self.w32(pre + "layernorm_embedding.bias"),
+                             x, w["enc_m0"], w["enc_r0"], T, S, pd, seed, self._sid(0, 0))
+            L_e = cfg.encoder_layers
+            for l in range(L_e):
+                a = w["enc"][l]
+                a["x"] = x
+                lp = pre + "layers.%d." % l
+                out = MEM[:T] if l == L_e - 1 else w["enc"][l + 1]["x"]
+                self._self_block_fwd(w, a, lp, x, w["enc_valid"], False, l, 1)
+                self._ffn_block_fwd(a, lp, a["x1"], out, "m2", "r2", l, 2)
+                x = out
 
         # ---- decoder, batched leave-one-out (BartDecoder.forward :530-660 over 9·B sequences)
         pre = bm + "decoder."
@@ -392,7 +437,7 @@ class StepEngine:
             ops.attn_fwd(self._cross_attn_args(w, a["qc"], a["kv"], a["A3"], a["lse_c"]))
             nm = a["A3"].shape[0]
             g(a["A3"].view(nm * T, D), self.w16(c + "out_proj.weight"), a["O3"].view(nm * T, D), bias=self.w32(c + "out_proj.bias"))
-            if multimodal:
+            if gates:
                 U = w["U"]
                 ops.gemm_cat(a["O3"][0], a["O3"][1], self.w16(c + "alpha_proj.weight"), U[0], bias=self.w32(c + "alpha_proj.bias"))
                 ops.gemm_cat(a["O3"][0], a["O3"][2], self.w16(c + "beta_proj.weight"), U[1], bias=self.w32(c + "beta_proj.bias"))
@@ -518,9 +563,9 @@ class StepEngine:
         if w is None:
             raise RuntimeError("backward() without a forward()")
         D, V = cfg.d_model, cfg.vocab_size
-        T, Tm, B, R, S, F = w["T"], w["Tm"], w["B"], w["R"], w["S"], w["F"]
+        T, Tt, Tm, B, R, S, F = w["T"], w["Tt"], w["Tm"], w["B"], w["R"], w["S"], w["F"]
         n_img, img_keys = w["n_img"], w["img_keys"]
-        multimodal = cfg.dataset != "text"
+        gates = cfg.multimodal
         pool, pd, seed = w["pool"], self.pd, self.seed
         bm = "bart_model.model."
         g = ops.gemm
@@ -548,14 +593,14 @@ class StepEngine:
             d1, d2 = self._ffn_block_bwd(w, a, lp, d1, d2, a["x2"], "m3", "r3", l, 6)
             # cross block
             dres = pool.get()
-            yc = a["yc"] if multimodal else a["O3"][0]
+            yc = a["yc"] if gates else a["O3"][0]
             dyc = pool.get() if pd > 0 else dres
             ops.add_ln_bwd(d1, d2, a["x1"], yc, self.w32(lp + "encoder_attn_layer_norm.weight"), a["m2"], a["r2"], dres, dyc,
                            self.g32(lp + "encoder_attn_layer_norm.weight"), self.g32(lp + "encoder_attn_layer_norm.bias"),
                            pd, seed, self._sid(5, l))
             pool.put(d1, d2)
             nm = a["A3"].shape[0]
-            if multimodal:
+            if gates:
                 dU, dO3 = w["dU"], w["dO3"]
                 ops.gate_bwd_u(dyc, a["O3"], a["AB"], dU, T, D)
                 self._bias_grad(dU[0], self.g32(c + "alpha_proj.bias"))
@@ -602,40 +647,44 @@ class StepEngine:
         # ---- memory gradients: table, image, text
         ops.cast_bf16(w["dMEM32"], w["dMEM16"])
         dMEM = w["dMEM16"]
-        if multimodal:
+        if F > 0:
             t = "table_encoder."
-            dtab = dMEM[T:T + B * F]
+            dtab = dMEM[Tt:Tt + B * F]
             self._wgrad(dtab, w["tab_h"], t + "linear.weight")
             g(dtab, self.w16(t + "linear.weight"), w["dtab_h"], b_t=True, act=ops.ACT_RELU, aux=w["tab_h"], aux_mode=ops.AUX_MUL_DACT)
             self._bias_grad(w["dtab_h"], self.g32(t + "fc.bias"))
             self._wgrad(w["dtab_h"], w["tabX"], t + "fc.weight")
             g(w["dtab_h"], self.w16(t + "fc.weight"), w["dtabX"], b_t=True)
-            batch = self._batch
-            if cfg.dataset == "yelp":
+            batch = w["batch"]
+            if cfg.table == "yelp":
                 ops.table_bits_bwd(w["dtabX"], batch.field_value[4], self.g32(t + "rating_embedding.weight"), B, F, 39, 1, 4)
                 ops.table_bits_bwd(w["dtabX"], batch.field_value[5], self.g32(t + "hours_embedding.weight"), B, F, 40, 7, 4)
             else:
                 ops.table_bits_bwd(w["dtabX"], batch.field_value[0], self.g32(t + "price_embedding.weight"), B, F, 0, 1, 11)
                 ops.table_bits_bwd(w["dtabX"], batch.field_value[1], self.g32(t + "rating_embedding.weight"), B, F, 1, 1, 4)
-            self._wgrad(dMEM[T + B * F:], w["img_in"], "img_encoder.linear.weight")
+            if n_img == 0:
+                self._ready(t + ("hours_embedding.weight" if cfg.table == "yelp" else "price_embedding.weight"))
+        if n_img > 0:
+            self._wgrad(dMEM[Tt + B * F:], w["img_in"], "img_encoder.linear.weight")
             self._ready("img_encoder.linear.weight")
 
-        # ---- encoder layers, last to first
-        pre = bm + "encoder."
-        d1 = pool.get()
-        d1.copy_(dMEM[:T])
-        d2 = None
-        for l in reversed(range(cfg.encoder_layers)):
-            a = w["enc"][l]
-            lp = pre + "layers.%d." % l
-            d1, d2 = self._ffn_block_bwd(w, a, lp, d1, d2, a["x1"], "m2", "r2", l, 2)
-            d1, d2 = self._self_block_bwd(w, a, lp, d1, d2, w["enc_valid"], False, l, 1)
-            self._ready(lp + "self_attn_layer_norm.bias")
-        ops.embed_ln_bwd(d1, d2, w["enc_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"), None, None,
-                         self.w32(pre + "layernorm_embedding.weight"), w["enc_m0"], w["enc_r0"], self.g32(bm + "shared.weight"),
-                         self.g32(pre + "embed_positions.weight"), None, self.g32(pre + "layernorm_embedding.weight"),
-                         self.g32(pre + "layernorm_embedding.bias"), w["dz32"], T, S, cfg.pad_token_id, pd, seed, self._sid(0, 0))
-        pool.put(d1, d2)
+        # ---- encoder layers, last to first (the img / table stages have no text memory: encoder gradients stay zero)
+        if Tt > 0:
+            pre = bm + "encoder."
+            d1 = pool.get()
+            d1.copy_(dMEM[:T])
+            d2 = None
+            for l in reversed(range(cfg.encoder_layers)):
+                a = w["enc"][l]
+                lp = pre + "layers.%d." % l
+                d1, d2 = self._ffn_block_bwd(w, a, lp, d1, d2, a["x1"], "m2", "r2", l, 2)
+                d1, d2 = self._self_block_bwd(w, a, lp, d1, d2, w["enc_valid"], False, l, 1)
+                self._ready(lp + "self_attn_layer_norm.bias")
+            ops.embed_ln_bwd(d1, d2, w["enc_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"), None, None,
+                             self.w32(pre + "layernorm_embedding.weight"), w["enc_m0"], w["enc_r0"], self.g32(bm + "shared.weight"),
+                             self.g32(pre + "embed_positions.weight"), None, self.g32(pre + "layernorm_embedding.weight"),
+                             self.g32(pre + "layernorm_embedding.bias"), w["dz32"], T, S, cfg.pad_token_id, pd, seed, self._sid(0, 0))
+            pool.put(d1, d2)
         self._ready(bm + "shared.weight")
         for n, p in self.params.items():
             if p.grad is None:

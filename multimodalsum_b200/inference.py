@@ -44,22 +44,22 @@ def table_dims(dataset):
 def table_forward(eng, field, field_value, out=None):
     """-> (emb bf16 [B, F, D], valid uint8 [B, F]).  `out`: optional [B*F, D] destination (a slice of a memory buffer)."""
     cfg = eng.cfg
-    if cfg.dataset not in ("yelp", "amazon"):
+    if cfg.table is None:
         raise RuntimeError("this model has no table encoder")
     _need_cuda(field, "field")
     dev = field.device
     D = cfg.d_model
-    F = table_dims(cfg.dataset)
+    F = table_dims(cfg.table)
     vals = [v.to(torch.int64).contiguous() for v in field_value]
     B = vals[0].shape[0]
     t = "table_encoder."
-    W1n = t + ("hours_embedding.weight" if cfg.dataset == "yelp" else "price_embedding.weight")
-    if cfg.dataset == "yelp":
+    W1n = t + ("hours_embedding.weight" if cfg.table == "yelp" else "price_embedding.weight")
+    if cfg.table == "yelp":
         W0, W1 = eng.w32(t + "rating_embedding.weight"), eng.w32(W1n)
     else:
         W0, W1 = eng.w32(W1n), eng.w32(t + "rating_embedding.weight")
     tabX, valid, tab_h = _bf(dev, B * F, 2 * D), torch.zeros(B, F, device=dev, dtype=torch.uint8), _bf(dev, B * F, D)
-    ops.table_fwd(cfg.dataset, B, eng.w32("bart_model.model.shared.weight"), field.to(torch.int64).contiguous(), vals, W0, W1,
+    ops.table_fwd(cfg.table, B, eng.w32("bart_model.model.shared.weight"), field.to(torch.int64).contiguous(), vals, W0, W1,
                   tabX, valid)
     ops.gemm(tabX, eng.w16(t + "fc.weight"), tab_h, bias=eng.w32(t + "fc.bias"), act=ops.ACT_RELU)
     if out is None:
@@ -191,7 +191,7 @@ def build_memory(eng, hiddens, masks):
     pres = None
     if len(hiddens) == 3:
         # table present: entity 0 only (:732); image present: any entity (:735)
-        pres = torch.stack([ent_v[1][:, 0], ent_v[2].amax(dim=1)], dim=1).contiguous()
+        pres = torch.stack([ent_v[1][:, 0], ent_v[2].max(dim=1).values], dim=1).contiguous()
     return Memory(MEM=MEM, B=B, mods=mods, mem_valid=torch.cat(valids).contiguous(), ent_valid=ent_valid,
                   inv_n=torch.stack(inv_n, dim=1).contiguous(), pres=pres, Et=ent_valid.shape[1])
 

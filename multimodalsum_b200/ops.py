@@ -8,7 +8,9 @@ from ._lib import GemmArgs
 from ._lib import check as _check_rc
 
 LAUNCHES = 0      # kernels launched through the C-ABI since import (bench.py: gpu_launches)
-GEMM_TIMER = None  # optional callable(flops) -> context manager bracketing each GEMM launch (bench.py roofline)
+# Optional instrumentation hook (bench.py roofline): callable(kind, work) -> context manager that brackets ONE C-ABI call with
+# CUDA events on the launching stream.  kind / work: "gemm" FLOPs; "attn_fwd" / "attn_bwd" FLOPs; row kernels algorithmic bytes.
+KERNEL_TIMER = None
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 AUX_NONE, AUX_STORE_PREACT, AUX_MUL_DACT = 0, 1, 2
@@ -81,8 +83,8 @@ def gemm(A, B, out=None, *, a_t=False, b_t=False, out_dtype=torch.bfloat16, bias
     a.act, a.aux_mode = act, aux_mode
     a.aux = aux.data_ptr() if aux is not None else None
     a.ld_aux = aux.stride(0) if aux is not None else 0
-    if GEMM_TIMER is not None:
-        with GEMM_TIMER(2.0 * M * N * K):
+    if KERNEL_TIMER is not None:
+        with KERNEL_TIMER("gemm", 2.0 * M * N * K):
             check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16")
     else:
         check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16")
@@ -109,12 +111,19 @@ def gemm_cat(A, A2, B, out=None, *, bias=None, out_dtype=torch.bfloat16):
     a.alpha = 1.0
     a.bias = bias.data_ptr() if bias is not None else None
     a.A2, a.lda2, a.k_split = A2.data_ptr(), A2.stride(0), K1
-    if GEMM_TIMER is not None:
-        with GEMM_TIMER(2.0 * M * N * K):
+    if KERNEL_TIMER is not None:
+        with KERNEL_TIMER("gemm", 2.0 * M * N * K):
             check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16(cat)")
     else:
         check(_lib.lib().mmsum_gemm_bf16(C.byref(a), _stream()), "mmsum_gemm_bf16(cat)")
     return out
+
+
+def _timed(kind, work, fn):
+    if KERNEL_TIMER is None:
+        return fn()
+    with KERNEL_TIMER(kind, work):
+        return fn()
 
 
 def cast_bf16(src, dst):
@@ -123,6 +132,11 @@ def cast_bf16(src, dst):
 
 
 def embed_ln_fwd(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, rows, S, p_drop, seed, sid):
+    # algorithmic bytes: one fp32 table row read + one bf16 row written per token (positions / LN parameters stay in L2)
+    _timed("embed_ln_fwd", rows * E.shape[1] * 6.0, lambda: _embed_ln_fwd(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, rows, S, p_drop, seed, sid))
+
+
+def _embed_ln_fwd(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, rows, S, p_drop, seed, sid):
     check(_lib.lib().mmsum_embed_ln_fwd(_ptr(ids), _ptr(E), _ptr(P), _ptr(rating_diff), _ptr(remb), _ptr(gamma), _ptr(beta),
                                         _ptr(out), _ptr(mean), _ptr(rstd), rows, S, E.shape[1], C.c_float(p_drop),
                                         C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_embed_ln_fwd")
@@ -138,11 +152,22 @@ def embed_ln_bwd(dout, dout2, ids, E, P, rating_diff, remb, gamma, mean, rstd, d
 
 def add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid):
     rows, d = res.shape
+    _timed("add_ln_fwd", 3.0 * rows * d * 2, lambda: _add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid))
+
+
+def _add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid):
+    rows, d = res.shape
     check(_lib.lib().mmsum_add_ln_fwd(_ptr(res), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(mean), _ptr(rstd), rows, d,
                                       C.c_float(p_drop), C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_add_ln_fwd")
 
 
 def add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid):
+    rows, d = res.shape
+    n_mats = 3 + (1 if d2 is not None else 0) + 1 + (1 if dy.data_ptr() != dres.data_ptr() else 0)   # d1 (+d2), res, y in; dres (+dy) out
+    _timed("add_ln_bwd", float(n_mats) * rows * d * 2, lambda: _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid))
+
+
+def _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid):
     rows, d = res.shape
     check(_lib.lib().mmsum_add_ln_bwd(_ptr(d1), _ptr(d2), _ptr(res), _ptr(y), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres),
                                       _ptr(dy), _ptr(dgamma), _ptr(dbeta), rows, d, C.c_float(p_drop), C.c_uint64(seed),
@@ -152,22 +177,44 @@ def add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_dro
 def colsum(x, out):
     """out[n] += Σ_r x[r, n]  (x bf16 2-D, possibly a column-slice view)."""
     _check2d(x, "x", torch.bfloat16)
+    _timed("colsum", 2.0 * x.shape[0] * x.shape[1], lambda: _colsum(x, out))
+
+
+def _colsum(x, out):
     check(_lib.lib().mmsum_colsum(_ptr(x), C.c_int64(x.stride(0)), x.shape[0], x.shape[1], _ptr(out), _stream()), "mmsum_colsum")
 
 
 def gate_fwd(o3, u, pres, y, ab, rows, rows_per_biz, d):
+    _timed("gate", 8.0 * rows * d * 2, lambda: _gate_fwd(o3, u, pres, y, ab, rows, rows_per_biz, d))
+
+
+def _gate_fwd(o3, u, pres, y, ab, rows, rows_per_biz, d):
     check(_lib.lib().mmsum_gate_fwd(_ptr(o3), _ptr(u), _ptr(pres), _ptr(y), _ptr(ab), rows, rows_per_biz, d, _stream()), "mmsum_gate_fwd")
 
 
 def gate_bwd_u(dy, o3, ab, du, rows, d):
+    _timed("gate", 8.0 * rows * d * 2, lambda: _gate_bwd_u(dy, o3, ab, du, rows, d))
+
+
+def _gate_bwd_u(dy, o3, ab, du, rows, d):
     check(_lib.lib().mmsum_gate_bwd_u(_ptr(dy), _ptr(o3), _ptr(ab), _ptr(du), rows, d, _stream()), "mmsum_gate_bwd_u")
 
 
 def gate_bwd_o(dy, ab, dca, dcb, do3, rows, d):
+    _timed("gate", 10.0 * rows * d * 2, lambda: _gate_bwd_o(dy, ab, dca, dcb, do3, rows, d))
+
+
+def _gate_bwd_o(dy, ab, dca, dcb, do3, rows, d):
     check(_lib.lib().mmsum_gate_bwd_o(_ptr(dy), _ptr(ab), _ptr(dca), _ptr(dcb), _ptr(do3), rows, d, _stream()), "mmsum_gate_bwd_o")
 
 
 def ce_fwd_bwd(logits, V, target, eps, gscale, gscale_dev, loss_rows, loss_out, loss_scale, write_grad):
+    rows = logits.shape[0]
+    _timed("ce_bwd" if write_grad else "ce_fwd", (2.0 if write_grad else 1.0) * rows * V * 2,
+           lambda: _ce_fwd_bwd(logits, V, target, eps, gscale, gscale_dev, loss_rows, loss_out, loss_scale, write_grad))
+
+
+def _ce_fwd_bwd(logits, V, target, eps, gscale, gscale_dev, loss_rows, loss_out, loss_scale, write_grad):
     rows = logits.shape[0]
     check(_lib.lib().mmsum_ce_fwd_bwd(_ptr(logits), C.c_int64(logits.stride(0)), rows, V, _ptr(target),
                                       C.c_float(-1.0 if eps is None else eps), C.c_float(gscale), _ptr(gscale_dev),
@@ -189,12 +236,25 @@ def attn_args(**kw):
     return a
 
 
+def attn_flops(a):
+    """Algorithmic forward FLOPs of one attention call: QK^T + PV over dense 128 x keys tiles of every
+    (sequence, head, entity) pair that is attended (the leave-one-out entity excluded; causal / pad savings not credited)."""
+    keys = 0
+    for i in range(a.n_mod):
+        m = a.mods[i]
+        keys += (m.E - (1 if m.loo else 0)) * m.Sk
+    return 4.0 * 128 * 64 * keys * a.n_qseq * a.H
+
+
 def attn_fwd(a):
-    check(_lib.lib().mmsum_attn_fwd(C.byref(a), _stream()), "mmsum_attn_fwd")
+    kind = "attn_self_fwd" if a.n_mod == 1 and a.mods[0].E == 1 else "attn_cross_fwd"
+    _timed(kind, attn_flops(a), lambda: check(_lib.lib().mmsum_attn_fwd(C.byref(a), _stream()), "mmsum_attn_fwd"))
 
 
 def attn_bwd(a):
-    check(_lib.lib().mmsum_attn_bwd(C.byref(a), _stream()), "mmsum_attn_bwd", 2)
+    # backward = 2.5 x forward algorithmic FLOPs (S, dP, dQ, dK, dV products; SURVEY App. H); two kernels (dQ, then dK/dV)
+    kind = "attn_self_bwd" if a.n_mod == 1 and a.mods[0].E == 1 else "attn_cross_bwd"
+    _timed(kind, 2.5 * attn_flops(a), lambda: check(_lib.lib().mmsum_attn_bwd(C.byref(a), _stream()), "mmsum_attn_bwd", 2))
 
 
 def prep_step(reviews, reviews_mask, rating, table_valid, img_mask, **kw):

@@ -59,7 +59,11 @@ class FusedAdamW:
 
     def step(self, lr=None):
         eng = self.engine
-        lr = self.param_groups[0]["lr"] if lr is None else lr
+        if lr is None:
+            lrs = {g["lr"] for g in self.param_groups if g["params"]}
+            if len(lrs) > 1:
+                raise ValueError("parameter groups with different learning rates are not supported by the fused step")
+            lr = lrs.pop() if lrs else self.lr
         self.step_count += 1
         b1, b2 = self.betas
         step_size = lr
@@ -81,6 +85,82 @@ class FusedAdamW:
     def grad_norm(self):
         return self.sumsq.sqrt()
 
+    # -- checkpoint interchange (src/train_utils.py:97 saves optimizer.state_dict() into training_state.bin) ---------------
+    def state_dict(self):
+        """torch.optim-style dict with transformers-AdamW state names (`step`, `exp_avg`, `exp_avg_sq`), so the reference's
+        own AdamW can `load_state_dict` it when built over the same parameter groups."""
+        eng = self.engine
+        by_id = {id(p): name for name, p in eng.params.items()}
+        state, groups, idx = {}, [], 0
+        for g in self.param_groups:
+            ids = []
+            for p in g["params"]:
+                name = by_id[id(p)]
+                o, n = eng.offsets[name], math.prod(eng.shapes[name])
+                if self.step_count > 0:
+                    state[idx] = {"step": self.step_count, "exp_avg": self.m[o:o + n].view(eng.shapes[name]).detach().cpu().clone(),
+                                  "exp_avg_sq": self.v[o:o + n].view(eng.shapes[name]).detach().cpu().clone()}
+                ids.append(idx)
+                idx += 1
+            groups.append({"lr": g["lr"], "betas": self.betas, "eps": self.eps, "weight_decay": float(g.get("weight_decay", 0.0)),
+                           "correct_bias": self.correct_bias, "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        eng = self.engine
+        by_id = {id(p): name for name, p in eng.params.items()}
+        idx = 0
+        steps = set()
+        for g, gs in zip(self.param_groups, sd["param_groups"]):
+            g["lr"] = gs["lr"]
+            for p in g["params"]:
+                st = sd["state"].get(idx)
+                if st is not None:
+                    name = by_id[id(p)]
+                    o, n = eng.offsets[name], math.prod(eng.shapes[name])
+                    self.m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                    self.v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.add(int(st["step"]))
+                idx += 1
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ; the fused optimizer keeps one")
+        self.step_count = steps.pop() if steps else 0
+
+
+class LinearWarmupSchedule:
+    """`get_linear_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps)` (src/transformer/optimization.py:70-97,
+    a torch LambdaLR): `step()` after every optimizer step sets lr = base_lr * lambda(step) in every parameter group.
+    As LambdaLR does, construction performs the step-0 update (lr = 0 when there is a warm-up)."""
+
+    def __init__(self, optimizer, num_warmup_steps, num_training_steps, last_epoch=-1):
+        self.optimizer = optimizer
+        self.num_warmup_steps, self.num_training_steps = num_warmup_steps, num_training_steps
+        self.base_lrs = [g["lr"] for g in optimizer.param_groups]
+        self.last_epoch = last_epoch
+        self.step()
+
+    def lr_lambda(self, current_step):
+        if current_step < self.num_warmup_steps:
+            return float(current_step) / float(max(1, self.num_warmup_steps))
+        return max(0.0, float(self.num_training_steps - current_step) / float(max(1, self.num_training_steps - self.num_warmup_steps)))
+
+    def step(self):
+        self.last_epoch += 1
+        for g, base in zip(self.optimizer.param_groups, self.base_lrs):
+            g["lr"] = base * self.lr_lambda(self.last_epoch)
+
+    def get_last_lr(self):
+        return [g["lr"] for g in self.optimizer.param_groups]
+
+    def state_dict(self):
+        return {"base_lrs": list(self.base_lrs), "last_epoch": self.last_epoch, "_step_count": self.last_epoch + 1,
+                "_last_lr": self.get_last_lr()}
+
+    def load_state_dict(self, sd):
+        self.base_lrs, self.last_epoch = list(sd["base_lrs"]), sd["last_epoch"]
+        for g, base in zip(self.optimizer.param_groups, self.base_lrs):
+            g["lr"] = base * self.lr_lambda(self.last_epoch)
+
 
 def get_optimizer(engine, lr, no_decay, named_parameters, special_condition=None, max_grad_norm=None):
     """src/train_utils.py:49-57, statement for statement — including quirk Q1: when `named_parameters` is a generator
@@ -94,6 +174,13 @@ def get_optimizer(engine, lr, no_decay, named_parameters, special_condition=None
          "weight_decay": 0.0},
     ]
     return FusedAdamW(engine, groups, lr=lr, max_grad_norm=max_grad_norm)
+
+
+def get_scheduler(args, t_epoch, optimizer):
+    """src/train_utils.py:59-63."""
+    t_total = t_epoch * args.num_epochs
+    warmup_step = int(t_total * args.warmup_ratio)
+    return LinearWarmupSchedule(optimizer, num_warmup_steps=warmup_step, num_training_steps=t_total)
 
 
 def linear_schedule_with_warmup(base_lr, num_warmup_steps, num_training_steps):

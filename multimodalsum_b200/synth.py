@@ -31,11 +31,32 @@ class ModelConfig:
     eos_token_id: int = 2
     dropout: float = 0.1
     init_std: float = 0.02
-    dataset: str = "yelp"  # 'yelp' | 'amazon' | 'text' (text-only: no table / image memory)
+    # 'yelp' | 'amazon': multimodal step (text + table + image memory, gated fusion)      src/multimodal_train.py
+    # 'text': text-only step (config 1)                                                   src/text_pretrain.py
+    # 'img' | 'table_yelp' | 'table_amazon': single-modality pretraining stages            src/img_pretrain.py, src/table_pretrain.py
+    dataset: str = "yelp"
 
     @property
     def head_dim(self):
         return self.d_model // self.heads
+
+    @property
+    def multimodal(self):
+        """Decoder cross-attention fuses three modalities with alpha/beta gates (BartForMultiEncConditionalGeneration)."""
+        return self.dataset in ("yelp", "amazon")
+
+    @property
+    def text_memory(self):
+        """The decoder attends to encoded reviews (leave-one-out); false for the img / table pretraining stages."""
+        return self.dataset in ("yelp", "amazon", "text")
+
+    @property
+    def table(self):
+        return {"yelp": "yelp", "amazon": "amazon", "table_yelp": "yelp", "table_amazon": "amazon"}.get(self.dataset)
+
+    @property
+    def image(self):
+        return self.dataset in ("yelp", "amazon", "img")
 
     def to_reference_dict(self):
         return dict(d_model=self.d_model, encoder_layers=self.encoder_layers, decoder_layers=self.decoder_layers,
@@ -64,7 +85,7 @@ def param_shapes(cfg: ModelConfig):
         for p in ("k_proj", "v_proj", "q_proj", "out_proj"):
             s[prefix + p + ".weight"] = (D, D)
             s[prefix + p + ".bias"] = (D,)
-        if cross and cfg.dataset != "text":
+        if cross and cfg.multimodal:
             for p in ("alpha_proj", "beta_proj"):
                 s[prefix + p + ".weight"] = (D, 2 * D)
                 s[prefix + p + ".bias"] = (D,)
@@ -92,10 +113,10 @@ def param_shapes(cfg: ModelConfig):
             s[lp + "fc2.bias"] = (D,)
             ln(lp + "final_layer_norm")
         ln(pre + "layernorm_embedding")
-    if cfg.dataset in ("yelp", "amazon"):
+    if cfg.table is not None:
         t = "table_encoder."
         s[t + "bart_embedding.weight"] = (V, D)  # alias of shared
-        if cfg.dataset == "yelp":
+        if cfg.table == "yelp":
             s[t + "rating_embedding.weight"] = (D, 4)
             s[t + "hours_embedding.weight"] = (D, 4)
         else:
@@ -104,6 +125,7 @@ def param_shapes(cfg: ModelConfig):
         s[t + "fc.weight"] = (D, 2 * D)
         s[t + "fc.bias"] = (D,)
         s[t + "linear.weight"] = (D, D)
+    if cfg.image:
         s["img_encoder.linear.weight"] = (D, 1024)
     return s
 
@@ -141,6 +163,13 @@ def make_state_dict(cfg: ModelConfig, seed=0, perturb=True, gates_open=False, lo
     return sd
 
 
+def make_grads(cfg: ModelConfig, seed=0, std=1e-3):
+    """Deterministic synthetic gradients keyed like `named_parameters()` (optimizer parity tests: the same gradients can be
+    rebuilt in the build container for the reference's AdamW and on the GPU box for the fused kernel)."""
+    return {name: _draw(name + "#grad", shape, std, seed) for name, shape in param_shapes(cfg).items()
+            if not name.endswith(ALIASES) and not name.endswith("final_logits_bias")}
+
+
 @dataclass
 class Batch:
     reviews: torch.Tensor          # i64 [B, R, S]
@@ -150,20 +179,24 @@ class Batch:
     field_value: list = dc_field(default_factory=list)
     img: torch.Tensor = None       # f32 [B, max_imgs, 196, 1024] pooled ResNet-101 stage-3 features
     img_mask: torch.Tensor = None  # bool [B, max_imgs]
+    labels: torch.Tensor = None    # i64 [B, S]: decoder targets of the img / table pretraining stages (reviews is None there)
 
     def to(self, device, non_blocking=False):
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
         return Batch(mv(self.reviews), mv(self.reviews_mask), mv(self.reviews_rating), mv(self.field),
-                     [mv(t) for t in self.field_value], mv(self.img), mv(self.img_mask))
+                     [mv(t) for t in self.field_value], mv(self.img), mv(self.img_mask), mv(self.labels))
 
     def pin(self):
         pv = lambda t: None if t is None else t.pin_memory()
         return Batch(pv(self.reviews), pv(self.reviews_mask), pv(self.reviews_rating), pv(self.field),
-                     [pv(t) for t in self.field_value], pv(self.img), pv(self.img_mask))
+                     [pv(t) for t in self.field_value], pv(self.img), pv(self.img_mask), pv(self.labels))
+
+    def tensors(self):
+        return [t for t in [self.reviews, self.reviews_mask, self.reviews_rating, self.field, self.img, self.img_mask, self.labels]
+                + list(self.field_value) if t is not None]
 
     def nbytes(self):
-        ts = [self.reviews, self.reviews_mask, self.reviews_rating, self.field, self.img, self.img_mask] + list(self.field_value)
-        return sum(t.numel() * t.element_size() for t in ts if t is not None)
+        return sum(t.numel() * t.element_size() for t in self.tensors())
 
 
 def _pad_tail(tok, g, lo=1):
@@ -195,7 +228,10 @@ def make_batch(cfg: ModelConfig, B, seed=1, n_reviews=9, seq_len=128, fixed_len=
     batch = Batch(rev, mask, rating)
     if cfg.dataset == "text":
         return batch
-    if cfg.dataset == "yelp":
+    if not cfg.text_memory:
+        # pretraining stages: one target review per business, memory = its images / its table only
+        batch = Batch(None, None, None, labels=rev[:, 0].contiguous())
+    if cfg.table == "yelp":
         batch.field = _pad_tail(torch.randint(3, V, (47, 6), generator=g), g)
         name = _pad_tail(torch.randint(3, V, (B, 24), generator=g), g)
         category = _pad_tail(torch.randint(3, V, (B, 6, 12), generator=g), g, lo=0)
@@ -207,7 +243,7 @@ def make_batch(cfg: ModelConfig, B, seed=1, n_reviews=9, seq_len=128, fixed_len=
         hours.scatter_(2, hsel.clamp(max=3).unsqueeze(-1), (hsel < 4).long().unsqueeze(-1))
         batch.field_value = [name, category, str_cat, str_bool, rbits, hours]
         mi = 10 if max_imgs is None else max_imgs
-    else:
+    elif cfg.table == "amazon":
         batch.field = torch.randint(3, V, (6, 1), generator=g)
         price = torch.randint(0, 2, (B, 11), generator=g)
         rbits = torch.randint(0, 2, (B, 4), generator=g)
@@ -217,6 +253,10 @@ def make_batch(cfg: ModelConfig, B, seed=1, n_reviews=9, seq_len=128, fixed_len=
         desc = _pad_tail(torch.randint(3, V, (B, 128), generator=g), g, lo=0)
         batch.field_value = [price, rbits, brand, name, category, desc]
         mi = 1 if max_imgs is None else max_imgs
+    else:
+        mi = 10 if max_imgs is None else max_imgs
+    if not cfg.image:
+        return batch
     batch.img = torch.relu(torch.randn(B, mi, 196, 1024, generator=g))
     if n_valid_imgs is None:
         k = torch.randint(0, mi + 1, (B,), generator=g)

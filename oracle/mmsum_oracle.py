@@ -238,20 +238,19 @@ def multimodal_memories(p, cfg, batch, training=False):
     text_valid = batch.reviews_mask.bool()
     if cfg.dataset == "text":
         return text, text_valid, None, None, None, None
-    tenc = yelp_table_encoder if cfg.dataset == "yelp" else amazon_table_encoder
+    tenc = yelp_table_encoder if cfg.table == "yelp" else amazon_table_encoder
     table, table_valid = tenc(p, batch.field, batch.field_value)
     img = F.linear(batch.img.to(text.dtype), p["img_encoder.linear.weight"])      # img_encoder.py:39-40
     img_valid = batch.img_mask.unsqueeze(-1).expand(-1, -1, img.shape[2])
     return text, text_valid, table.unsqueeze(1), table_valid.unsqueeze(1), img, img_valid
 
 
-def step_loss(p, cfg, batch, label_smoothing=0.1, training=False, return_logits=False):
+def step_loss_passes(p, cfg, batch, label_smoothing=0.1, training=False, return_logits=False):
     """MultimodalSum.forward, multimodal_train.py:124-163 (and TextSupervised.forward, text_pretrain.py:71-113 for
-    cfg.dataset == 'text'): leave-one-out loop over the R reviews, mean of the R losses."""
+    cfg.dataset == 'text'): generator over the R leave-one-out passes, yielding (loss_i, logits_i or None)."""
     text, text_valid, table, table_valid, img, img_valid = multimodal_memories(p, cfg, batch, training)
     B, R, S = batch.reviews.shape
     rating = batch.reviews_rating.to(text.dtype)
-    losses, all_logits = [], []
     for i in range(R):
         others = [j for j in range(R) if j != i]
         rating_diff = (rating[:, i] - rating[:, others].mean(dim=1)).unsqueeze(1)
@@ -264,15 +263,43 @@ def step_loss(p, cfg, batch, label_smoothing=0.1, training=False, return_logits=
             valids = [text_valid[:, others], table_valid, img_valid]
         x = decoder(p, cfg, dec_ids, mems, valids, rating_diff, training)
         logits = lm_logits(x, p)
-        if return_logits:
-            all_logits.append(logits)
-        losses.append(label_smoothing_loss(logits.view(-1, logits.shape[-1]), labels.reshape(-1), label_smoothing))
+        yield label_smoothing_loss(logits.view(-1, logits.shape[-1]), labels.reshape(-1), label_smoothing), \
+            (logits if return_logits else None)
+
+
+def step_loss(p, cfg, batch, label_smoothing=0.1, training=False, return_logits=False):
+    """Mean of the R pass losses (multimodal_train.py:162)."""
+    losses, all_logits = [], []
+    for li, lg in step_loss_passes(p, cfg, batch, label_smoothing, training, return_logits):
+        losses.append(li)
+        all_logits.append(lg)
     loss = torch.stack(losses).mean()
     return (loss, all_logits) if return_logits else loss
 
 
-def step_loss_and_grads(sd, cfg, batch, label_smoothing=0.1, dtype=torch.float32, device="cpu", training=False):
-    """Forward + backward of the oracle; returns (loss, {name: grad}) keyed like the reference's named_parameters()."""
+def stage_step_loss(p, cfg, batch, label_smoothing=0.1, training=False):
+    """ImgSupervised.forward (img_pretrain.py:91-141) / TableSupervised.forward (table_pretrain.py:90-129): the memory is
+    the projected image features [B, max_imgs, 196, D] (mask repeated over the 196 keys) or the table encoder's output
+    [B, 1, F, D]; rating_diff = 0; decoder inputs = shift_tokens_right(labels); one loss over all B*128 rows."""
+    if cfg.image:
+        mem = F.linear(batch.img.to(p["img_encoder.linear.weight"].dtype), p["img_encoder.linear.weight"])
+        valid = batch.img_mask.unsqueeze(-1).expand(-1, -1, mem.shape[2])
+    else:
+        tenc = yelp_table_encoder if cfg.table == "yelp" else amazon_table_encoder
+        mem, valid = tenc(p, batch.field, batch.field_value)
+        mem, valid = mem.unsqueeze(1), valid.unsqueeze(1)
+    labels = batch.labels
+    rd = torch.zeros(labels.shape[0], 1, dtype=mem.dtype, device=mem.device)
+    dec_ids = shift_tokens_right(labels, cfg.pad_token_id, cfg.bos_token_id, cfg.eos_token_id)
+    x = decoder(p, cfg, dec_ids, mem, valid, rd, training)
+    logits = lm_logits(x, p)
+    return label_smoothing_loss(logits.view(-1, logits.shape[-1]), labels.reshape(-1), label_smoothing)
+
+
+def step_loss_and_grads(sd, cfg, batch, label_smoothing=0.1, dtype=torch.float32, device="cpu", training=False, low_memory=False):
+    """Forward + backward of the oracle; returns (loss, {name: grad}) keyed like the reference's named_parameters().
+    `low_memory`: back-propagate each leave-one-out pass as soon as its loss exists (same sum of gradients, one pass of
+    activations alive at a time) — for the full-size GPU comparisons at 16 businesses."""
     p = {}
     leaf = {}
     for k, v in sd.items():
@@ -287,11 +314,19 @@ def step_loss_and_grads(sd, cfg, batch, label_smoothing=0.1, dtype=torch.float32
     shared = p["bart_model.model.shared.weight"]
     p["bart_model.model.encoder.embed_tokens.weight"] = shared
     p["bart_model.model.decoder.embed_tokens.weight"] = shared
-    if cfg.dataset != "text":
+    if cfg.table is not None:
         p["table_encoder.bart_embedding.weight"] = shared
     b = batch.to(device)
-    loss = step_loss(p, cfg, b, label_smoothing, training)
-    loss.backward()
+    if low_memory and cfg.text_memory:
+        R = b.reviews.shape[1]
+        loss = torch.zeros((), dtype=dtype, device=device)
+        for li, _ in step_loss_passes(p, cfg, b, label_smoothing, training):
+            (li / R).backward(retain_graph=True)
+            loss = loss + li.detach() / R
+            del li
+    else:
+        loss = (step_loss if cfg.text_memory else stage_step_loss)(p, cfg, b, label_smoothing, training)
+        loss.backward()
     grads = {k: t.grad for k, t in leaf.items() if t.grad is not None}
     return loss.detach(), grads, p
 

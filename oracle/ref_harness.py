@@ -99,7 +99,7 @@ def build_reference_model(cfg, state_dict, dtype=torch.float32, label_smoothing=
     model = MT.MultimodalSum.__new__(MT.MultimodalSum)
     nn.Module.__init__(model)
     model.bart_model = m["MultiEnc"](bcfg)
-    TableEnc = m["TE"].YelpTableEncoder if cfg.dataset == "yelp" else m["TE"].AmazonTableEncoder
+    TableEnc = m["TE"].YelpTableEncoder if cfg.table == "yelp" else m["TE"].AmazonTableEncoder
     model.table_encoder = TableEnc(model.bart_model.model.shared)
     model.img_encoder = _FeatProj(cfg.d_model)
     model.get_multimodal_outputs = types.MethodType(_get_multimodal_outputs, model)
@@ -145,6 +145,58 @@ def reference_text_step(cfg, state_dict, batch, dtype=torch.float32, label_smoot
     assert not unexpected and not missing, (missing, unexpected)
     model = model.to(dtype).train()
     loss = model(batch.reviews, batch.reviews_mask, batch.reviews_rating.to(dtype))[0]
+    model.zero_grad()
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    return loss.detach(), grads, model
+
+
+class _FeatBox:
+    """Lets the UNMODIFIED ImgSupervised.forward (src/img_pretrain.py:108-113) run on pooled features: it only calls
+    `.size()` and `.reshape([-1, 3, 224, 224])` on its image input before handing it to `img_encoder`."""
+
+    def __init__(self, feats):
+        self.feats = feats
+
+    def size(self):
+        return self.feats.size()
+
+    def reshape(self, shape):
+        return self.feats
+
+
+def reference_stage_step(cfg, state_dict, batch, dtype=torch.float32, label_smoothing=0.1):
+    """The reference's single-modality pretraining steps, unmodified: img_pretrain.ImgSupervised.forward
+    (src/img_pretrain.py:91-141) / table_pretrain.TableSupervised.forward (src/table_pretrain.py:90-129)."""
+    m = _import_reference()
+    import warnings
+    bcfg = m["BartConfig"].from_json_file(os.path.join(REF_ROOT, "cfg", "bart-large.json"))
+    for k, v in cfg.to_reference_dict().items():
+        setattr(bcfg, k, v)
+    bcfg.dropout = 0.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if cfg.image:
+            import img_pretrain as SP
+            model = SP.ImgSupervised.__new__(SP.ImgSupervised)
+            nn.Module.__init__(model)
+            model.bart_model = m["Enc"](bcfg)
+            model.img_encoder = _FeatProj(cfg.d_model)
+        else:
+            import table_pretrain as SP
+            model = SP.TableSupervised.__new__(SP.TableSupervised)
+            nn.Module.__init__(model)
+            model.bart_model = m["Enc"](bcfg)
+            TableEnc = m["TE"].YelpTableEncoder if cfg.table == "yelp" else m["TE"].AmazonTableEncoder
+            model.table_encoder = TableEnc(model.bart_model.model.shared)
+    SP.args = argparse.Namespace(label_smoothing=label_smoothing)
+    missing, unexpected = model.load_state_dict(state_dict, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    model = model.to(dtype).train()
+    if cfg.image:
+        loss = model(_FeatBox(batch.img.to(dtype)), batch.img_mask, labels=batch.labels)[0]
+    else:
+        loss = model(batch.field, batch.field_value, labels=batch.labels)[0]
     model.zero_grad()
     loss.backward()
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}

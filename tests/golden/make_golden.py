@@ -32,6 +32,10 @@ CASES = {
     "full_yelp_b1": (dict(dataset="yelp", dropout=0.0), dict(seed=0), dict(B=1, seed=1, n_reviews=9, n_valid_imgs=4)),
     "full_yelp_b1_gates_open": (dict(dataset="yelp", dropout=0.0), dict(seed=0, gates_open=True), dict(B=1, seed=7, n_reviews=9)),
     "full_text_b1": (dict(dataset="text", dropout=0.0), dict(seed=0), dict(B=1, seed=8, n_reviews=9)),
+    # single-modality pretraining stages (src/img_pretrain.py, src/table_pretrain.py)
+    "small_img": (dict(SMALL, dataset="img"), dict(seed=9), dict(B=3, seed=10, max_imgs=3)),
+    "small_table_yelp": (dict(SMALL, dataset="table_yelp"), dict(seed=9), dict(B=3, seed=11)),
+    "small_table_amazon": (dict(SMALL, dataset="table_amazon"), dict(seed=9), dict(B=3, seed=12)),
 }
 
 
@@ -85,6 +89,8 @@ def main(which):
         cfg, sd, batch = build_case(name)
         if cfg.dataset == "text":
             loss, grads, _ = RH.reference_text_step(cfg, sd, batch, dtype=torch.float32, label_smoothing=None)
+        elif not cfg.text_memory:
+            loss, grads, _ = RH.reference_stage_step(cfg, sd, batch, dtype=torch.float32, label_smoothing=0.1)
         else:
             loss, grads, _ = RH.reference_step(cfg, sd, batch, dtype=torch.float32, label_smoothing=0.1)
         out = {"case": json.dumps(dict(name=name, cfg=CASES[name][0], sd=CASES[name][1], batch=CASES[name][2],
@@ -98,9 +104,65 @@ def main(which):
         print("%s: loss %.9f, %d grads, %.1fs" % (name, loss.item(), len(names), time.time() - t0), flush=True)
 
 
+OPT_CASE = dict(cfg=dict(SMALL, dataset="yelp"), sd=dict(seed=0), grads=dict(seed=4, std=1e-3), lr=1e-3, steps=3,
+                max_grad_norm=1.0, num_epochs=1, t_epoch=4, warmup_ratio=0.5, no_decay=["bias", "LayerNorm.weight"])
+
+
+def make_optimizer_golden():
+    """clip_grad_norm_ + AdamW + linear warm-up schedule exactly as src/multimodal_train.py:359-364 drives them:
+    the reference's own get_optimizer / get_scheduler (src/train_utils.py:49-63, incl. the exhausted-generator quirk Q1),
+    the vendored transformers-3.0.2 AdamW (src/transformer/optimization.py:168-267), torch's clip_grad_norm_."""
+    import argparse
+    from multimodalsum_b200.synth import make_grads
+    c = OPT_CASE
+    cfg = ModelConfig(**c["cfg"])
+    sd = make_state_dict(cfg, **c["sd"])
+    grads = make_grads(cfg, **c["grads"])
+    model = RH.build_reference_model(cfg, sd, dtype=torch.float32)
+    import train_utils as TU          # the reference's (RH put /root/reference/src on sys.path)
+    opt = TU.get_optimizer(c["lr"], c["no_decay"], model.named_parameters(), None)
+    sched = TU.get_scheduler(argparse.Namespace(num_epochs=c["num_epochs"], warmup_ratio=c["warmup_ratio"]), c["t_epoch"], opt)
+    named = dict(model.named_parameters())
+    lrs, gnorms = [], []
+    for _ in range(c["steps"]):
+        opt.zero_grad()
+        for n, p in named.items():
+            p.grad = grads[n].clone()
+        lrs.append(opt.param_groups[0]["lr"])
+        gnorms.append(float(torch.nn.utils.clip_grad_norm_(model.parameters(), c["max_grad_norm"])))
+        opt.step()
+        sched.step()
+    names = sorted(named)
+    np.savez_compressed(os.path.join(HERE, "adamw_small.npz"),
+                        case=json.dumps(dict(name="adamw_small", torch=torch.__version__, **c)),
+                        names=np.array(names), lrs=np.array(lrs), gnorms=np.array(gnorms),
+                        norms=np.array([named[n].detach().double().norm().item() for n in names]),
+                        delta_norms=np.array([(named[n].detach().double() - sd[n].double()).norm().item() for n in names]),
+                        samples=np.stack([np.pad(sample(named[n].detach()), (0, 64 - len(sample(named[n].detach())))) for n in names]),
+                        sched_lrs=np.array([TU_lr for TU_lr in _sched_table(c)]))
+    print("adamw_small: lrs %s, grad norms %s" % (lrs, gnorms), flush=True)
+
+
+def _sched_table(c):
+    """lr after k scheduler steps, k = 0..t_total+1, from the reference's get_scheduler on a dummy optimizer."""
+    import argparse
+    import train_utils as TU
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=c["lr"])
+    sched = TU.get_scheduler(argparse.Namespace(num_epochs=c["num_epochs"], warmup_ratio=c["warmup_ratio"]), c["t_epoch"], opt)
+    out = [opt.param_groups[0]["lr"]]
+    for _ in range(c["t_epoch"] * c["num_epochs"] + 1):
+        opt.step()
+        sched.step()
+        out.append(opt.param_groups[0]["lr"])
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "gen"):
         make_generation_goldens()
-    if which != "gen":
+    if which in ("all", "opt"):
+        make_optimizer_golden()
+    if which not in ("gen", "opt"):
         main(which)

@@ -23,6 +23,37 @@ def load_golden(name):
                 label_smoothing=None if cfg.dataset == "text" else 0.1)
 
 
+def load_optimizer_golden(name="adamw_small"):
+    """Parameters after `steps` rounds of clip_grad_norm_ + AdamW + linear warm-up as the UNMODIFIED reference runs them
+    (tests/golden/make_golden.py opt)."""
+    from multimodalsum_b200.synth import make_grads
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    case = json.loads(str(z["case"]))
+    cfg = ModelConfig(**case["cfg"])
+    names = [str(n) for n in z["names"]]
+    return dict(case=case, cfg=cfg, sd=make_state_dict(cfg, **case["sd"]), grads=make_grads(cfg, **case["grads"]), names=names,
+                lrs=z["lrs"].tolist(), gnorms=z["gnorms"].tolist(), norms=dict(zip(names, z["norms"].tolist())),
+                delta_norms=dict(zip(names, z["delta_norms"].tolist())), samples=dict(zip(names, z["samples"])),
+                sched_lrs=z["sched_lrs"].tolist())
+
+
+def check_params_against_optimizer_golden(gold, params, rtol=2e-5):
+    """params: {name: tensor} after the golden's steps.  The UPDATE (p - p0) must match to rtol of its own norm; sampled
+    entries of p must match to rtol of the update's RMS."""
+    bad = []
+    for n in gold["names"]:
+        p = params[n].detach().double().cpu()
+        p0 = gold["sd"][n].double()
+        dn = (p - p0).norm().item()
+        ref_dn = gold["delta_norms"][n]
+        smp = sample(p)
+        rms = max(ref_dn, 1e-12) / max(p.numel(), 1) ** 0.5
+        e_smp = float(np.abs(smp - gold["samples"][n]).max())
+        if abs(dn - ref_dn) > rtol * max(ref_dn, 1e-12) + 1e-12 or e_smp > 50 * rtol * rms + 1e-9:
+            bad.append((n, dn, ref_dn, e_smp, rms))
+    return bad
+
+
 def sample(g):
     s = g.detach().flatten()[::997][:64].double().cpu().numpy()
     return np.pad(s, (0, 64 - len(s)))

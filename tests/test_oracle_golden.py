@@ -6,7 +6,7 @@ import torch
 from golden_util import compare_grads, load_golden
 from oracle import mmsum_oracle as OR
 
-SMALL = ["small_yelp", "small_yelp_gates_open", "small_amazon", "small_text"]
+SMALL = ["small_yelp", "small_yelp_gates_open", "small_amazon", "small_text", "small_img", "small_table_yelp", "small_table_amazon"]
 
 
 @pytest.mark.parametrize("name", SMALL)

@@ -15,13 +15,25 @@ from golden_util import load_golden, weight_sibling
 pytestmark = pytest.mark.gpu
 
 
+def _stage_inputs(cfg, b):
+    if cfg.dataset == "img":
+        return (b.img, b.img_mask), dict(labels=b.labels)
+    return (b.field, b.field_value), dict(labels=b.labels)
+
+
 def _run_cuda_step(gold, dropout=0.0):
-    from multimodalsum_b200.modules import AmazonTableEncoder, MultimodalSum, TextSupervised, YelpTableEncoder
+    from multimodalsum_b200.modules import (AmazonTableEncoder, ImgSupervised, MultimodalSum, TableSupervised, TextSupervised,
+                                            YelpTableEncoder)
     cfg = gold["cfg"]
     cfg.dropout = dropout
     dev = torch.device("cuda")
     if cfg.dataset == "text":
         model = TextSupervised(config=cfg, label_smoothing=None)
+    elif cfg.dataset == "img":
+        model = ImgSupervised(config=cfg, label_smoothing=0.1)
+    elif cfg.dataset.startswith("table_"):
+        model = TableSupervised(TableEncoder=YelpTableEncoder if cfg.table == "yelp" else AmazonTableEncoder, config=cfg,
+                                label_smoothing=0.1)
     else:
         model = MultimodalSum(TableEncoder=YelpTableEncoder if cfg.dataset == "yelp" else AmazonTableEncoder, config=cfg,
                               label_smoothing=0.1)
@@ -31,6 +43,9 @@ def _run_cuda_step(gold, dropout=0.0):
     b = gold["batch"].to(dev)
     if cfg.dataset == "text":
         loss = model(b.reviews, b.reviews_mask, b.reviews_rating)[0]
+    elif not cfg.text_memory:
+        a, kw = _stage_inputs(cfg, b)
+        loss = model(*a, **kw)[0]
     else:
         loss = model(b.reviews, b.reviews_mask, b.reviews_rating, b.field, b.field_value, b.img, b.img_mask)[0]
     model.zero_grad()
@@ -66,7 +81,8 @@ def _check(gold, loss, grads, oracle_grads=None, tol_vec=5e-2, tol_norm=1e-2, to
     assert not bad, "%d tensors out of tolerance, worst: %s" % (len(bad), sorted(bad, key=lambda t: -max(t[1], t[2]))[:8])
 
 
-@pytest.mark.parametrize("name", ["small_yelp", "small_yelp_gates_open", "small_amazon", "small_text"])
+@pytest.mark.parametrize("name", ["small_yelp", "small_yelp_gates_open", "small_amazon", "small_text",
+                                  "small_img", "small_table_yelp", "small_table_amazon"])
 def test_step_matches_reference_small(name):
     from oracle import mmsum_oracle as OR
     gold = load_golden(name)
@@ -109,6 +125,100 @@ def test_step_matches_oracle_at_72_sequences():
     loss, grads, _ = _run_cuda_step(gold)
     assert all(n in grads for n in names)
     _check(gold, loss, grads, ograds)
+
+
+def _oracle_gold(cfg, sd, batch, label_smoothing=0.1):
+    """Reference values for a case too large for a committed golden: the fp32 oracle on the GPU, one leave-one-out pass of
+    activations alive at a time (the oracle itself is pinned to the reference by tests/test_oracle_golden.py)."""
+    from oracle import mmsum_oracle as OR
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    oloss, ograds, _ = OR.step_loss_and_grads(sd, cfg, batch, label_smoothing, dtype=torch.float32, device="cuda", low_memory=True)
+    names = [n for n in ograds if not n.endswith("final_logits_bias")]
+    gold = dict(cfg=cfg, sd=sd, batch=batch, loss=float(oloss), names=names,
+                norms={n: ograds[n].double().norm().item() for n in names})
+    return gold, ograds
+
+
+def _step_then_oracle(cfg, sd, batch):
+    gold0 = dict(cfg=cfg, sd=sd, batch=batch)
+    loss, grads, model = _run_cuda_step(gold0)
+    grads = {n: g.cpu() for n, g in grads.items()}
+    del model
+    torch.cuda.empty_cache()
+    gold, ograds = _oracle_gold(cfg, sd, batch)
+    ograds = {n: g.cpu() for n, g in ograds.items()}
+    torch.cuda.empty_cache()
+    assert all(n in grads for n in gold["names"])
+    _check(gold, loss, grads, ograds)
+
+
+def test_step_benchmark_config_b16_full_bart_large():
+    """THE benchmarked configuration (BASELINE configs[1], bench.py): 16 businesses x 9 reviews (144 sequences), 12 + 12
+    layers, 100 valid tokens per 128-token frame, 47 table fields, 10 x 196 image keys — CUDA step vs the fp32 oracle."""
+    from multimodalsum_b200.synth import ModelConfig, make_batch, make_state_dict
+    cfg = ModelConfig(dataset="yelp", dropout=0.0)
+    sd = make_state_dict(cfg, seed=0, perturb=True, gates_open=True)
+    batch = make_batch(cfg, 16, seed=1234, fixed_len=100, n_valid_imgs=10)
+    _step_then_oracle(cfg, sd, batch)
+
+
+def test_step_amazon_full_width_b8():
+    """BASELINE configs[3] shape at full width and depth: 8 products, 133-row table tile, 1 image, 70 valid tokens."""
+    from multimodalsum_b200.synth import ModelConfig, make_batch, make_state_dict
+    cfg = ModelConfig(dataset="amazon", dropout=0.0)
+    sd = make_state_dict(cfg, seed=2, perturb=True, gates_open=True)
+    batch = make_batch(cfg, 8, seed=77, fixed_len=70, n_valid_imgs=1)
+    _step_then_oracle(cfg, sd, batch)
+
+
+def test_stock_torch_optimizer_updates_the_bf16_compute_copy():
+    """INTEGRATION.md §1 path: the reference's stock optimizer flow (torch / transformers AdamW + clip_grad_norm_) writes
+    the fp32 masters through the Parameters; the next forward must see the update (bf16 compute copy re-cast)."""
+    gold = load_golden("small_yelp")
+    _, _, model = _run_cuda_step(gold)
+    eng = model.engine
+    b = gold["batch"].to("cuda")
+    args = (b.reviews, b.reviews_mask, b.reviews_rating, b.field, b.field_value, b.img, b.img_mask)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=0.01)
+    losses = []
+    for _ in range(3):
+        loss = model(*args)[0]
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        losses.append(loss.item())
+    assert losses[1] < losses[0] - 1e-3 and losses[2] < losses[1] - 1e-3, losses
+    model(*args)
+    assert torch.equal(eng.W16, eng.W32.to(torch.bfloat16))
+    # load_state_dict after the first forward is honoured as well
+    model.load_state_dict(gold["sd"], strict=False)
+    l0 = model(*args)[0].item()
+    assert abs(l0 - gold["loss"]) <= 1e-2 * abs(gold["loss"])
+
+
+def test_backward_of_a_stale_step_raises():
+    gold = load_golden("small_yelp")
+    _, _, model = _run_cuda_step(gold)
+    b = gold["batch"].to("cuda")
+    args = (b.reviews, b.reviews_mask, b.reviews_rating, b.field, b.field_value, b.img, b.img_mask)
+    l1 = model(*args)[0]
+    model(*args)
+    with pytest.raises(RuntimeError):
+        l1.backward()
+
+
+def test_step_accepts_non_canonical_input_dtypes():
+    """int32 ids, a sliced (non-contiguous) mask, an int64 image mask: converted at the module boundary, same loss."""
+    gold = load_golden("small_yelp")
+    loss, _, model = _run_cuda_step(gold)
+    b = gold["batch"].to("cuda")
+    wide = torch.zeros(b.reviews_mask.shape[0], b.reviews_mask.shape[1], 2 * b.reviews_mask.shape[2], dtype=torch.int64, device="cuda")
+    wide[:, :, ::2] = b.reviews_mask
+    l2 = model(b.reviews.to(torch.int32), wide[:, :, ::2], b.reviews_rating.double(), b.field.to(torch.int32),
+               [v.to(torch.int32) for v in b.field_value], b.img, b.img_mask.to(torch.int64))[0]
+    assert abs(l2.item() - loss) <= 1e-6 * abs(loss)
 
 
 def test_step_full_text_only_config1():
