@@ -103,10 +103,11 @@ int mmsum_embed_ln_bwd(const void* dout, const void* dout2 /* optional addend */
  * (LayerNorm factory :972-980, eps 1e-5).  Dropout masks are a pure function of (seed, stream_id, element). */
 int mmsum_add_ln_fwd(const void* res, const void* y, const float* gamma, const float* beta, void* out, float* mean,
                      float* rstd, int32_t rows, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
-/* backward: upstream = d1 (+ d2 if not NULL); dres = dz, dy = dz * mask (may alias dres when p_drop == 0); dgamma/dbeta += */
+/* backward: upstream = d1 (+ d2 if not NULL); dres = dz, dy = dz * mask (may alias dres when p_drop == 0); dgamma/dbeta +=;
+ * dbias (optional, fp32 [d_model]) += column sums of dy = the bias gradient of the Linear that produced y (out_proj / fc2) */
 int mmsum_add_ln_bwd(const void* d1, const void* d2, const void* res, const void* y, const float* gamma, const float* mean,
-                     const float* rstd, void* dres, void* dy, float* dgamma, float* dbeta, int32_t rows, int32_t d_model,
-                     float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+                     const float* rstd, void* dres, void* dy, float* dgamma, float* dbeta, float* dbias, int32_t rows,
+                     int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
 
 /* out[n] += sum_r x[r,n]  (bias gradients) */
 int mmsum_colsum(const void* x, int64_t ld, int32_t rows, int32_t N, float* out, void* stream);
@@ -120,9 +121,12 @@ int mmsum_gate_bwd_o(const void* dy, const void* ab, const void* dca, const void
                      int32_t d_model, void* stream);
 
 /* label-smoothed CE over bf16 logits [rows, ld] (src/utils.py:32-38; eps < 0: plain CE, src/text_pretrain.py:97);
- * loss_rows[r] per-row loss (computed before the row is overwritten); loss_out (optional) = loss_scale * sum(loss_rows); write_grad: logits := dlogits * gscale */
+ * loss_rows[r] per-row loss (computed before the row is overwritten); loss_out (optional) = loss_scale * sum(loss_rows);
+ * write_grad: logits := dlogits * gscale.  lse_rows (optional fp32 [rows]): written by the loss pass (write_grad = 0), read by
+ * the gradient pass (write_grad = 1), which then reads the logits once instead of twice and leaves loss_rows untouched */
 int mmsum_ce_fwd_bwd(void* logits, int64_t ld, int32_t rows, int32_t V, const int32_t* target, float eps, float gscale,
-                     const float* gscale_dev /* optional device scalar multiplied into gscale */, float* loss_rows, float* loss_out, float loss_scale, int32_t write_grad, void* stream);
+                     const float* gscale_dev /* optional device scalar multiplied into gscale */, float* loss_rows, float* loss_out,
+                     float loss_scale, float* lse_rows, int32_t write_grad, void* stream);
 
 /* integer bookkeeping of one step: decoder inputs (shift_tokens_right :225-246), pad masks (:249-254), rating_diff
  * (src/multimodal_train.py:154-156), memory key/entity validity, 1/#valid entities, modality presence */

@@ -258,6 +258,7 @@ class StepEngine:
         self.ldv = (cfg.vocab_size + 7) // 8 * 8
         w["logits"] = bf(T, self.ldv)
         w["loss_rows"] = f32(T)
+        w["lse_rows"] = f32(T)
         w["loss"] = f32(1)
         # backward scratch
         w["pool"] = _Pool(5, (T, D), dev)
@@ -453,7 +454,8 @@ class StepEngine:
         # ---- LM head + loss (:2281, src/utils.py:32-38); mean over all 9·B·128 rows == mean of the 9 pass means
         logits = w["logits"]
         g(x, self.w16(bm + "shared.weight"), logits[:, :V], bias=self.w32_flb(), raster_m_fast=True)
-        ops.ce_fwd_bwd(logits, V, w["labels"], label_smoothing, 0.0, None, w["loss_rows"], w["loss"], 1.0 / T, False)
+        ops.ce_fwd_bwd(logits, V, w["labels"], label_smoothing, 0.0, None, w["loss_rows"], w["loss"], 1.0 / T, False,
+                       lse_rows=w["lse_rows"])
         return w["loss"]
 
     def w32_flb(self):
@@ -516,11 +518,11 @@ class StepEngine:
         pool, pd = w["pool"], self.pd
         dres = pool.get()
         df = pool.get() if pd > 0 else dres
+        # the fc2 bias gradient (column sums of df) is accumulated by the same kernel
         ops.add_ln_bwd(d1, d2, xin, a["f"], self.w32(lp + "final_layer_norm.weight"), a[mk], a[rk], dres, df,
                        self.g32(lp + "final_layer_norm.weight"), self.g32(lp + "final_layer_norm.bias"), pd, self.seed,
-                       self._sid(kind, l))
+                       self._sid(kind, l), dbias=self.g32(lp + "fc2.bias"))
         pool.put(d1, d2)
-        self._bias_grad(df, self.g32(lp + "fc2.bias"))
         self._wgrad(df, a["a"], lp + "fc2.weight")
         dH = w["dH"]
         ops.gemm(df, self.w16(lp + "fc2.weight"), dH, b_t=True, act=ops.ACT_GELU, aux=a["h"], aux_mode=ops.AUX_MUL_DACT)
@@ -540,9 +542,8 @@ class StepEngine:
         do = pool.get() if pd > 0 else dres
         ops.add_ln_bwd(d1, d2, a["x"], a["o"], self.w32(lp + "self_attn_layer_norm.weight"), a["m1"], a["r1"], dres, do,
                        self.g32(lp + "self_attn_layer_norm.weight"), self.g32(lp + "self_attn_layer_norm.bias"), pd, self.seed,
-                       self._sid(kind, l))
+                       self._sid(kind, l), dbias=self.g32(s + "out_proj.bias"))
         pool.put(d1, d2)
-        self._bias_grad(do, self.g32(s + "out_proj.bias"))
         self._wgrad(do, a["ctx"], s + "out_proj.weight")
         dctx = pool.get()
         ops.gemm(do, self.w16(s + "out_proj.weight"), dctx, b_t=True)
@@ -576,7 +577,8 @@ class StepEngine:
 
         # ---- loss + LM head
         logits = w["logits"]
-        ops.ce_fwd_bwd(logits, V, w["labels"], self.label_smoothing, 1.0 / T, grad_out, w["loss_rows"], None, 0.0, True)
+        ops.ce_fwd_bwd(logits, V, w["labels"], self.label_smoothing, 1.0 / T, grad_out, w["loss_rows"], None, 0.0, True,
+                       lse_rows=w["lse_rows"])
         dl = logits[:, :V]
         d1 = pool.get()
         g(dl, self.w16(bm + "shared.weight"), d1, b_t=True)
@@ -597,7 +599,7 @@ class StepEngine:
             dyc = pool.get() if pd > 0 else dres
             ops.add_ln_bwd(d1, d2, a["x1"], yc, self.w32(lp + "encoder_attn_layer_norm.weight"), a["m2"], a["r2"], dres, dyc,
                            self.g32(lp + "encoder_attn_layer_norm.weight"), self.g32(lp + "encoder_attn_layer_norm.bias"),
-                           pd, seed, self._sid(5, l))
+                           pd, seed, self._sid(5, l), dbias=None if gates else self.g32(c + "out_proj.bias"))
             pool.put(d1, d2)
             nm = a["A3"].shape[0]
             if gates:
@@ -614,8 +616,9 @@ class StepEngine:
                 ops.gate_bwd_o(dyc, a["AB"], w["dca"], w["dcb"], dO3, T, D)
                 dO3f = dO3.view(nm * T, D)
             else:
-                dO3f = dyc
-            self._bias_grad(dO3f, self.g32(c + "out_proj.bias"))
+                dO3f = dyc                          # single memory: out_proj.bias gradient came out of add_ln_bwd
+            if gates:
+                self._bias_grad(dO3f, self.g32(c + "out_proj.bias"))
             self._wgrad(dO3f, a["A3"].view(nm * T, D), c + "out_proj.weight")
             dA3 = w["dA3"]
             g(dO3f, self.w16(c + "out_proj.weight"), dA3.view(nm * T, D), b_t=True)

@@ -161,16 +161,17 @@ def _add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid):
                                       C.c_float(p_drop), C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_add_ln_fwd")
 
 
-def add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid):
+def add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid, dbias=None):
+    """dbias (optional fp32 [d]) += column sums of dy: the bias gradient of the Linear that produced y."""
     rows, d = res.shape
     n_mats = 3 + (1 if d2 is not None else 0) + 1 + (1 if dy.data_ptr() != dres.data_ptr() else 0)   # d1 (+d2), res, y in; dres (+dy) out
-    _timed("add_ln_bwd", float(n_mats) * rows * d * 2, lambda: _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid))
+    _timed("add_ln_bwd", float(n_mats) * rows * d * 2, lambda: _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid, dbias))
 
 
-def _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid):
+def _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid, dbias):
     rows, d = res.shape
     check(_lib.lib().mmsum_add_ln_bwd(_ptr(d1), _ptr(d2), _ptr(res), _ptr(y), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres),
-                                      _ptr(dy), _ptr(dgamma), _ptr(dbeta), rows, d, C.c_float(p_drop), C.c_uint64(seed),
+                                      _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), rows, d, C.c_float(p_drop), C.c_uint64(seed),
                                       C.c_uint32(sid), _stream()), "mmsum_add_ln_bwd")
 
 
@@ -208,17 +209,18 @@ def _gate_bwd_o(dy, ab, dca, dcb, do3, rows, d):
     check(_lib.lib().mmsum_gate_bwd_o(_ptr(dy), _ptr(ab), _ptr(dca), _ptr(dcb), _ptr(do3), rows, d, _stream()), "mmsum_gate_bwd_o")
 
 
-def ce_fwd_bwd(logits, V, target, eps, gscale, gscale_dev, loss_rows, loss_out, loss_scale, write_grad):
+def ce_fwd_bwd(logits, V, target, eps, gscale, gscale_dev, loss_rows, loss_out, loss_scale, write_grad, lse_rows=None):
+    """lse_rows (optional fp32 [rows]): written by the loss pass, read by the gradient pass (one read of the logits, not two)."""
     rows = logits.shape[0]
     _timed("ce_bwd" if write_grad else "ce_fwd", (2.0 if write_grad else 1.0) * rows * V * 2,
-           lambda: _ce_fwd_bwd(logits, V, target, eps, gscale, gscale_dev, loss_rows, loss_out, loss_scale, write_grad))
+           lambda: _ce_fwd_bwd(logits, V, target, eps, gscale, gscale_dev, loss_rows, loss_out, loss_scale, write_grad, lse_rows))
 
 
-def _ce_fwd_bwd(logits, V, target, eps, gscale, gscale_dev, loss_rows, loss_out, loss_scale, write_grad):
+def _ce_fwd_bwd(logits, V, target, eps, gscale, gscale_dev, loss_rows, loss_out, loss_scale, write_grad, lse_rows):
     rows = logits.shape[0]
     check(_lib.lib().mmsum_ce_fwd_bwd(_ptr(logits), C.c_int64(logits.stride(0)), rows, V, _ptr(target),
                                       C.c_float(-1.0 if eps is None else eps), C.c_float(gscale), _ptr(gscale_dev),
-                                      _ptr(loss_rows), _ptr(loss_out), C.c_float(loss_scale), int(write_grad), _stream()),
+                                      _ptr(loss_rows), _ptr(loss_out), C.c_float(loss_scale), _ptr(lse_rows), int(write_grad), _stream()),
           "mmsum_ce_fwd_bwd", 2 if loss_out is not None else 1)
 
 

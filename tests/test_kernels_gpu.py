@@ -97,10 +97,13 @@ def test_add_ln_fwd_bwd():
     dres = torch.empty_like(res)
     dg = torch.zeros(D, device=_dev())
     db = torch.zeros(D, device=_dev())
-    ops.add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dres, dg, db, 0.0, 1, 1)
+    dbias = torch.zeros(D, device=_dev())
+    ops.add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dres, dg, db, 0.0, 1, 1, dbias=dbias)
     _close(dres, rf.grad, 1e-2, "ln dres")
     _close(dg, gf.grad, 2e-3, "ln dgamma")
     _close(db, bf.grad, 2e-3, "ln dbeta")
+    # folded bias gradient of the producing Linear = column sums of dy exactly as stored (bf16)
+    _close(dbias, dres.float().sum(0), 1e-4, "ln dbias")
 
 
 def test_add_ln_dropout_mask_consistency():
@@ -201,14 +204,19 @@ def test_ce_fwd_bwd(eps, V):
     ref_rows.mean().backward()
     loss_rows = torch.empty(rows, device=_dev())
     loss = torch.empty(1, device=_dev())
-    ops.ce_fwd_bwd(logits, V, tgt, eps, 0.0, None, loss_rows, loss, 1.0 / rows, False)
+    lse = torch.empty(rows, device=_dev())
+    ops.ce_fwd_bwd(logits, V, tgt, eps, 0.0, None, loss_rows, loss, 1.0 / rows, False, lse_rows=lse)
     assert torch.allclose(loss_rows, ref_rows.detach(), rtol=2e-5, atol=2e-5)
     assert abs(loss.item() - ref_rows.mean().item()) < 1e-4
+    assert torch.allclose(lse, torch.logsumexp(lf.detach(), -1), rtol=1e-5, atol=1e-5)
     gs = torch.full((1,), 2.0, device=_dev())
-    ops.ce_fwd_bwd(logits, V, tgt, eps, 1.0 / rows, gs, loss_rows, None, 0.0, True)
+    saved = logits.clone()
+    ops.ce_fwd_bwd(logits, V, tgt, eps, 1.0 / rows, gs, loss_rows, None, 0.0, True)        # statistics recomputed
     got = logits[:, :V].float()
     ref = 2.0 * lf.grad
     assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    ops.ce_fwd_bwd(saved, V, tgt, eps, 1.0 / rows, gs, loss_rows, None, 0.0, True, lse_rows=lse)   # saved log-sum-exp
+    assert torch.equal(saved[:, :V], logits[:, :V])
 
 
 # ------------------------------------------------------------------ attention
