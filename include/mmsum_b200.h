@@ -84,6 +84,20 @@ typedef struct MmsumAttnArgs {
 int mmsum_attn_fwd(const MmsumAttnArgs* args, void* stream);
 int mmsum_attn_bwd(const MmsumAttnArgs* args, void* stream); /* dQ/DELTA pass, then dK/dV pass */
 
+/* ---- decode-step attention (beam search, BASELINE config 5) ------------------------------------------
+ * Replaces the cached branch of SelfAttention.get_head_output (src/transformer/modeling_multimodalsum.py:774-815, 889-920)
+ * and the cache re-gathering of _reorder_cache (:3103-3115, :663-669).
+ * mmsum_attn_decode_cross: MmsumAttnArgs with ONE query row per hypothesis: Q [n_qseq, ldq], O per modality [n_qseq, ldo] at
+ *   mods[m].o_off; R = hypotheses (beams, <= 8) per business, adjacent; they attend to the same un-expanded per-business memory
+ *   rows of KV (K|V read once per business and head).  inv_n [n_qseq, n_mod]; LSE / DELTA / dQ / dKV unused; loo must be 0.
+ * mmsum_attn_decode_self: qkv [n_hyp, ldqkv] = q | k | v of the newest position (heads of 64); appends k, v to
+ *   cache [n_hyp, 128, 2*H*64] at row (n, pos) and sets hist[n][pos] = n; attends to positions 0..pos where position j < pos of
+ *   hypothesis n is read from cache row (hist[n][j], j).  Re-ranking the beams is `hist = hist[beam_idx]` (int32 [n_hyp, 128]);
+ *   the caches never move.  pos_dev: device scalar.  out [n_hyp, ldo] bf16. */
+int mmsum_attn_decode_cross(const MmsumAttnArgs* args, void* stream);
+int mmsum_attn_decode_self(const void* qkv, int64_t ldqkv, void* cache, int32_t* hist, const int32_t* pos_dev, void* out,
+                           int64_t ldo, int32_t n_hyp, int32_t H, float scale, void* stream);
+
 /* ---- HBM-bound row kernels (d_model = 1024) ----------------------------------------------------- */
 /* fp32 -> bf16 (weight arena cast, feature cast) */
 int mmsum_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
@@ -93,6 +107,11 @@ int mmsum_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int mmsum_embed_ln_fwd(const int32_t* ids, const float* E, const float* P, const float* rating_diff, const float* remb,
                        const float* gamma, const float* beta, void* out, float* mean, float* rstd, int32_t rows,
                        int32_t S, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+/* decode step (eval, one token per hypothesis): as above with S = 1, every row at decoder position pos_dev[0] (device
+ * memory, so the launch can be replayed from a CUDA graph); the cached branch of BartDecoder.forward :583-597, :964-965 */
+int mmsum_embed_ln_decode(const int32_t* ids, const float* E, const float* P, const float* rating_diff, const float* remb,
+                          const float* gamma, const float* beta, void* out, float* mean, float* rstd, int32_t rows,
+                          int32_t d_model, const int32_t* pos_dev, void* stream);
 /* backward: scatter-add into dE (pad id skipped, nn.Embedding(padding_idx=1) :1001), dP, dremb, dgamma, dbeta (all +=) */
 int mmsum_embed_ln_bwd(const void* dout, const void* dout2 /* optional addend */, const int32_t* ids, const float* E, const float* P, const float* rating_diff,
                        const float* remb, const float* gamma, const float* mean, const float* rstd, float* dE, float* dP,

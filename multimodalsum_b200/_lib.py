@@ -76,12 +76,13 @@ def lib():
     return _lib
 
 
-# every symbol include/mmsum_b200.h declares (tests/test_abi.py cross-checks this list against the header)
+# every symbol include/mmsum_b200.h declares (tests/test_host_logic.py cross-checks this list against the header)
 EXPORTS = [
     "mmsum_gemm_bf16", "mmsum_attn_fwd", "mmsum_attn_bwd", "mmsum_cast_f32_bf16",
     "mmsum_embed_ln_fwd", "mmsum_embed_ln_bwd", "mmsum_add_ln_fwd", "mmsum_add_ln_bwd", "mmsum_colsum",
     "mmsum_gate_fwd", "mmsum_gate_bwd_u", "mmsum_gate_bwd_o", "mmsum_ce_fwd_bwd", "mmsum_prep_step",
     "mmsum_table_fwd", "mmsum_table_bits_bwd", "mmsum_grad_sumsq", "mmsum_adamw_step",
+    "mmsum_embed_ln_decode", "mmsum_attn_decode_cross", "mmsum_attn_decode_self",
 ]
 
 

@@ -92,13 +92,15 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int* __restrict
                                                            const float* __restrict__ remb, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, bf16* __restrict__ out,
                                                            float* __restrict__ mean_o, float* __restrict__ rstd_o,
-                                                           int rows, int S, DropCfg dc) {
+                                                           int rows, int S, DropCfg dc, const int* __restrict__ pos_dev) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   float z[VPL], p[VPL];
   load_row_f32(E + (long long)ids[row] * D, lane, z);
-  load_row_f32(P + (long long)((row % S) + 2) * D, lane, p);
+  // decode steps: every row sits at the same position, read from device memory (the launch is replayed from a CUDA graph)
+  const int pos = (pos_dev != nullptr) ? pos_dev[0] : (row % S);
+  load_row_f32(P + (long long)(pos + 2) * D, lane, p);
 #pragma unroll
   for (int i = 0; i < VPL; ++i) z[i] += p[i];
   if (rating_diff != nullptr) {
@@ -869,7 +871,18 @@ extern "C" int mmsum_embed_ln_fwd(const int32_t* ids, const float* E, const floa
   if (d_model != D || rows <= 0 || S <= 0 || !ids || !E || !P || !out) return MMSUM_ERR_INVALID;
   embed_ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(ids, E, P, rating_diff, remb, gamma, beta,
                                                                    reinterpret_cast<bf16*>(out), mean, rstd, rows, S,
-                                                                   make_drop(p_drop, seed, stream_id));
+                                                                   make_drop(p_drop, seed, stream_id), nullptr);
+  MMSUM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int mmsum_embed_ln_decode(const int32_t* ids, const float* E, const float* P, const float* rating_diff,
+                                     const float* remb, const float* gamma, const float* beta, void* out, float* mean,
+                                     float* rstd, int32_t rows, int32_t d_model, const int32_t* pos_dev, void* stream) {
+  if (d_model != D || rows <= 0 || !ids || !E || !P || !out || !pos_dev) return MMSUM_ERR_INVALID;
+  embed_ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(ids, E, P, rating_diff, remb, gamma, beta,
+                                                                   reinterpret_cast<bf16*>(out), mean, rstd, rows, 1,
+                                                                   make_drop(0.f, 0, 0), pos_dev);
   MMSUM_CHECK_LAUNCH();
   return 0;
 }

@@ -9,9 +9,11 @@ Design (B200-first, not the reference's):
     UN-EXPANDED per business — all beams of a business attend to the same memory (the reference expands every memory
     num_beams times and re-gathers the expanded K/V cache with index_select at every token, :2598-2627, :3004-3010);
   * decoding is incremental (`Generator.step_logits`): only the newest token of every hypothesis runs through the
-    decoder; per-layer self-attention K|V caches receive the new row straight from the K|V GEMM and are permuted by
-    `beam_idx` after each step.  `last_logits` recomputes the whole prefix in a 128-position causal frame with the
-    training kernels and is kept as the cross-check of the cached path;
+    decoder, on decode-shaped attention kernels (csrc/decode_sm100.cu: one query row per hypothesis, K|V streamed once
+    per business and head for all beams; self-attention caches that never move, addressed through a slot table that the
+    beam re-ranking permutes), and the ~200 launches of a step are replayed from one CUDA graph.  `last_logits`
+    recomputes the whole prefix in a 128-position causal frame with the training kernels and is kept as the cross-check
+    of the cached path;
   * the beam bookkeeping is VECTORISED OVER BUSINESSES AND RUNS ON THE DEVICE (`BeamSearch`): n-gram blocking, the
     top-2k candidate merge, the per-business hypothesis pools and the early-stopping flags are tensor ops without a
     single `.item()` / `.tolist()` in the token loop (the reference loops over batch x beam in Python with host syncs
@@ -236,85 +238,58 @@ class Generator:
         return INF.lm_head(self.eng, x[:, input_ids.shape[1] - 1])      # strided [N, D] view: the GEMM reads it in place
 
     # ------------------------------------------------------------------ one cached decode step (all beams)
-    @torch.no_grad()
-    def step_logits(self, st, input_ids, rating_diff):
-        """Incremental decoding (`_use_saved_state` / cached branch of `get_head_output`, modeling_multimodalsum.py:774-815,
-        889-920): only the newest token of every hypothesis goes through the decoder.  Self-attention K|V of all earlier
-        positions live in per-layer caches [N, 128, 2D] (the new row is written in place by the K|V GEMM), cross-attention
-        K|V are the static per-business projections.  Call `reorder_cache(st, beam_idx)` after every beam re-ranking
-        (`_reorder_cache`, :3103-3115).  input_ids [N, cur_len] -> fp32 logits [N, V] of the last position.
-
-        The attention kernels work on 128-row query tiles: the self-attention query of hypothesis n sits in row t of its own
-        causal frame (rows != t are ignored), and the `beams` cross-attention queries of a business share one frame (rows
-        0..beams-1) because they attend to the same memory."""
+    def _decode_ws(self, st, N, dev):
         eng, cfg, mem = self.eng, self.eng.cfg, st.mem
-        dev = input_ids.device
-        D, H, V, FF = cfg.d_model, cfg.heads, cfg.vocab_size, cfg.ffn_dim
-        N, cur = input_ids.shape
+        D, H, V, FF, L = cfg.d_model, cfg.heads, cfg.vocab_size, cfg.ffn_dim, cfg.decoder_layers
         S = INF.FRAME
-        if cur > S:
-            raise ValueError("decoder frames up to 128 tokens")
-        if st.beams > S:
-            raise ValueError("at most 128 beams")
-        t = cur - 1
-        beams, B = st.beams, mem.B
         nm = len(mem.mods)
-        if st.cws is None:
-            bf = lambda *s: torch.empty(s, device=dev, dtype=torch.bfloat16)
-            zbf = lambda *s: torch.zeros(s, device=dev, dtype=torch.bfloat16)
-            f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
-            L = cfg.decoder_layers
-            st.cws = dict(x=bf(N, D), x1=bf(N, D), x2=bf(N, D), nxt=bf(N, D), o=bf(N, D), qc=bf(N, D), a=bf(N, FF), f=bf(N, D),
-                          qf=zbf(N * S, D), ctx=zbf(N * S, D),                 # self-attention query / context frames
-                          kvs=[zbf(N, S, 2 * D) for _ in range(L)],            # self-attention K|V caches (finite everywhere)
-                          kvs_alt=[zbf(N, S, 2 * D) for _ in range(L)],
-                          qcf=zbf(B * S, D), A3f=zbf(nm, B * S, D),            # cross-attention frames: one per business
-                          A3=bf(nm, N, D), O3=bf(nm, N, D), U=bf(2, N, D), AB=bf(2, N, D), yc=bf(N, D),
-                          mean=f32(N), rstd=f32(N), lse=f32(N, H, 1, S), lse_c=f32(B, H, mem.Et, S),
-                          ids=torch.empty(N, device=dev, dtype=torch.int32), pos=-1)
-        w = st.cws
-        if t != w["pos"] + 1:
-            raise ValueError("step_logits must be called with consecutive lengths (got position %d after %d)" % (t, w["pos"]))
-        w["pos"] = t
+        bf = lambda *s: torch.empty(s, device=dev, dtype=torch.bfloat16)
+        f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        w = dict(x=bf(N, D), x1=bf(N, D), x2=bf(N, D), nxt=bf(N, D), o=bf(N, D), qc=bf(N, D), a=bf(N, FF), f=bf(N, D),
+                 qkv=bf(N, 3 * D), ctx=bf(N, D),
+                 kvs=[torch.zeros(N, S, 2 * D, device=dev, dtype=torch.bfloat16) for _ in range(L)],   # self K|V caches: never move
+                 hist=torch.zeros(N, S, device=dev, dtype=torch.int32),                                 # slot table (see decode_sm100.cu)
+                 hist_alt=torch.zeros(N, S, device=dev, dtype=torch.int32),
+                 A3=bf(nm, N, D), O3=bf(nm, N, D), U=bf(2, N, D), AB=bf(2, N, D), yc=bf(N, D),
+                 mean=f32(N), rstd=f32(N), ids=torch.zeros(N, device=dev, dtype=torch.int32),
+                 pos_dev=torch.zeros(1, device=dev, dtype=torch.int32), rd=torch.zeros(N, device=dev),
+                 logits=f32(N, (V + 3) // 4 * 4)[:, :V],                                               # 16-byte row pitch for TMA
+                 inv_n=mem.inv_n.repeat_interleave(st.beams, dim=0).contiguous(), pos=-1, graph=None)
+        return w
+
+    def _decode_launches(self, st):
+        """Every kernel of one decode step; all per-step state (token ids, position, slot table) is read from device memory."""
+        eng, cfg, mem, w = self.eng, self.eng.cfg, st.mem, st.cws
+        D, H = cfg.d_model, cfg.heads
+        N = w["x"].shape[0]
+        nm = len(mem.mods)
         g = ops.gemm
         bm = "bart_model.model."
         pre = bm + "decoder."
-        w["ids"].copy_(input_ids[:, t])
-        x = w["x"]
-        # position t for every row: the kernel adds P[(row % S) + 2], so pass S = 1 and the table shifted by t rows
-        ops.embed_ln_fwd(w["ids"], eng.w32(bm + "shared.weight"), eng.w32(pre + "embed_positions.weight")[t:],
-                         rating_diff.reshape(-1).float().contiguous(), eng.w32(pre + "rating_embeddings"),
-                         eng.w32(pre + "layernorm_embedding.weight"), eng.w32(pre + "layernorm_embedding.bias"), x, w["mean"], w["rstd"],
-                         N, 1, 0.0, 0, 0)
-        Tf = B * S
-        mods = INF.cross_mods(mem, Tf, D)
-        q_row = w["qf"].view(N, S, D)[:, t]          # strided [N, D] views: the GEMMs read / write them in place
-        ctx_row = w["ctx"].view(N, S, D)[:, t]
-        nxt = w["nxt"]
+        scale = cfg.head_dim ** -0.5
+        x, nxt = w["x"], w["nxt"]
+        ops.embed_ln_decode(w["ids"], eng.w32(bm + "shared.weight"), eng.w32(pre + "embed_positions.weight"), w["rd"],
+                            eng.w32(pre + "rating_embeddings"), eng.w32(pre + "layernorm_embedding.weight"),
+                            eng.w32(pre + "layernorm_embedding.bias"), x, w["mean"], w["rstd"], N, w["pos_dev"])
+        cross = ops.attn_args(Q=w["qc"], ldq=D, q_col=0, KV=mem.kv[0], ldkv=2 * D, k_col=0, v_col=D, O=w["A3"], ldo=D, LSE=None,
+                              key_valid=mem.mem_valid, ent_valid=mem.ent_valid, inv_n=w["inv_n"], n_qseq=N, H=H, R=st.beams,
+                              causal=0, E_total=mem.Et, scale=scale, mods=INF.cross_mods(mem, N, D))
         for l in range(cfg.decoder_layers):
             lp = pre + "layers.%d." % l
             s_, c = lp + "self_attn.", lp + "encoder_attn."
-            wqkv, bqkv = eng.w16(s_ + "q_proj.weight", s_ + "v_proj.weight"), eng.w32(s_ + "q_proj.bias", s_ + "v_proj.bias")
-            cache = w["kvs"][l]
-            g(x, wqkv[:D], q_row, bias=bqkv[:D])
-            g(x, wqkv[D:], cache[:, t], bias=bqkv[D:])                      # appends this position's K|V to the cache
-            ops.attn_fwd(ops.attn_args(Q=w["qf"], ldq=D, q_col=0, KV=cache.view(N * S, 2 * D), ldkv=2 * D, k_col=0, v_col=D, O=w["ctx"],
-                                       ldo=D, LSE=w["lse"], key_valid=None, ent_valid=None, inv_n=None, n_qseq=N, H=H, R=1, causal=1,
-                                       E_total=1, scale=cfg.head_dim ** -0.5, mods=[(0, 0, 1, S, 0, 0)]))
-            g(ctx_row, eng.w16(s_ + "out_proj.weight"), w["o"], bias=eng.w32(s_ + "out_proj.bias"))
+            g(x, eng.w16(s_ + "q_proj.weight", s_ + "v_proj.weight"), w["qkv"], bias=eng.w32(s_ + "q_proj.bias", s_ + "v_proj.bias"))
+            ops.attn_decode_self(w["qkv"], w["kvs"][l], w["hist"], w["pos_dev"], w["ctx"], H, scale)
+            g(w["ctx"], eng.w16(s_ + "out_proj.weight"), w["o"], bias=eng.w32(s_ + "out_proj.bias"))
             ops.add_ln_fwd(x, w["o"], eng.w32(lp + "self_attn_layer_norm.weight"), eng.w32(lp + "self_attn_layer_norm.bias"), w["x1"],
                            w["mean"], w["rstd"], 0.0, 0, 0)
             g(w["x1"], eng.w16(c + "q_proj.weight"), w["qc"], bias=eng.w32(c + "q_proj.bias"))
-            w["qcf"].view(B, S, D)[:, :beams].copy_(w["qc"].view(B, beams, D))
-            ops.attn_fwd(ops.attn_args(Q=w["qcf"], ldq=D, q_col=0, KV=mem.kv[l], ldkv=2 * D, k_col=0, v_col=D, O=w["A3f"], ldo=D,
-                                       LSE=w["lse_c"], key_valid=mem.mem_valid, ent_valid=mem.ent_valid, inv_n=mem.inv_n, n_qseq=B,
-                                       H=H, R=1, causal=0, E_total=mem.Et, scale=cfg.head_dim ** -0.5, mods=mods))
-            w["A3"].view(nm, B, beams, D).copy_(w["A3f"].view(nm, B, S, D)[:, :, :beams])
+            cross.KV = mem.kv[l].data_ptr()
+            ops.attn_decode_cross(cross)
             g(w["A3"].view(nm * N, D), eng.w16(c + "out_proj.weight"), w["O3"].view(nm * N, D), bias=eng.w32(c + "out_proj.bias"))
             if nm == 3:
                 ops.gemm_cat(w["O3"][0], w["O3"][1], eng.w16(c + "alpha_proj.weight"), w["U"][0], bias=eng.w32(c + "alpha_proj.bias"))
                 ops.gemm_cat(w["O3"][0], w["O3"][2], eng.w16(c + "beta_proj.weight"), w["U"][1], bias=eng.w32(c + "beta_proj.bias"))
-                ops.gate_fwd(w["O3"], w["U"], mem.pres, w["yc"], w["AB"], N, beams, D)
+                ops.gate_fwd(w["O3"], w["U"], mem.pres, w["yc"], w["AB"], N, st.beams, D)
                 yc = w["yc"]
             else:
                 yc = w["O3"][0]
@@ -325,19 +300,66 @@ class Generator:
             ops.add_ln_fwd(w["x2"], w["f"], eng.w32(lp + "final_layer_norm.weight"), eng.w32(lp + "final_layer_norm.bias"), nxt,
                            w["mean"], w["rstd"], 0.0, 0, 0)
             x, nxt = nxt, x
-        w["x"], w["nxt"] = x, nxt
-        return INF.lm_head(eng, x)
+        g(x, eng.w16(bm + "shared.weight"), w["logits"], bias=eng.w32_flb())
+
+    @torch.no_grad()
+    def step_logits(self, st, input_ids, rating_diff):
+        """Incremental decoding (`_use_saved_state` / cached branch of `get_head_output`, modeling_multimodalsum.py:774-815,
+        889-920): only the newest token of every hypothesis goes through the decoder.  input_ids [N, cur_len] -> fp32 logits
+        [N, V] of the last position (a buffer that the next call overwrites).  Call `reorder_cache(st, beam_idx)` after every
+        beam re-ranking (`_reorder_cache`, :3103-3115).
+
+        Decode-shaped kernels (csrc/decode_sm100.cu): the self-attention K|V of earlier positions stay where they were written
+        and are found through a slot table that `reorder_cache` permutes (128 KB instead of 12 layers of caches); the
+        cross-attention reads the un-expanded per-business K|V once per business and head for all of its beams.  The ~200
+        launches of a step take their per-step inputs (token ids, position, slot table) from device memory, so from the second
+        token on the whole step is replayed from ONE CUDA graph (MMSUM_DECODE_GRAPH=0 launches it kernel by kernel)."""
+        import os
+        dev = input_ids.device
+        N, cur = input_ids.shape
+        if cur > INF.FRAME:
+            raise ValueError("decoder frames up to 128 tokens")
+        if st.beams > 8:
+            raise ValueError("the decode attention kernel handles up to 8 beams per business")
+        t = cur - 1
+        if st.cws is None:
+            st.cws = self._decode_ws(st, N, dev)
+        w = st.cws
+        if t != w["pos"] + 1:
+            raise ValueError("step_logits must be called with consecutive lengths (got position %d after %d)" % (t, w["pos"]))
+        w["pos"] = t
+        w["ids"].copy_(input_ids[:, t])
+        w["rd"].copy_(rating_diff.reshape(-1))
+        if w["graph"] is None:
+            self._decode_launches(st)                 # first token: plain launches (also sets the one-time function attributes)
+            w["graph"] = False
+            if os.environ.get("MMSUM_DECODE_GRAPH", "1") != "0":
+                try:
+                    graph = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(graph):
+                        self._decode_launches(st)     # re-records the same step; replays read the then-current device state
+                    w["graph"] = graph
+                except Exception as e:                # noqa: BLE001 — same kernels, launched one by one
+                    import warnings
+                    warnings.warn("CUDA-graph capture of the decode step failed (%s); launching kernel by kernel" % (e,))
+                    w["graph"] = False
+        elif w["graph"] is False:
+            self._decode_launches(st)
+        else:
+            w["graph"].replay()
+        w["pos_dev"].add_(1)
+        return w["logits"]
 
     @torch.no_grad()
     def reorder_cache(self, st, beam_idx):
-        """`_reorder_cache` (:3103-3115): hypothesis i continues hypothesis beam_idx[i]; only the self-attention caches move
-        (the cross-attention K|V are per business and beam_idx never crosses businesses)."""
+        """`_reorder_cache` (:3103-3115): hypothesis i continues hypothesis beam_idx[i].  Only the slot table moves: the
+        self-attention caches stay in place and the cross-attention K|V are per business (beam_idx never crosses businesses)."""
         w = st.cws
         if w is None:
             return
-        for l in range(len(w["kvs"])):
-            torch.index_select(w["kvs"][l], 0, beam_idx, out=w["kvs_alt"][l])
-            w["kvs"][l], w["kvs_alt"][l] = w["kvs_alt"][l], w["kvs"][l]
+        torch.index_select(w["hist"], 0, beam_idx, out=w["hist_alt"])
+        w["hist"].copy_(w["hist_alt"])
 
     # ------------------------------------------------------------------ public entry points
     @torch.no_grad()

@@ -259,6 +259,23 @@ def attn_bwd(a):
     _timed(kind, 2.5 * attn_flops(a), lambda: check(_lib.lib().mmsum_attn_bwd(C.byref(a), _stream()), "mmsum_attn_bwd", 2))
 
 
+def attn_decode_cross(a):
+    """One query row per hypothesis against the un-expanded per-business memory (see include/mmsum_b200.h)."""
+    check(_lib.lib().mmsum_attn_decode_cross(C.byref(a), _stream()), "mmsum_attn_decode_cross")
+
+
+def attn_decode_self(qkv, cache, hist, pos_dev, out, H, scale):
+    n = qkv.shape[0]
+    check(_lib.lib().mmsum_attn_decode_self(_ptr(qkv), C.c_int64(qkv.stride(0)), _ptr(cache), _ptr(hist), _ptr(pos_dev), _ptr(out),
+                                            C.c_int64(out.stride(0)), n, H, C.c_float(scale), _stream()), "mmsum_attn_decode_self")
+
+
+def embed_ln_decode(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, rows, pos_dev):
+    check(_lib.lib().mmsum_embed_ln_decode(_ptr(ids), _ptr(E), _ptr(P), _ptr(rating_diff), _ptr(remb), _ptr(gamma), _ptr(beta),
+                                           _ptr(out), _ptr(mean), _ptr(rstd), rows, E.shape[1], _ptr(pos_dev), _stream()),
+          "mmsum_embed_ln_decode")
+
+
 def prep_step(reviews, reviews_mask, rating, table_valid, img_mask, **kw):
     a = _lib.PrepArgs()
     for k, v in kw.items():

@@ -342,6 +342,86 @@ def test_multi_entity_cross_attention_fwd_bwd():
     _close(dkv[:, D:], kvf.grad[:, D:], 2e-2, "cross dv")
 
 
+# ------------------------------------------------------------------ decode-step attention
+@pytest.mark.parametrize("beams,Sk_text", [(4, 158), (1, 128), (8, 208)])
+def test_decode_cross_attention(beams, Sk_text):
+    """One query row per hypothesis, the beams of a business share its un-expanded memory: text entities with ragged valid
+    lengths, a partially masked table, images with null entities and a business without images."""
+    ops = _ops()
+    from oracle import mmsum_oracle as OR
+    torch.manual_seed(11)
+    B, R, H, hd, F_, n_img, ik = 3, 4, 16, 64, 47, 3, 196
+    N = B * beams
+    Tt = B * R * Sk_text
+    Tm = Tt + B * F_ + B * n_img * ik
+    Et = R + 1 + n_img
+    dev = _dev()
+    q = torch.randn(N, D, device=dev).to(torch.bfloat16)
+    kv = torch.randn(Tm, 2 * D, device=dev).to(torch.bfloat16)
+    lens = torch.randint(30, Sk_text + 1, (B, R), device=dev)
+    tvalid = torch.arange(Sk_text, device=dev)[None, None, :] < lens[:, :, None]
+    tvalid[0, 1] = False                                                             # a null review
+    tabvalid = torch.rand(B, 1, F_, device=dev) > 0.3
+    tabvalid[:, :, 0] = True
+    imask = torch.tensor([[True, False, True], [False, False, False], [True, True, True]], device=dev)
+    ivalid = imask[:, :, None].expand(B, n_img, ik)
+    mem_valid = torch.cat([tvalid.reshape(-1), tabvalid.reshape(-1), ivalid.reshape(-1)]).to(torch.uint8)
+    ent_valid = torch.cat([tvalid.any(-1), tabvalid.any(-1), imask], dim=1).to(torch.uint8).contiguous()
+    cnt = torch.stack([tvalid.any(-1).sum(1), tabvalid.any(-1).sum(1), imask.sum(1)], dim=1).float()
+    inv_n = torch.where(cnt > 0, 1.0 / cnt.clamp(min=1), torch.zeros_like(cnt)).repeat_interleave(beams, dim=0).contiguous()
+    A3 = torch.full((3, N, D), 7.0, device=dev, dtype=torch.bfloat16)               # must be fully overwritten
+    mods = [(0, 0, R, Sk_text, 0, 0), (Tt, N * D, 1, F_, 0, R), (Tt + B * F_, 2 * N * D, n_img, ik, 0, R + 1)]
+    a = ops.attn_args(Q=q, ldq=D, q_col=0, KV=kv, ldkv=2 * D, k_col=0, v_col=D, O=A3, ldo=D, LSE=None, key_valid=mem_valid,
+                      ent_valid=ent_valid, inv_n=inv_n, n_qseq=N, H=H, R=beams, causal=0, E_total=Et, scale=hd ** -0.5, mods=mods)
+    ops.attn_decode_cross(a)
+    kvf, qf = kv.float(), q.float().view(B, beams, H, hd).transpose(1, 2) * hd ** -0.5   # [B,H,beams,hd]
+
+    def ref_modality(k, v, valid):
+        E, Sk = k.shape[1], k.shape[2]
+        kk = k.view(B, E, Sk, H, hd).permute(0, 1, 3, 2, 4)
+        vv = v.view(B, E, Sk, H, hd).permute(0, 1, 3, 2, 4)
+        wgt = (qf[:, None] @ kk.transpose(-1, -2)).masked_fill(~valid[:, :, None, None, :], OR.NEG_CROSS)
+        o = (torch.softmax(wgt, -1) @ vv).masked_fill((~valid.any(-1))[:, :, None, None, None], 0.0)
+        n = valid.any(-1).sum(1).clamp(min=1).float()
+        return (o.sum(1) / n[:, None, None, None]).transpose(1, 2).reshape(N, D)
+
+    ref = torch.stack([
+        ref_modality(kvf[:Tt, :D].view(B, R, Sk_text, D), kvf[:Tt, D:].view(B, R, Sk_text, D), tvalid),
+        ref_modality(kvf[Tt:Tt + B * F_, :D].view(B, 1, F_, D), kvf[Tt:Tt + B * F_, D:].view(B, 1, F_, D), tabvalid),
+        ref_modality(kvf[Tt + B * F_:, :D].view(B, n_img, ik, D), kvf[Tt + B * F_:, D:].view(B, n_img, ik, D), ivalid)])
+    _close(A3, ref, 1.5e-2, "decode cross")
+    assert A3[2].view(B, beams, D)[1].abs().max().item() == 0.0                     # business without images -> exactly 0
+
+
+def test_decode_self_attention_with_slot_table():
+    """Token-by-token causal self-attention against caches that never move: after every step the hypotheses are re-ranked
+    (children may share a parent) by permuting the slot table only."""
+    ops = _ops()
+    torch.manual_seed(12)
+    N, H, hd, S = 12, 16, 64, 128
+    dev = _dev()
+    cache = torch.zeros(N, S, 2 * D, device=dev, dtype=torch.bfloat16)
+    hist = torch.zeros(N, S, device=dev, dtype=torch.int32)
+    pos = torch.zeros(1, device=dev, dtype=torch.int32)
+    out = torch.empty(N, D, device=dev, dtype=torch.bfloat16)
+    Kh = torch.zeros(N, S, D, device=dev)     # reference: per-hypothesis history, physically re-gathered as the reference does
+    Vh = torch.zeros(N, S, D, device=dev)
+    g = torch.Generator().manual_seed(3)
+    for t in range(40):
+        qkv = torch.randn(N, 3 * D, device=dev).to(torch.bfloat16)
+        ops.attn_decode_self(qkv, cache, hist, pos, out, H, hd ** -0.5)
+        Kh[:, t], Vh[:, t] = qkv[:, D:2 * D].float(), qkv[:, 2 * D:].float()
+        qf = qkv[:, :D].float().view(N, H, 1, hd) * hd ** -0.5
+        kk = Kh[:, :t + 1].view(N, t + 1, H, hd).transpose(1, 2)
+        vv = Vh[:, :t + 1].view(N, t + 1, H, hd).transpose(1, 2)
+        ref = (torch.softmax(qf @ kk.transpose(-1, -2), -1) @ vv).transpose(1, 2).reshape(N, D)
+        _close(out, ref, 1.5e-2, "decode self t=%d" % t)
+        src = ((torch.arange(N) // 4) * 4 + torch.randint(0, 4, (N,), generator=g)).to(dev)
+        hist.copy_(hist.index_select(0, src))
+        Kh, Vh = Kh[src], Vh[src]
+        pos += 1
+
+
 # ------------------------------------------------------------------ gates
 def test_gate_fwd_bwd():
     ops = _ops()
