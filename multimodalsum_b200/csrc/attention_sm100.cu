@@ -1506,12 +1506,8 @@ extern "C" int mmsum_attn_fwd(const MmsumAttnArgs* a, void* stream_v) {
   AttnMaps mp;
   if (int rc = build_maps(a, &mp, false)) return rc;
   const int smem = (int)sizeof(FwdSmem) + 1024;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  static std::atomic<unsigned long long> attr{0};
+  if (int rc = ensure_dyn_smem(attn_fwd_tc_kernel, smem, attr)) return rc;
   // self-attention shape (one modality, one entity per sequence, no leave-one-out): heads become the CTA's items
   const int head_mode = (a->n_mod == 1 && a->mods[0].E == 1 && !a->mods[0].loo && a->H <= kMaxEnt && a->n_qseq >= 64) ? 1 : 0;
   static const bool use_v1 = (getenv("MMSUM_ATTN_FWD_V1") != nullptr);   // A/B switch: the first forward kernel
@@ -1519,12 +1515,8 @@ extern "C" int mmsum_attn_fwd(const MmsumAttnArgs* a, void* stream_v) {
     MMSUM_LAUNCH_PDL(attn_fwd_tc_kernel, head_mode ? a->n_qseq : a->n_qseq * a->H, kAttnThreads, smem, stream, mp, *a, head_mode);
   } else {
     const int smem2 = (int)sizeof(Fwd2Smem) + 1024;
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-      if (e != cudaSuccess) return (int)e;
-      attr2 = true;
-    }
+    static std::atomic<unsigned long long> attr2{0};
+    if (int rc = ensure_dyn_smem(attn_fwd_tc2_kernel, smem2, attr2)) return rc;
     MMSUM_LAUNCH_PDL(attn_fwd_tc2_kernel, head_mode ? a->n_qseq : a->n_qseq * a->H, kF2Threads, smem2, stream, mp, *a, head_mode);
   }
   MMSUM_CHECK_LAUNCH();
@@ -1557,14 +1549,9 @@ extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
     if (int rc = make_tmap(&do64, a->O, 0, (uint64_t)a->ldo, orows, (uint64_t)a->ldo * 2, 64, QH)) return rc;
   }
   const int smem_q = (int)sizeof(BwdQSmem) + 1024, smem_kv = (int)sizeof(BwdKVSmem) + 1024;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  static std::atomic<unsigned long long> attr_q{0}, attr_kv{0};
+  if (int rc = ensure_dyn_smem(attn_bwd_dq_tc_kernel, smem_q, attr_q)) return rc;
+  if (int rc = ensure_dyn_smem(attn_bwd_dkv_tc_kernel, smem_kv, attr_kv)) return rc;
   // profiling knob (tools/gpu_bench_attn.py): MMSUM_ATTN_BWD_PART=1 launches only dQ/DELTA, =2 only dK/dV
   static const int part = [] { const char* e = getenv("MMSUM_ATTN_BWD_PART"); return e ? atoi(e) : 0; }();
   if (part != 2) {

@@ -9,6 +9,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #define MMSUM_OK 0
 #define MMSUM_ERR_INVALID (-1)
 #define MMSUM_ERR_DRIVER (-2)
@@ -33,6 +35,20 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     cudaError_t _le = launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__);  \
     if (_le != cudaSuccess) return (int)_le;                                                             \
   } while (0)
+
+// One-time opt-in to > 48 KB of dynamic shared memory, tracked PER DEVICE (bit d of `done`) and safe to race: the attribute
+// call is idempotent, the flag is only an optimisation.
+template <typename K>
+static inline int ensure_dyn_smem(K kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return MMSUM_ERR_DRIVER;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return (int)e;
+  done.fetch_or(bit, std::memory_order_release);
+  return 0;
+}
 
 #define MMSUM_CHECK_LAUNCH()                         \
   do {                                               \

@@ -374,12 +374,8 @@ extern "C" int mmsum_attn_decode_cross(const MmsumAttnArgs* a, void* stream_v) {
     if (int rc = make_tmap(&mp.kv[m], a->KV, 0, (uint64_t)a->ldkv, rows, (uint64_t)a->ldkv * 2, 64, (uint32_t)((md.Sk + 15) & ~15))) return rc;
   }
   const int smem = (int)sizeof(DecSmem) + 1024;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_decode_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  static std::atomic<unsigned long long> attr{0};
+  if (int rc = ensure_dyn_smem(attn_decode_cross_kernel, smem, attr)) return rc;
   attn_decode_cross_kernel<<<n_biz * a->H, kDecWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream_v)>>>(mp, *a);
   MMSUM_CHECK_LAUNCH();
   return 0;

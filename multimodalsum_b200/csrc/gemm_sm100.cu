@@ -388,14 +388,14 @@ int make_tmap(CUtensorMap* out, const void* ptr, int dtype /*0 bf16, 1 f32*/, ui
 }
 
 static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
-    else n = kNumSMs;
-  }
-  return n;
+  static std::atomic<int> cached[64];       // per device; 0 = not queried yet
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMs;
+  const int c = cached[dev & 63].load(std::memory_order_relaxed);
+  if (c > 0) return c;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMs;
+  cached[dev & 63].store(v, std::memory_order_relaxed);
+  return v;
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
@@ -403,13 +403,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
                        const CUtensorMap& taux,
                        const GemmKernelArgs& ka, int grid, cudaStream_t stream) {
   using L = GemmSmem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_set{0};     // one per template instantiation
+  if (int rc = ensure_dyn_smem(gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>, L::kTotal, attr_set)) return rc;
   cudaError_t le = launch_pdl(gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>, dim3(grid), dim3(kGemmThreads), (size_t)L::kTotal, stream,
                               ta, ta2, tb, td, taux, ka);
   if (le != cudaSuccess) return (int)le;
@@ -428,7 +423,12 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
   if (!a->out_f32 && a->accumulate) return MMSUM_ERR_INVALID;
   if (a->aux_mode != 0 && (!a->aux || (a->N % 8) != 0 || (a->ld_aux % 8) != 0)) return MMSUM_ERR_INVALID;
   int bn = a->block_n;
-  if (bn == 0) bn = (a->N > 128) ? 256 : 128;
+  if (bn == 0) {
+    bn = (a->N > 128) ? 256 : 128;
+    // skinny problems (decode steps: M = a few hundred rows): 128-wide tiles double the number of CTAs that stream the
+    // weights and halve each CTA's K loop when 256-wide tiles would leave most of the SMs idle
+    if (bn == 256 && a->aux_mode == 0 && (long long)((a->M + BM - 1) / BM) * ((a->N + 255) / 256) * 2 <= num_sms()) bn = 128;
+  }
   if (bn != 128 && bn != 256) return MMSUM_ERR_INVALID;
   if (a->aux_mode != 0) {   // fused-activation epilogues exist for row-major A and 256-wide tiles
     if (a->aux_mode < 0 || a->aux_mode > 2 || a->a_mn_major) return MMSUM_ERR_INVALID;

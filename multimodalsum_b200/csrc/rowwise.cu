@@ -920,12 +920,8 @@ extern "C" int mmsum_add_ln_bwd(const void* d1, const void* d2, const void* res,
                                 float* dbias, int32_t rows, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream) {
   if (d_model != D || rows <= 0 || !d1 || !res || !y || !dres || !dy) return MMSUM_ERR_INVALID;
   if (p_drop > 0.f && dres == dy) return MMSUM_ERR_INVALID;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(add_ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * VPL * 32 * 4);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  static std::atomic<unsigned long long> attr{0};
+  if (int rc = ensure_dyn_smem(add_ln_bwd_kernel, 4 * 3 * VPL * 32 * 4, attr)) return rc;
   MMSUM_LAUNCH_PDL(add_ln_bwd_kernel, nblocks(rows, 4 * 4, 148 * 3), 128, 4 * 3 * VPL * 32 * 4, STREAM(stream), 
       reinterpret_cast<const bf16*>(d1), reinterpret_cast<const bf16*>(d2), reinterpret_cast<const bf16*>(res),
       reinterpret_cast<const bf16*>(y), gamma, mean, rstd, reinterpret_cast<bf16*>(dres), reinterpret_cast<bf16*>(dy),

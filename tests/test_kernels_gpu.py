@@ -51,6 +51,23 @@ def test_gemm_variants(M, N, K, a_t, b_t, f32, acc):
     _close(Dm, Af @ Bf.t() + base, 1.5e-2 if not f32 else 2e-3, "gemm")
 
 
+@pytest.mark.parametrize("M,N,K,block_n", [(256, 1024, 4096, 128), (256, 3072, 1024, 128), (256, 1024, 1024, 0), (768, 1024, 1024, 0),
+                                            (256, 50265, 1024, 0)])
+def test_gemm_skinny_decode_shapes(M, N, K, block_n):
+    """Decode-step GEMMs (256 hypotheses): 128-wide tiles over several N tiles, bias, strided fp32 output for the LM head."""
+    ops = _ops()
+    torch.manual_seed(4)
+    A = torch.randn(M, K, device=_dev()).to(torch.bfloat16)
+    B = (torch.randn(N, K, device=_dev()) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device=_dev())
+    if N == 50265:
+        out = torch.empty(M, (N + 3) // 4 * 4, device=_dev())[:, :N]
+        ops.gemm(A, B, out, bias=bias)
+    else:
+        out = ops.gemm(A, B, bias=bias, block_n=block_n)
+    _close(out, A.float() @ B.float().t() + bias, 1e-2, "skinny gemm")
+
+
 def test_gemm_epilogues_and_cat():
     ops = _ops()
     torch.manual_seed(1)
