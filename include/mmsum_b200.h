@@ -122,11 +122,10 @@ int mmsum_embed_ln_bwd(const void* dout, const void* dout2 /* optional addend */
  * (LayerNorm factory :972-980, eps 1e-5).  Dropout masks are a pure function of (seed, stream_id, element). */
 int mmsum_add_ln_fwd(const void* res, const void* y, const float* gamma, const float* beta, void* out, float* mean,
                      float* rstd, int32_t rows, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
-/* backward: upstream = d1 (+ d2 if not NULL); dres = dz, dy = dz * mask (may alias dres when p_drop == 0); dgamma/dbeta +=;
- * dbias (optional, fp32 [d_model]) += column sums of dy = the bias gradient of the Linear that produced y (out_proj / fc2) */
+/* backward: upstream = d1 (+ d2 if not NULL); dres = dz, dy = dz * mask (may alias dres when p_drop == 0); dgamma/dbeta += */
 int mmsum_add_ln_bwd(const void* d1, const void* d2, const void* res, const void* y, const float* gamma, const float* mean,
-                     const float* rstd, void* dres, void* dy, float* dgamma, float* dbeta, float* dbias, int32_t rows,
-                     int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+                     const float* rstd, void* dres, void* dy, float* dgamma, float* dbeta, int32_t rows, int32_t d_model,
+                     float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
 
 /* out[n] += sum_r x[r,n]  (bias gradients) */
 int mmsum_colsum(const void* x, int64_t ld, int32_t rows, int32_t N, float* out, void* stream);

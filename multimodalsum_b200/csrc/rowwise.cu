@@ -281,9 +281,10 @@ __global__ void __launch_bounds__(256, 2) add_ln_fwd_kernel(const bf16* __restri
 }
 
 // backward: dout = d1 (+ d2); z recomputed from res, y.  dres = dz (bf16), dy = dz * dropmask (bf16; same buffer
-// allowed when dropout is off), dgamma/dbeta accumulated with atomics (fp32).  dbias (optional) += column sums of dy as
-// stored (bf16-rounded): the bias gradient of the Linear that produced y (out_proj / fc2), which otherwise costs one more
-// pass over dy in a separate kernel.
+// allowed when dropout is off), dgamma/dbeta accumulated with atomics (fp32).
+// (Measured and dropped in round 2: also accumulating the column sums of dy here — the bias gradient of the Linear that
+//  produced y — to save the separate colsum launch: a third 16 KB smem accumulator per warp and the extra spills at the
+//  168-register cap made this kernel 27 % slower, 55 -> 70 us, more than the side-stream colsum ever cost.)
 // dgamma / dbeta partial sums live in shared memory ([warp][value i][lane]: conflict-free), not in 64 registers, so
 // three 128-thread blocks fit per SM; one atomic per column per block at the end.
 __global__ void __launch_bounds__(128, 3) add_ln_bwd_kernel(const bf16* __restrict__ d1, const bf16* __restrict__ d2,
@@ -291,16 +292,15 @@ __global__ void __launch_bounds__(128, 3) add_ln_bwd_kernel(const bf16* __restri
                                                             const float* __restrict__ gamma, const float* __restrict__ mean_i,
                                                             const float* __restrict__ rstd_i, bf16* __restrict__ dres,
                                                             bf16* __restrict__ dy_out, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, float* __restrict__ dbias, int rows, DropCfg dc) {
+                                                            float* __restrict__ dbeta, int rows, DropCfg dc) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float sacc[];                      // [4 warps][3][VPL][32]
+  extern __shared__ float sacc[];                      // [4 warps][2][VPL][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float* sg = sacc + warp * (3 * VPL * 32);
+  float* sg = sacc + warp * (2 * VPL * 32);
   float* sb = sg + VPL * 32;
-  float* sy = sb + VPL * 32;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) { sg[i * 32 + lane] = 0.f; sb[i * 32 + lane] = 0.f; sy[i * 32 + lane] = 0.f; }
+  for (int i = 0; i < VPL; ++i) { sg[i * 32 + lane] = 0.f; sb[i * 32 + lane] = 0.f; }
   for (int row = blockIdx.x * nw + warp; row < rows; row += gridDim.x * nw) {
     // all 12-16 global loads of the row are issued before the first use (the kernel is latency-bound otherwise)
     uint4 ry[4], rr[4], r1[4], r2[4];
@@ -356,23 +356,16 @@ __global__ void __launch_bounds__(128, 3) add_ln_bwd_kernel(const bf16* __restri
       for (int i = 0; i < VPL; ++i) t[i] = ((keep >> i) & 1u) ? t[i] * dc.scale : 0.f;
       store_row_bf16(dy_out + (long long)row * D, lane, t);
     }
-    if (dbias != nullptr) {
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) sy[i * 32 + lane] += __bfloat162float(__float2bfloat16_rn(t[i]));
-    }
   }
   __syncthreads();
   // column c = (i>>3)*256 + lane*8 + (i&7)  <->  (i, lane)
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     const int j = c >> 8, l = (c & 255) >> 3, k = c & 7;
     const int idx = (j * 8 + k) * 32 + l;
-    float a = 0.f, bsum = 0.f, ysum = 0.f;
-    for (int w = 0; w < nw; ++w) {
-      a += sacc[w * (3 * VPL * 32) + idx]; bsum += sacc[w * (3 * VPL * 32) + VPL * 32 + idx]; ysum += sacc[w * (3 * VPL * 32) + 2 * VPL * 32 + idx];
-    }
+    float a = 0.f, bsum = 0.f;
+    for (int w = 0; w < nw; ++w) { a += sacc[w * (2 * VPL * 32) + idx]; bsum += sacc[w * (2 * VPL * 32) + VPL * 32 + idx]; }
     atomicAdd(dgamma + c, a);
     atomicAdd(dbeta + c, bsum);
-    if (dbias != nullptr) atomicAdd(dbias + c, ysum);
   }
 }
 
@@ -917,15 +910,15 @@ extern "C" int mmsum_add_ln_fwd(const void* res, const void* y, const float* gam
 
 extern "C" int mmsum_add_ln_bwd(const void* d1, const void* d2, const void* res, const void* y, const float* gamma,
                                 const float* mean, const float* rstd, void* dres, void* dy, float* dgamma, float* dbeta,
-                                float* dbias, int32_t rows, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream) {
+                                int32_t rows, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream) {
   if (d_model != D || rows <= 0 || !d1 || !res || !y || !dres || !dy) return MMSUM_ERR_INVALID;
   if (p_drop > 0.f && dres == dy) return MMSUM_ERR_INVALID;
   static std::atomic<unsigned long long> attr{0};
-  if (int rc = ensure_dyn_smem(add_ln_bwd_kernel, 4 * 3 * VPL * 32 * 4, attr)) return rc;
-  MMSUM_LAUNCH_PDL(add_ln_bwd_kernel, nblocks(rows, 4 * 4, 148 * 3), 128, 4 * 3 * VPL * 32 * 4, STREAM(stream), 
+  if (int rc = ensure_dyn_smem(add_ln_bwd_kernel, 4 * 2 * VPL * 32 * 4, attr)) return rc;
+  MMSUM_LAUNCH_PDL(add_ln_bwd_kernel, nblocks(rows, 4 * 4, 148 * 3), 128, 4 * 2 * VPL * 32 * 4, STREAM(stream), 
       reinterpret_cast<const bf16*>(d1), reinterpret_cast<const bf16*>(d2), reinterpret_cast<const bf16*>(res),
       reinterpret_cast<const bf16*>(y), gamma, mean, rstd, reinterpret_cast<bf16*>(dres), reinterpret_cast<bf16*>(dy),
-      dgamma, dbeta, dbias, rows, make_drop(p_drop, seed, stream_id));
+      dgamma, dbeta, rows, make_drop(p_drop, seed, stream_id));
   MMSUM_CHECK_LAUNCH();
   return 0;
 }

@@ -518,11 +518,11 @@ class StepEngine:
         pool, pd = w["pool"], self.pd
         dres = pool.get()
         df = pool.get() if pd > 0 else dres
-        # the fc2 bias gradient (column sums of df) is accumulated by the same kernel
         ops.add_ln_bwd(d1, d2, xin, a["f"], self.w32(lp + "final_layer_norm.weight"), a[mk], a[rk], dres, df,
                        self.g32(lp + "final_layer_norm.weight"), self.g32(lp + "final_layer_norm.bias"), pd, self.seed,
-                       self._sid(kind, l), dbias=self.g32(lp + "fc2.bias"))
+                       self._sid(kind, l))
         pool.put(d1, d2)
+        self._bias_grad(df, self.g32(lp + "fc2.bias"))
         self._wgrad(df, a["a"], lp + "fc2.weight")
         dH = w["dH"]
         ops.gemm(df, self.w16(lp + "fc2.weight"), dH, b_t=True, act=ops.ACT_GELU, aux=a["h"], aux_mode=ops.AUX_MUL_DACT)
@@ -542,8 +542,9 @@ class StepEngine:
         do = pool.get() if pd > 0 else dres
         ops.add_ln_bwd(d1, d2, a["x"], a["o"], self.w32(lp + "self_attn_layer_norm.weight"), a["m1"], a["r1"], dres, do,
                        self.g32(lp + "self_attn_layer_norm.weight"), self.g32(lp + "self_attn_layer_norm.bias"), pd, self.seed,
-                       self._sid(kind, l), dbias=self.g32(s + "out_proj.bias"))
+                       self._sid(kind, l))
         pool.put(d1, d2)
+        self._bias_grad(do, self.g32(s + "out_proj.bias"))
         self._wgrad(do, a["ctx"], s + "out_proj.weight")
         dctx = pool.get()
         ops.gemm(do, self.w16(s + "out_proj.weight"), dctx, b_t=True)
@@ -599,7 +600,7 @@ class StepEngine:
             dyc = pool.get() if pd > 0 else dres
             ops.add_ln_bwd(d1, d2, a["x1"], yc, self.w32(lp + "encoder_attn_layer_norm.weight"), a["m2"], a["r2"], dres, dyc,
                            self.g32(lp + "encoder_attn_layer_norm.weight"), self.g32(lp + "encoder_attn_layer_norm.bias"),
-                           pd, seed, self._sid(5, l), dbias=None if gates else self.g32(c + "out_proj.bias"))
+                           pd, seed, self._sid(5, l))
             pool.put(d1, d2)
             nm = a["A3"].shape[0]
             if gates:
@@ -616,9 +617,8 @@ class StepEngine:
                 ops.gate_bwd_o(dyc, a["AB"], w["dca"], w["dcb"], dO3, T, D)
                 dO3f = dO3.view(nm * T, D)
             else:
-                dO3f = dyc                          # single memory: out_proj.bias gradient came out of add_ln_bwd
-            if gates:
-                self._bias_grad(dO3f, self.g32(c + "out_proj.bias"))
+                dO3f = dyc
+            self._bias_grad(dO3f, self.g32(c + "out_proj.bias"))
             self._wgrad(dO3f, a["A3"].view(nm * T, D), c + "out_proj.weight")
             dA3 = w["dA3"]
             g(dO3f, self.w16(c + "out_proj.weight"), dA3.view(nm * T, D), b_t=True)

@@ -161,17 +161,16 @@ def _add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid):
                                       C.c_float(p_drop), C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_add_ln_fwd")
 
 
-def add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid, dbias=None):
-    """dbias (optional fp32 [d]) += column sums of dy: the bias gradient of the Linear that produced y."""
+def add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid):
     rows, d = res.shape
     n_mats = 3 + (1 if d2 is not None else 0) + 1 + (1 if dy.data_ptr() != dres.data_ptr() else 0)   # d1 (+d2), res, y in; dres (+dy) out
-    _timed("add_ln_bwd", float(n_mats) * rows * d * 2, lambda: _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid, dbias))
+    _timed("add_ln_bwd", float(n_mats) * rows * d * 2, lambda: _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid))
 
 
-def _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid, dbias):
+def _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid):
     rows, d = res.shape
     check(_lib.lib().mmsum_add_ln_bwd(_ptr(d1), _ptr(d2), _ptr(res), _ptr(y), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres),
-                                      _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), rows, d, C.c_float(p_drop), C.c_uint64(seed),
+                                      _ptr(dy), _ptr(dgamma), _ptr(dbeta), rows, d, C.c_float(p_drop), C.c_uint64(seed),
                                       C.c_uint32(sid), _stream()), "mmsum_add_ln_bwd")
 
 

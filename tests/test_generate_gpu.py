@@ -39,17 +39,18 @@ def test_beam_search_exact_ids_on_tie_free_case(use_cache):
 
 
 def test_cached_decode_matches_prefix_recompute():
-    """`step_logits` (one token per hypothesis, caches permuted by `reorder_cache` after every step) against `last_logits`
-    (whole prefix recomputed) on the same token histories, 4 beams per business, including beam permutations inside a
-    business: same bf16 kernels on the same values -> log-probabilities agree to 2e-2 nats and the arg-max is identical
-    wherever the top-2 margin exceeds 0.1 nats."""
+    """`step_logits` (one token per hypothesis on the decode-shaped kernels, slot table permuted by `reorder_cache` after
+    every step) against `last_logits` (whole prefix recomputed in 128-row frames on the training kernels) on the same token
+    histories, 4 beams per business, including beam permutations inside a business: two independent bf16 kernel families,
+    each within 0.05 nats of the fp32 oracle -> log-probabilities agree to 4e-2 nats and the arg-max is identical wherever
+    the top-2 margin exceeds 0.1 nats."""
     gen, cfg, sd, batch, gk, ref = _setup("gen_small_yelp_s128")
     beams = 4
     B = batch.reviews.shape[0]
     N = B * beams
     st_c = gen.encode(batch.reviews, batch.reviews_mask, batch.field, batch.field_value, batch.img, batch.img_mask, beams)
     st_r = gen.encode(batch.reviews, batch.reviews_mask, batch.field, batch.field_value, batch.img, batch.img_mask, beams)
-    _cached_vs_recompute(gen, cfg, st_c, st_r, B, beams, steps=10, tol=2e-2)
+    _cached_vs_recompute(gen, cfg, st_c, st_r, B, beams, steps=10, tol=4e-2)
 
 
 def _cached_vs_recompute(gen, cfg, st_c, st_r, B, beams, steps, tol):
@@ -110,10 +111,17 @@ def test_generation_at_config5_shape():
         checked += int(tie_free.sum())
     assert worst <= 0.05, worst
     assert checked > 0
-    del ofn, p
+    # the incremental decoder (decode-shaped kernels, CUDA-graph replay from the second token) against the oracle as well
+    st_i = gen.encode(*args, beams)
+    for cur in range(1, 7):
+        li = gen.step_logits(st_i, ids[:, :cur].contiguous(), rd)
+        if cur in (1, 3, 6):
+            lo = torch.log_softmax(ofn(ids[:, :cur].contiguous()), -1)
+            assert (torch.log_softmax(li.float(), -1) - lo).abs().max().item() <= 0.05
+    del ofn, p, st_i
     torch.cuda.empty_cache()
     st_c, st_r = gen.encode(*args, beams), st
-    _cached_vs_recompute(gen, cfg, st_c, st_r, B, beams, steps=6, tol=2e-2)
+    _cached_vs_recompute(gen, cfg, st_c, st_r, B, beams, steps=6, tol=4e-2)
     out = gen.generate(*args, num_beams=beams, max_length=12, no_repeat_ngram_size=3, early_stopping=True)
     assert out.shape[0] == B and out.shape[1] <= 12 and (out[:, 0] == cfg.eos_token_id).all() and (out[:, 1] == cfg.bos_token_id).all()
 
