@@ -10,8 +10,10 @@
 //       un-expanded per-business memory (the reference expands the memory per beam and re-gathers it every token,
 //       :2598-2627, :3004-3010), so K_e / V_e of every entity are read ONCE per business and head: TMA (128B swizzle) ->
 //       per-warp smem stage -> ldmatrix -> mma.sync m16n8k16 (bf16, fp32 accumulate; the beams are the M rows, padded to 16)
-//       -> per-entity softmax in registers -> P V -> mean over the valid entities of the modality.  Four warps walk the
-//       entities round-robin; each warp overlaps the next entity's K load with the current entity's softmax / P V.
+//       -> per-entity softmax in registers -> P V -> mean over the valid entities of the modality.  Eight warps pull
+//       entities from a shared counter; a warp owns ONE 26 KB stage that holds the entity's K, then (loaded during the
+//       softmax) its V — eight independent load -> compute chains per SM keep HBM busy where four double-staged warps
+//       moving in lock-step did not (203 -> see profiles/r02_decode_* per layer at the config-5 shape).
 //   attn_decode_self_kernel   one warp per (hypothesis, head): appends the new position's K|V to the cache and attends to
 //       positions 0..t through a per-hypothesis slot table (`hist[n][j]` = cache row that holds position j of hypothesis n),
 //       so re-ranking the beams permutes a 128 KB table instead of copying 12 layers of K|V caches (_reorder_cache,
@@ -29,7 +31,7 @@ int make_tmap(CUtensorMap* out, const void* ptr, int dtype, uint64_t inner, uint
 static constexpr int DHD = 64;
 static constexpr int kDecMaxKeys = 208;                 // keys per entity, multiple of 16
 static constexpr int kDecStage = kDecMaxKeys * 128;     // 26 KB: one entity's K (or V) head slice, 128 B per key row
-static constexpr int kDecWarps = 4;
+static constexpr int kDecWarps = 8;
 static constexpr int kDecMaxEnt = 32;
 static constexpr int kDecMaxBeams = 8;
 static constexpr float kDecLog2e = 1.4426950408889634f;
@@ -38,12 +40,12 @@ struct DecItem { int kv_row0; short nkeys, mod; };
 struct DecMaps { CUtensorMap kv[3]; };
 
 struct DecSmem {
-  uint8_t k[kDecWarps][kDecStage];
-  uint8_t v[kDecWarps][kDecStage];
+  uint8_t kv[kDecWarps][kDecStage];      // per warp: the current entity's K, later overwritten by its V
   float oacc[3][kDecMaxBeams][DHD];
-  uint64_t bar_k[kDecWarps], bar_v[kDecWarps];
+  uint64_t bar[kDecWarps];
   DecItem items[kDecMaxEnt];
   int n_items;
+  int next_item;
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t (&r)[4]) {
@@ -88,11 +90,11 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, ok);
     if (ok) sm.items[__popc(bal & ((1u << lane) - 1u))] = it;
-    if (lane == 0) sm.n_items = __popc(bal);
+    if (lane == 0) { sm.n_items = __popc(bal); sm.next_item = 0; }
   }
   for (int i = threadIdx.x; i < 3 * kDecMaxBeams * DHD; i += blockDim.x) (&sm.oacc[0][0][0])[i] = 0.f;
   if (threadIdx.x == 32) {
-    for (int w = 0; w < kDecWarps; ++w) { mbar_init(&sm.bar_k[w], 1); mbar_init(&sm.bar_v[w], 1); }
+    for (int w = 0; w < kDecWarps; ++w) mbar_init(&sm.bar[w], 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -113,16 +115,11 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
     }
   }
   const float sc = p.scale * kDecLog2e;
-  const uint32_t k_base = smem_u32(sm.k[warp]), v_base = smem_u32(sm.v[warp]);
-  auto load_k = [&](const DecItem& it) {
+  const uint32_t k_base = smem_u32(sm.kv[warp]), v_base = k_base;
+  auto load_tile = [&](const DecItem& it, int col) {
     const int n16 = (it.nkeys + 15) & ~15;
-    mbar_expect_tx(&sm.bar_k[warp], n16 * 128);
-    tma_load_2d(sm.k[warp], &maps.kv[it.mod], &sm.bar_k[warp], p.k_col + h * DHD, it.kv_row0);
-  };
-  auto load_v = [&](const DecItem& it) {
-    const int n16 = (it.nkeys + 15) & ~15;
-    mbar_expect_tx(&sm.bar_v[warp], n16 * 128);
-    tma_load_2d(sm.v[warp], &maps.kv[it.mod], &sm.bar_v[warp], p.v_col + h * DHD, it.kv_row0);
+    mbar_expect_tx(&sm.bar[warp], n16 * 128);
+    tma_load_2d(sm.kv[warp], &maps.kv[it.mod], &sm.bar[warp], col + h * DHD, it.kv_row0);
   };
   float oc[8][4];
 #pragma unroll
@@ -141,9 +138,13 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
   };
 
   uint32_t phase = 0;
-  if (warp < n_items && lane == 0) { load_k(sm.items[warp]); load_v(sm.items[warp]); }
-  for (int i = warp; i < n_items; i += kDecWarps) {
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(&sm.next_item, 1);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= n_items) break;
     const DecItem it = sm.items[i];
+    if (lane == 0) load_tile(it, p.k_col);
     if (it.mod != cur_mod) { flush(cur_mod); cur_mod = it.mod; }
     const int nkeys = it.nkeys;
     const int nblk = (nkeys + 15) >> 4;
@@ -160,7 +161,8 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
 
     // ---- S = Q K^T: 16 (beams, padded) x 16 keys per block; only the first 8 rows are kept
     float s[kDecMaxKeys / 16][2][2];
-    mbar_wait(&sm.bar_k[warp], phase);
+    mbar_wait(&sm.bar[warp], phase);
+    phase ^= 1;
 #pragma unroll
     for (int kb = 0; kb < kDecMaxKeys / 16; ++kb) {
       if (kb < nblk) {
@@ -178,25 +180,30 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
         s[kb][0][0] = d0[0]; s[kb][0][1] = d0[1]; s[kb][1][0] = d1[0]; s[kb][1][1] = d1[1];
       }
     }
-    // K stage is free: the next entity's keys stream in while this one's softmax / P V run
+    // every lane has consumed the keys: the entity's values stream into the same stage while the softmax runs
     __syncwarp();
-    const int nxt = i + kDecWarps;
-    if (nxt < n_items && lane == 0) load_k(sm.items[nxt]);
+    if (lane == 0) load_tile(it, p.v_col);
 
     // ---- softmax over the entity's keys (row = beam g; the 4 lanes of a group share a row)
     float mx = -INFINITY;
+    int n_valid = 0;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) n_valid += __popc(words[c]);
+    const bool all_valid = (n_valid == nkeys);        // warp-uniform: only the 16-key tail block can hold masked keys
 #pragma unroll
     for (int kb = 0; kb < kDecMaxKeys / 16; ++kb) {
       if (kb < nblk) {
+        if (!all_valid || kb == nblk - 1) {
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+          for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int key = kb * 16 + nt * 8 + 2 * t + j;
-            const bool ok = (words[key >> 5] >> (key & 31)) & 1u;
-            s[kb][nt][j] = ok ? s[kb][nt][j] : -INFINITY;
-            mx = fmaxf(mx, s[kb][nt][j]);
-          }
+            for (int j = 0; j < 2; ++j) {
+              const int key = kb * 16 + nt * 8 + 2 * t + j;
+              const bool ok = (words[key >> 5] >> (key & 31)) & 1u;
+              s[kb][nt][j] = ok ? s[kb][nt][j] : -INFINITY;
+            }
+        }
+        mx = fmaxf(mx, fmaxf(fmaxf(s[kb][0][0], s[kb][0][1]), fmaxf(s[kb][1][0], s[kb][1][1])));
       }
     }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -221,7 +228,8 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
     const float wgt = (l > 0.f) ? __fdividef(inv_n, l) : 0.f;
 
     // ---- O += (wgt P) V: P as A fragments straight from the score registers (rows 8..15 are zero)
-    mbar_wait(&sm.bar_v[warp], phase);
+    mbar_wait(&sm.bar[warp], phase);
+    phase ^= 1;
 #pragma unroll
     for (int kb = 0; kb < kDecMaxKeys / 16; ++kb) {
       if (kb < nblk) {
@@ -239,9 +247,7 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
         }
       }
     }
-    __syncwarp();
-    if (nxt < n_items && lane == 0) load_v(sm.items[nxt]);
-    phase ^= 1;
+    __syncwarp();          // the stage may be overwritten by the next entity's keys
   }
   flush(cur_mod);
   __syncthreads();

@@ -254,7 +254,8 @@ class Generator:
                  mean=f32(N), rstd=f32(N), ids=torch.zeros(N, device=dev, dtype=torch.int32),
                  pos_dev=torch.zeros(1, device=dev, dtype=torch.int32), rd=torch.zeros(N, device=dev),
                  logits=f32(N, (V + 3) // 4 * 4)[:, :V],                                               # 16-byte row pitch for TMA
-                 inv_n=mem.inv_n.repeat_interleave(st.beams, dim=0).contiguous(), pos=-1, graph=None)
+                 inv_n=mem.inv_n.repeat_interleave(st.beams, dim=0).contiguous(), pos=-1, graph=None,
+                 side=torch.cuda.Stream(device=dev), ev_fork=torch.cuda.Event(), ev_join=torch.cuda.Event())
         return w
 
     def _decode_launches(self, st):
@@ -287,8 +288,15 @@ class Generator:
             ops.attn_decode_cross(cross)
             g(w["A3"].view(nm * N, D), eng.w16(c + "out_proj.weight"), w["O3"].view(nm * N, D), bias=eng.w32(c + "out_proj.bias"))
             if nm == 3:
+                # the two gate projections are independent 16-CTA GEMMs: they run side by side (a fork / join in the graph)
+                main = torch.cuda.current_stream()
+                w["ev_fork"].record(main)
+                w["side"].wait_event(w["ev_fork"])
+                with torch.cuda.stream(w["side"]):
+                    ops.gemm_cat(w["O3"][0], w["O3"][2], eng.w16(c + "beta_proj.weight"), w["U"][1], bias=eng.w32(c + "beta_proj.bias"))
+                    w["ev_join"].record(w["side"])
                 ops.gemm_cat(w["O3"][0], w["O3"][1], eng.w16(c + "alpha_proj.weight"), w["U"][0], bias=eng.w32(c + "alpha_proj.bias"))
-                ops.gemm_cat(w["O3"][0], w["O3"][2], eng.w16(c + "beta_proj.weight"), w["U"][1], bias=eng.w32(c + "beta_proj.bias"))
+                main.wait_event(w["ev_join"])
                 ops.gate_fwd(w["O3"], w["U"], mem.pres, w["yc"], w["AB"], N, st.beams, D)
                 yc = w["yc"]
             else:
