@@ -52,7 +52,7 @@ class BeamSearch:
         self.cur_len = 1
         bs = torch.zeros(B, k, device=dev)
         bs[:, 1:] = -1e9                                      # only the first beam of a business is live at the start
-        self.beam_scores = bs.view(-1)
+        self.beam_scores = bs.view(-1).contiguous()
         self.done = torch.zeros(B, dtype=torch.bool, device=dev)
         self.pool_score = torch.full((B, k), NEG, device=dev)
         self.pool_tok = torch.full((B, k, max_length), pad, dtype=torch.long, device=dev)
@@ -62,6 +62,16 @@ class BeamSearch:
         self.slot_ids = torch.arange(k, device=dev)
         self.row0 = (self.rows * k)[:, None]
         self.scores_ext = torch.empty(N, V + 1, device=dev)   # column V absorbs the "nothing banned" scatter writes
+        lt = lambda v: torch.tensor([v], dtype=torch.long, device=dev)
+        self.cur_t = lt(1)                                    # current length as a device scalar (see advance)
+        self.bos_t, self.eos_t, self.pad_t, self.v_col = lt(bos), lt(eos), lt(pad), lt(V)
+        self.neg_t = torch.full((1,), NEG, device=dev)
+        n = no_repeat_ngram_size
+        self.ng_ar = torch.arange(max(n - 1, 0), device=dev)
+        self.win_ar = torch.arange(max(max_length - n + 1, 0), device=dev)
+        self.own = self.row0 + self.slot_ids[None, :]
+        self.beam_idx = torch.arange(N, device=dev)
+        self.next_tok = torch.zeros(N, dtype=torch.long, device=dev)
 
     # -- hypothesis pool --------------------------------------------------------------------------------
     def _admit(self, active, score, tokens, length):
@@ -75,7 +85,8 @@ class BeamSearch:
         r = self.rows
         self.pool_score[r, slot] = torch.where(accept, score, self.pool_score[r, slot])
         self.pool_tok[r, slot] = torch.where(accept[:, None], tokens, self.pool_tok[r, slot])
-        self.pool_len[r, slot] = torch.where(accept, torch.full_like(self.pool_len[r, slot], length), self.pool_len[r, slot])
+        length = length if torch.is_tensor(length) else torch.full((1,), length, dtype=torch.long, device=self.dev)
+        self.pool_len[r, slot] = torch.where(accept, length.expand_as(accept), self.pool_len[r, slot])
         self.pool_n += (accept & ~full).long()
 
     def _pool_worst(self):
@@ -85,25 +96,32 @@ class BeamSearch:
     # -- one token --------------------------------------------------------------------------------------
     def advance(self, logits):
         """logits: fp32 [N, V] next-token logits of the current prefixes.  Returns beam_idx [N] (hypothesis i continues
-        hypothesis beam_idx[i]) for the decoder's cache re-ordering."""
-        B, k, V, cur = self.B, self.k, self.V, self.cur_len
-        if cur == 1 or cur == self.max_length - 1:
-            # adjust_logits_during_generation (:3084-3089): only BOS may follow the start token, only EOS may close the frame
-            forced = self.bos if cur == 1 else self.eos
-            keep = logits[:, forced].clone()
-            logits = torch.full_like(logits, NEG)
-            logits[:, forced] = keep
+        hypothesis beam_idx[i]) for the decoder's cache re-ordering.
+
+        Every shape is static and every piece of per-step state (`cur_t`, `ids`, `beam_scores`, `done`, the pools,
+        `beam_idx`, `next_tok`) is a fixed device buffer updated in place: the current length enters as the device scalar
+        `cur_t`, never as a Python value, so the whole update can be recorded once in a CUDA graph (together with the decoder
+        step) and replayed for every token."""
+        B, k, V, L = self.B, self.k, self.V, self.max_length
+        cur = self.cur_t                                                           # long [1]
+        # adjust_logits_during_generation (:3084-3089): only BOS may follow the start token, only EOS may close the frame
+        forced_now = (cur == 1) | (cur == L - 1)
+        forced_tok = torch.where(cur == 1, self.bos_t, self.eos_t).expand(logits.shape[0], 1)
+        forced_logits = torch.full_like(logits, NEG).scatter_(1, forced_tok, logits.gather(1, forced_tok))
+        logits = torch.where(forced_now, forced_logits, logits)
         scores = self.scores_ext
         torch.log_softmax(logits, dim=-1, out=scores[:, :V])
         # postprocess_next_token_scores (generation_utils.py:57-99)
-        if cur < self.min_length:
-            scores[:, self.eos] = NEG
+        if self.min_length > 0:
+            scores[:, self.eos] = torch.where(cur < self.min_length, self.neg_t, scores[:, self.eos])
         n = self.ngram
-        if n > 0 and cur >= n:
-            # calc_banned_ngram_tokens (:848-868): a token is banned when it would complete an n-gram already in the prefix
-            win = self.ids[:, :cur].unfold(1, n, 1)                               # [N, cur-n+1, n]
-            hit = (win[:, :, :n - 1] == self.ids[:, cur - n + 1:cur][:, None, :]).all(dim=-1)
-            scores.scatter_(1, torch.where(hit, win[:, :, n - 1], torch.full_like(win[:, :, n - 1], V)), NEG)
+        if n > 0 and L >= n:
+            # calc_banned_ngram_tokens (:848-868): a token is banned when it would complete an n-gram already in the prefix.
+            # windows over the whole frame; window i is real when it ends inside the prefix (i <= cur - n)
+            win = self.ids.unfold(1, n, 1)                                          # [N, L-n+1, n]
+            sfx = self.ids.gather(1, (cur - n + 1 + self.ng_ar).clamp(min=0)[None, :].expand(self.ids.shape[0], -1))
+            hit = (win[:, :, :n - 1] == sfx[:, None, :]).all(dim=-1) & (self.win_ar <= cur - n)[None, :]
+            scores.scatter_(1, torch.where(hit, win[:, :, n - 1], self.v_col), NEG)
         cand = (scores[:, :V] + self.beam_scores[:, None]).view(B, k * V)
         cs, ci = torch.topk(cand, 2 * k, dim=1, largest=True, sorted=True)
         tok = ci % V
@@ -111,7 +129,7 @@ class BeamSearch:
         is_eos = tok == self.eos
         # finished candidates among the first k ranks enter the pool of their business (:2949-2957)
         live = ~self.done
-        norm = float(cur) ** self.length_penalty
+        norm = cur.to(cs.dtype) ** self.length_penalty
         for r in range(k):
             self._admit(is_eos[:, r] & live, cs[:, r] / norm, self.ids[src[:, r]], cur)
         # the first k unfinished candidates, in rank order, are the next beams (:2958-2966)
@@ -123,17 +141,18 @@ class BeamSearch:
         else:
             finished = (self.pool_n >= k) & (self._pool_worst() >= cs[:, 0] / norm)
         # businesses that were already done keep dummy beams (score 0, pad token); their rows are never read again
-        own = self.row0 + self.slot_ids[None, :]
         nscore = torch.where(live[:, None], nscore, torch.zeros_like(nscore))
-        ntok = torch.where(live[:, None], ntok, torch.full_like(ntok, self.pad))
-        nsrc = torch.where(live[:, None], nsrc, own)
-        self.done = self.done | finished
-        beam_idx = nsrc.reshape(-1)
-        self.beam_scores = nscore.reshape(-1)
-        self.ids = self.ids[beam_idx]
-        self.ids[:, cur] = ntok.reshape(-1)
-        self.cur_len = cur + 1
-        return beam_idx
+        ntok = torch.where(live[:, None], ntok, self.pad_t)
+        nsrc = torch.where(live[:, None], nsrc, self.own)
+        self.done.logical_or_(finished)
+        self.beam_idx.copy_(nsrc.reshape(-1))
+        self.next_tok.copy_(ntok.reshape(-1))
+        self.beam_scores.copy_(nscore.reshape(-1))
+        self.ids.copy_(self.ids[self.beam_idx])
+        self.ids.scatter_(1, cur.expand(self.ids.shape[0], 1), self.next_tok[:, None])
+        cur.add_(1)
+        self.cur_len += 1
+        return self.beam_idx
 
     # -- result -----------------------------------------------------------------------------------------
     def finalize(self):
@@ -333,6 +352,8 @@ class Generator:
         if st.cws is None:
             st.cws = self._decode_ws(st, N, dev)
         w = st.cws
+        if w.get("fused"):
+            raise RuntimeError("this DecodeState is driven by the fused token loop; build a fresh one with encode()/prepare()")
         if t != w["pos"] + 1:
             raise ValueError("step_logits must be called with consecutive lengths (got position %d after %d)" % (t, w["pos"]))
         w["pos"] = t
@@ -369,6 +390,70 @@ class Generator:
         torch.index_select(w["hist"], 0, beam_idx, out=w["hist_alt"])
         w["hist"].copy_(w["hist_alt"])
 
+    # ------------------------------------------------------------------ fused token loop (one CUDA graph per token)
+    @torch.no_grad()
+    def _fused_beam_search(self, st, rd, poll_every=8, **kw):
+        """Decoder step + beam update + cache re-ranking of one token recorded ONCE and replayed: the host issues a single
+        graph launch per token (the reference runs ~47 k eager ops and several host syncs per token, :2857-3010).  The first
+        token runs kernel by kernel (one-time function attributes, allocator warm-up), the capture follows it."""
+        import os
+        cfg, mem = self.eng.cfg, st.mem
+        dev = mem.MEM.device
+        B, k = mem.B, st.beams
+        N = B * k
+        bs = BeamSearch(B, cfg.vocab_size, dev, k, kw["max_length"], kw["min_length"], kw["length_penalty"], kw["no_repeat_ngram_size"],
+                        kw["early_stopping"], cfg.pad_token_id, cfg.bos_token_id, cfg.eos_token_id)
+        st.cws = w = self._decode_ws(st, N, dev)
+        w["fused"] = True
+        w["rd"].copy_(rd.reshape(-1))
+        w["ids"].copy_(bs.ids[:, 0])
+
+        def token_step():
+            self._decode_launches(st)
+            beam_idx = bs.advance(w["logits"])
+            torch.index_select(w["hist"], 0, beam_idx, out=w["hist_alt"])       # _reorder_cache: only the slot table moves
+            w["hist"].copy_(w["hist_alt"])
+            w["ids"].copy_(bs.next_tok)
+            w["pos_dev"].add_(1)
+
+        max_length = kw["max_length"]
+        if max_length <= 1:
+            return bs.finalize()
+        token_step()
+        graph = None
+        if bs.cur_len < max_length and os.environ.get("MMSUM_DECODE_GRAPH", "1") != "0":
+            try:
+                host_len = bs.cur_len
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    token_step()
+                bs.cur_len = host_len             # the capture ran the Python bookkeeping once without executing anything
+                graph = g
+            except Exception as e:                # noqa: BLE001 — same kernels, launched one by one
+                import warnings
+                warnings.warn("CUDA-graph capture of the token step failed (%s); launching kernel by kernel" % (e,))
+                bs.cur_len = host_len
+        self.last_used_graph = graph is not None
+        flag = torch.zeros(1, dtype=torch.bool, pin_memory=True)
+        ev = None
+        while bs.cur_len < max_length:
+            if graph is not None:
+                graph.replay()
+                bs.cur_len += 1
+            else:
+                token_step()
+            if ev is not None and ev.query():
+                if bool(flag[0]):
+                    break
+                ev = None
+            if ev is None and bs.cur_len % poll_every == 0:
+                flag.copy_(bs.done.all().reshape(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+        self.last_decode_steps = bs.cur_len - 1
+        return bs.finalize()
+
     # ------------------------------------------------------------------ public entry points
     @torch.no_grad()
     def generate_from_memory(self, mem, rating_diff=None, num_beams=4, max_length=20, min_length=0, length_penalty=1.0,
@@ -379,10 +464,12 @@ class Generator:
         B, dev = mem.B, mem.MEM.device
         rd = torch.zeros(B, device=dev) if rating_diff is None else rating_diff.reshape(B).float()
         rd = rd.repeat_interleave(num_beams).contiguous()
+        if num_beams > 8:
+            use_cache = False                     # the decode attention kernel holds up to 8 beams per business
         if use_cache:
-            logits_fn, reorder_fn = (lambda ids: self.step_logits(st, ids, rd)), (lambda beam_idx: self.reorder_cache(st, beam_idx))
-        else:
-            logits_fn, reorder_fn = (lambda ids: self.last_logits(st, ids, rd)), None
+            return self._fused_beam_search(st, rd, max_length=max_length, min_length=min_length, length_penalty=length_penalty,
+                                           no_repeat_ngram_size=no_repeat_ngram_size, early_stopping=early_stopping)
+        logits_fn, reorder_fn = (lambda ids: self.last_logits(st, ids, rd)), None
         return beam_search(logits_fn, B, cfg.vocab_size, dev, num_beams=num_beams, max_length=max_length, min_length=min_length,
                            length_penalty=length_penalty, no_repeat_ngram_size=no_repeat_ngram_size, early_stopping=early_stopping,
                            pad=cfg.pad_token_id, bos=cfg.bos_token_id, eos=cfg.eos_token_id, reorder_fn=reorder_fn)
