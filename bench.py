@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--businesses", type=int, default=None, help="businesses per GPU (train: 16, generate: 64)")
     ap.add_argument("--max-length", type=int, default=128, help="generate: decoder frame (src/test.py --max_length)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the Amazon / generation workloads appended to the default run")
     ap.add_argument("--cpu-seconds", type=float, default=240.0, help="time budget of the reference arm")
     a = ap.parse_args()
     a.workload = a.workload or a.dataset or "yelp"
@@ -283,12 +284,7 @@ def run_train(args):
     from multimodalsum_b200.synth import ModelConfig, make_batch
 
     world, rank, local_rank = _dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group(backend="nccl", init_method="env://", device_id=dev)
     B = args.businesses
     amazon = args.workload == "amazon"
     cfg = ModelConfig(dataset=args.workload, dropout=0.1)
@@ -405,9 +401,7 @@ def run_train(args):
     final_loss = float(loss_host.item())
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     peaks = load_peaks()
     traffic = load_traffic()
     tfb = TFLOP_PER_BUSINESS[args.workload]
@@ -443,9 +437,7 @@ def run_train(args):
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_steps(3, 1, 60.0, args.workload)
         line["cpu_baseline"] = {"value": r["value"], "unit": "businesses/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 # ------------------------------------------------------------------------------------------------ generation workload (config 5)
@@ -461,12 +453,7 @@ def run_generate(args):
     from multimodalsum_b200.synth import ModelConfig, make_batch
 
     world, rank, local_rank = _dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group(backend="nccl", init_method="env://", device_id=dev)
     B, beams, max_length = args.businesses, 4, args.max_length
     cfg = ModelConfig(dataset="yelp", dropout=0.0)
     torch.manual_seed(0)
@@ -511,6 +498,13 @@ def run_generate(args):
     ms_per_step = max_over_ranks(s.elapsed_time(e)) / args.steps
     tokens = max_length - 1                       # decode steps of a full frame (random-init weights never finish early)
     value = B * world * tokens / (ms_per_step / 1e3)
+    # memory encoding alone (encoder + table + image heads + 12 cross K|V projections)
+    s.record()
+    for _ in range(3):
+        st = gen.encode(resident.reviews, resident.reviews_mask, resident.field, resident.field_value, resident.img, resident.img_mask, beams)
+    e.record()
+    torch.cuda.synchronize()
+    enc_ms = s.elapsed_time(e) / 3
     # decode-step-only timing: the incremental decoder alone, 16 consecutive positions
     st = gen.encode(resident.reviews, resident.reviews_mask, resident.field, resident.field_value, resident.img, resident.img_mask, beams)
     N = B * beams
@@ -538,9 +532,7 @@ def run_generate(args):
     barrier()
     e2e_ms = max_over_ranks(s.elapsed_time(e)) / args.steps
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     peaks = load_peaks()
     mem = st.mem
     D = cfg.d_model
@@ -565,22 +557,59 @@ def run_generate(args):
         "roofline": {"kernel": "incremental decode step (all kernels of one token: 12 decoder layers + LM head)", "bound": "hbm",
                      "achieved": step_bytes / (dec_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": step_bytes / (dec_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                     "peak_source": peaks["source"], "decode_step_ms": dec_ms,
+                     "peak_source": peaks["source"], "decode_step_ms": dec_ms, "encode_ms": enc_ms,
+                     "token_ms_incl_beam_update": (ms_per_step - enc_ms) / tokens,
                      "algorithmic_bytes_per_step": {"cross_kv": kv_bytes, "decoder_weights_and_lm_head": dec_w, "self_kv_cache": self_bytes}},
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def _free_gpu():
+    import gc
+    import torch
+    gc.collect()
+    torch.cuda.empty_cache()
 
 
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "generate":
-        run_generate(args)
-    else:
-        run_train(args)
+        return
+    import copy
+    import torch
+    import torch.distributed as dist
+    world, rank, local_rank = _dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", init_method="env://", device_id=torch.device("cuda", local_rank))
+    line = run_generate(args) if args.workload == "generate" else run_train(args)
+    if args.workload == "yelp" and not args.no_secondary:
+        # the other BASELINE configs, measured in the same run so that the driver's default invocation records them:
+        # configs[3] (Amazon shape, every N) and configs[4] (beam-4 generation; replicas only, so N = 1)
+        sec = {}
+        _free_gpu()
+        a2 = copy.copy(args)
+        a2.workload, a2.businesses, a2.steps, a2.no_cpu_baseline = "amazon", 16, min(args.steps, 5), True
+        r = run_train(a2)
+        if r is not None:
+            sec["amazon_configs3"] = {k: r[k] for k in ("value", "unit", "ms_per_step", "n_gpus", "steps", "e2e", "config", "clocks", "tc_fraction_step")}
+            sec["amazon_configs3"]["roofline_frac_gemm"] = r["roofline"]["frac"]
+        if world == 1:
+            _free_gpu()
+            a3 = copy.copy(args)
+            a3.workload, a3.businesses, a3.steps = "generate", 64, 3
+            r = run_generate(a3)
+            if r is not None:
+                sec["generate_configs4"] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "e2e", "config", "clocks", "roofline")}
+        if line is not None:
+            line["secondary"] = sec
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
