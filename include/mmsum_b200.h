@@ -98,6 +98,14 @@ int mmsum_attn_decode_cross(const MmsumAttnArgs* args, void* stream);
 int mmsum_attn_decode_self(const void* qkv, int64_t ldqkv, void* cache, int32_t* hist, const int32_t* pos_dev, void* out,
                            int64_t ldo, int32_t n_hyp, int32_t H, float scale, void* stream);
 
+/* Candidate selection of one beam-search token, per hypothesis row: forced BOS / EOS (adjust_logits_during_generation,
+ * modeling_multimodalsum.py:3084-3101), log_softmax, EOS ban below min_length and n-gram ban from the row's own history
+ * (generation_utils.py:57-99, 848-868), + beam_scores, top-K (:2919-2925).  logits fp32 [rows, ld]; ids int64 [rows, L] token
+ * history; cur_dev: device scalar, current length; K in {2,4,8,16}; out_val / out_tok [rows, K] sorted by descending score. */
+int mmsum_beam_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, const float* beam_scores, const int64_t* ids,
+                    int32_t L, const int64_t* cur_dev, int32_t min_length, int32_t ngram, int32_t bos, int32_t eos, int32_t K,
+                    float* out_val, int32_t* out_tok, void* stream);
+
 /* ---- HBM-bound row kernels (d_model = 1024) ----------------------------------------------------- */
 /* fp32 -> bf16 (weight arena cast, feature cast) */
 int mmsum_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);

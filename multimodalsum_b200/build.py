@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmmsum_b200.so")
-SOURCES = ["gemm_sm100.cu", "attention_sm100.cu", "decode_sm100.cu", "rowwise.cu", "optim.cu"]
+SOURCES = ["gemm_sm100.cu", "attention_sm100.cu", "decode_sm100.cu", "beam_sm100.cu", "rowwise.cu", "optim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",

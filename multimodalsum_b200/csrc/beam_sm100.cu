@@ -1,0 +1,163 @@
+// Device-side candidate selection of one beam-search token (BASELINE config 5).
+//
+// Replaces, per hypothesis row, the chain the reference runs on [N, V] tensors plus host loops every token:
+//   adjust_logits_during_generation (force BOS after the start token / EOS at the end of the frame,
+//   src/transformer/modeling_multimodalsum.py:3084-3101), log_softmax (:2893), the EOS ban below min_length and the n-gram
+//   ban (postprocess_next_token_scores / calc_banned_ngram_tokens, src/transformer/generation_utils.py:57-99, 848-868 —
+//   Python loops over batch x beam with .tolist()), `scores + beam_scores` and the top-2k selection (:2919-2925).
+// One CTA per row: pass 1 = log-sum-exp of the UNBANNED row (as the reference: bans are applied to the log-probabilities),
+// the banned tokens of the row are found from its own history, pass 2 = top-K of the remaining tokens.  The global top-2k
+// of a business is a subset of the union of its rows' top-2k, so the host side only merges k x 2k candidates.
+// HBM/L2-bound: the fp32 logits row (201 KB) is read twice.
+#include "common.cuh"
+#include "../../include/mmsum_b200.h"
+
+namespace mmsum {
+
+static constexpr int kBeamThreads = 256;
+static constexpr int kMaxBan = 160;
+
+struct Cand { float v; int tok; int src; };
+__device__ __forceinline__ bool cand_better(float v, int tok, float v2, int tok2) { return v > v2 || (v == v2 && tok < tok2); }
+
+template <int K>
+__global__ void __launch_bounds__(kBeamThreads)
+beam_topk_kernel(const float* __restrict__ logits, long long ld, int V, const float* __restrict__ beam_scores,
+                 const long long* __restrict__ ids, int L, const long long* __restrict__ cur_dev, int min_length, int ngram,
+                 int bos, int eos, float* __restrict__ out_val, int* __restrict__ out_tok) {
+  __shared__ float red_m[8], red_s[8];
+  __shared__ int s_ban[kMaxBan];
+  __shared__ int s_nban;
+  __shared__ float s_cv[8];
+  __shared__ int s_ct[8], s_cs[8];
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* z = logits + (long long)row * ld;
+  const long long* hist = ids + (long long)row * L;
+  const int cur = (int)cur_dev[0];
+  const float bscore = beam_scores[row];
+  float* ov = out_val + (long long)row * K;
+  int* ot = out_tok + (long long)row * K;
+  const int forced = (cur == 1) ? bos : ((cur == L - 1) ? eos : -1);
+  if (forced >= 0) {
+    // a forced token carries log-probability 0, every other token -inf (their identity is irrelevant; keep them distinct,
+    // unfinished and different from the forced token as torch.topk would)
+    if (tid < K) {
+      ov[tid] = (tid == 0) ? bscore : -INFINITY;
+      ot[tid] = (tid == 0) ? forced : (tid + 2 + (forced > 2 && tid + 2 >= forced ? 1 : 0));
+    }
+    return;
+  }
+  if (tid == 0) s_nban = 0;
+  // ---- pass 1: log-sum-exp of the row
+  float m = -INFINITY, s = 0.f;
+  const int nvec = V >> 2;
+  for (int i = tid; i < nvec; i += kBeamThreads) {
+    const float4 f = *reinterpret_cast<const float4*>(z + 4 * i);
+    const float bm = fmaxf(fmaxf(f.x, f.y), fmaxf(f.z, f.w));
+    const float mn = fmaxf(m, bm);
+    s = s * __expf(m - mn) + __expf(f.x - mn) + __expf(f.y - mn) + __expf(f.z - mn) + __expf(f.w - mn);
+    m = mn;
+  }
+  for (int i = nvec * 4 + tid; i < V; i += kBeamThreads) {
+    const float v = z[i];
+    const float mn = fmaxf(m, v);
+    s = s * __expf(m - mn) + __expf(v - mn);
+    m = mn;
+  }
+  const float wm = warp_max(m);
+  s = (m == -INFINITY) ? 0.f : s * __expf(m - wm);
+  s = warp_sum(s);
+  if (lane == 0) { red_m[warp] = wm; red_s[warp] = s; }
+  __syncthreads();
+  float M = red_m[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) M = fmaxf(M, red_m[w]);
+  float S = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) S += (red_m[w] == -INFINITY) ? 0.f : red_s[w] * __expf(red_m[w] - M);
+  const float lse = M + logf(S);
+  // ---- banned tokens of this row: the EOS below min_length, and every token that would complete an n-gram already present
+  if (tid == 0 && cur < min_length) s_ban[atomicAdd(&s_nban, 1)] = eos;
+  if (ngram > 0 && cur >= ngram) {
+    for (int i = tid; i <= cur - ngram; i += kBeamThreads) {
+      bool hit = true;
+      for (int j = 0; j < ngram - 1; ++j) hit = hit && (hist[i + j] == hist[cur - ngram + 1 + j]);
+      if (hit) {
+        const int slot = atomicAdd(&s_nban, 1);
+        if (slot < kMaxBan) s_ban[slot] = (int)hist[i + ngram - 1];
+      }
+    }
+  }
+  __syncthreads();
+  const int nban = min(s_nban, kMaxBan);
+  // ---- pass 2: per-thread top-K (sorted, descending), then K rounds of block arg-max over the list heads
+  float tv[K];
+  int tt[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) { tv[j] = -INFINITY; tt[j] = 0x7fffffff; }
+  auto offer = [&](float v, int tok) {
+    if (cand_better(v, tok, tv[K - 1], tt[K - 1])) {
+      for (int b = 0; b < nban; ++b) if (s_ban[b] == tok) return;
+      tv[K - 1] = v; tt[K - 1] = tok;
+#pragma unroll
+      for (int j = K - 1; j > 0; --j) {
+        if (cand_better(tv[j], tt[j], tv[j - 1], tt[j - 1])) {
+          const float fv = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = fv;
+          const int ft = tt[j]; tt[j] = tt[j - 1]; tt[j - 1] = ft;
+        }
+      }
+    }
+  };
+  for (int i = tid; i < nvec; i += kBeamThreads) {
+    const float4 f = *reinterpret_cast<const float4*>(z + 4 * i);
+    offer(f.x, 4 * i); offer(f.y, 4 * i + 1); offer(f.z, 4 * i + 2); offer(f.w, 4 * i + 3);
+  }
+  for (int i = nvec * 4 + tid; i < V; i += kBeamThreads) offer(z[i], i);
+  int head = 0;
+  for (int r = 0; r < K; ++r) {
+    float bv = -INFINITY; int bt = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < K; ++j) if (j == head) { bv = tv[j]; bt = tt[j]; }
+    int bsrc = tid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int t2 = __shfl_xor_sync(0xffffffffu, bt, o);
+      const int s2 = __shfl_xor_sync(0xffffffffu, bsrc, o);
+      if (cand_better(v2, t2, bv, bt)) { bv = v2; bt = t2; bsrc = s2; }
+    }
+    if (lane == 0) { s_cv[warp] = bv; s_ct[warp] = bt; s_cs[warp] = bsrc; }
+    __syncthreads();
+    float gv = s_cv[0]; int gt = s_ct[0], gs = s_cs[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) if (cand_better(s_cv[w], s_ct[w], gv, gt)) { gv = s_cv[w]; gt = s_ct[w]; gs = s_cs[w]; }
+    if (tid == gs && head < K) ++head;
+    if (tid == 0) {
+      ov[r] = (gv == -INFINITY) ? -INFINITY : (gv - lse + bscore);
+      ot[r] = (gt == 0x7fffffff) ? (r + 3) : gt;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace mmsum
+
+using namespace mmsum;
+
+extern "C" int mmsum_beam_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, const float* beam_scores,
+                               const int64_t* ids, int32_t L, const int64_t* cur_dev, int32_t min_length, int32_t ngram,
+                               int32_t bos, int32_t eos, int32_t K, float* out_val, int32_t* out_tok, void* stream_v) {
+  if (!logits || !beam_scores || !ids || !cur_dev || !out_val || !out_tok || rows <= 0 || V < 32 || L < 2) return MMSUM_ERR_INVALID;
+  if ((ld % 4) || ld < V || (reinterpret_cast<uintptr_t>(logits) & 15)) return MMSUM_ERR_INVALID;
+  if (ngram < 0 || ngram > 8 || L - 1 + 1 > kMaxBan) return MMSUM_ERR_INVALID;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  const long long* ids_ll = reinterpret_cast<const long long*>(ids);
+  const long long* cur_ll = reinterpret_cast<const long long*>(cur_dev);
+  if (K == 8) beam_topk_kernel<8><<<rows, kBeamThreads, 0, stream>>>(logits, ld, V, beam_scores, ids_ll, L, cur_ll, min_length, ngram, bos, eos, out_val, out_tok);
+  else if (K == 16) beam_topk_kernel<16><<<rows, kBeamThreads, 0, stream>>>(logits, ld, V, beam_scores, ids_ll, L, cur_ll, min_length, ngram, bos, eos, out_val, out_tok);
+  else if (K == 2) beam_topk_kernel<2><<<rows, kBeamThreads, 0, stream>>>(logits, ld, V, beam_scores, ids_ll, L, cur_ll, min_length, ngram, bos, eos, out_val, out_tok);
+  else if (K == 4) beam_topk_kernel<4><<<rows, kBeamThreads, 0, stream>>>(logits, ld, V, beam_scores, ids_ll, L, cur_ll, min_length, ngram, bos, eos, out_val, out_tok);
+  else return MMSUM_ERR_INVALID;
+  MMSUM_CHECK_LAUNCH();
+  return 0;
+}

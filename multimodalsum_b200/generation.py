@@ -72,6 +72,8 @@ class BeamSearch:
         self.own = self.row0 + self.slot_ids[None, :]
         self.beam_idx = torch.arange(N, device=dev)
         self.next_tok = torch.zeros(N, dtype=torch.long, device=dev)
+        self.cand_val = self.cand_tok = None
+        self.use_kernel = True                                # fused candidate-selection kernel on CUDA (tests switch it off)
 
     # -- hypothesis pool --------------------------------------------------------------------------------
     def _admit(self, active, score, tokens, length):
@@ -104,6 +106,18 @@ class BeamSearch:
         step) and replayed for every token."""
         B, k, V, L = self.B, self.k, self.V, self.max_length
         cur = self.cur_t                                                           # long [1]
+        if self.use_kernel and logits.is_cuda and 2 * k in (2, 4, 8, 16) and L <= 160 and logits.stride(0) % 4 == 0:
+            # fused per-row kernel (csrc/beam_sm100.cu): forced tokens, log-softmax, bans, + beam score, top-2k of the row;
+            # the top-2k of a business is then merged from its k x 2k row candidates
+            if self.cand_val is None:
+                self.cand_val = torch.empty(B * k, 2 * k, device=self.dev)
+                self.cand_tok = torch.empty(B * k, 2 * k, device=self.dev, dtype=torch.int32)
+            ops.beam_topk(logits, V, self.beam_scores, self.ids, cur, self.min_length, self.ngram, self.bos, self.eos, 2 * k,
+                          self.cand_val, self.cand_tok)
+            cs, cj = torch.topk(self.cand_val.view(B, k * 2 * k), 2 * k, dim=1, largest=True, sorted=True)
+            tok = self.cand_tok.view(B, k * 2 * k).gather(1, cj).long()
+            src = self.row0 + cj // (2 * k)
+            return self._update(cs, tok, src)
         # adjust_logits_during_generation (:3084-3089): only BOS may follow the start token, only EOS may close the frame
         forced_now = (cur == 1) | (cur == L - 1)
         forced_tok = torch.where(cur == 1, self.bos_t, self.eos_t).expand(logits.shape[0], 1)
@@ -124,8 +138,11 @@ class BeamSearch:
             scores.scatter_(1, torch.where(hit, win[:, :, n - 1], self.v_col), NEG)
         cand = (scores[:, :V] + self.beam_scores[:, None]).view(B, k * V)
         cs, ci = torch.topk(cand, 2 * k, dim=1, largest=True, sorted=True)
-        tok = ci % V
-        src = self.row0 + ci // V                                                  # effective (global) beam index
+        return self._update(cs, ci % V, self.row0 + ci // V)
+
+    def _update(self, cs, tok, src):
+        """cs / tok / src [B, 2k]: score, token and effective (global) beam index of the 2k best continuations per business."""
+        k, cur = self.k, self.cur_t
         is_eos = tok == self.eos
         # finished candidates among the first k ranks enter the pool of their business (:2949-2957)
         live = ~self.done

@@ -275,6 +275,13 @@ def embed_ln_decode(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, 
           "mmsum_embed_ln_decode")
 
 
+def beam_topk(logits, V, beam_scores, ids, cur_dev, min_length, ngram, bos, eos, K, out_val, out_tok):
+    """Per-row candidate selection of one beam-search token (see include/mmsum_b200.h)."""
+    check(_lib.lib().mmsum_beam_topk(_ptr(logits), C.c_int64(logits.stride(0)), logits.shape[0], V, _ptr(beam_scores), _ptr(ids),
+                                     ids.shape[1], _ptr(cur_dev), min_length, ngram, bos, eos, K, _ptr(out_val), _ptr(out_tok),
+                                     _stream()), "mmsum_beam_topk")
+
+
 def prep_step(reviews, reviews_mask, rating, table_valid, img_mask, **kw):
     a = _lib.PrepArgs()
     for k, v in kw.items():

@@ -157,3 +157,34 @@ def test_teacher_forced_next_token_logits(name):
     assert checked > 0
 
 
+
+
+@pytest.mark.parametrize("k,V,ngram,min_length", [(4, 50265, 3, 0), (1, 1000, 2, 6), (8, 777, 3, 0), (2, 50265, 0, 0)])
+def test_beam_candidate_kernel_matches_tensor_implementation(k, V, ngram, min_length):
+    """The fused per-row candidate kernel (forced tokens, log-softmax, EOS / n-gram bans, top-2k) drives the same beam search as
+    the tensor-op implementation that tests/test_generate_oracle.py pins to the reference: identical token histories, beam
+    re-ranking, hypothesis pools and done flags over a whole frame on random logits (low-entropy rows so that hypotheses
+    finish and n-grams repeat)."""
+    from multimodalsum_b200.generation import BeamSearch
+    torch.manual_seed(20 + k)
+    B, L = 6, 24
+    N = B * k
+    mk = lambda: BeamSearch(B, V, torch.device("cuda"), k, L, min_length, 1.0, ngram, True, 1, 0, 2)
+    a, b = mk(), mk()
+    b.use_kernel = False
+    ld = (V + 3) // 4 * 4
+    for step in range(L - 1):
+        logits = torch.zeros(N, ld, device="cuda")[:, :V]
+        logits.copy_(torch.randn(N, V, device="cuda") * 3)
+        logits[:, 2] += 4.0                          # EOS is competitive: hypotheses finish along the way
+        logits[:, 3:6] += 6.0                        # a few dominant tokens: repeated n-grams get banned
+        ia = a.advance(logits.clone())
+        ib = b.advance(logits.clone())
+        assert torch.equal(a.done, b.done), step
+        live = (~a.done).repeat_interleave(k)
+        assert torch.equal(ia[live], ib[live]) and torch.equal(a.ids[live], b.ids[live]), step
+        assert torch.allclose(a.beam_scores[live], b.beam_scores[live], rtol=1e-5, atol=1e-4), step
+        assert torch.equal(a.pool_n, b.pool_n) and torch.equal(a.pool_len, b.pool_len) and torch.equal(a.pool_tok, b.pool_tok), step
+        fin = a.slot_ids[None, :] < a.pool_n[:, None]
+        assert torch.allclose(a.pool_score[fin], b.pool_score[fin], rtol=1e-5, atol=1e-4), step
+    assert torch.equal(a.finalize(), b.finalize())
