@@ -17,6 +17,12 @@
 //                             swizzled smem staging, TMA store (or TMA reduce-add for split-K / grad accumulation)
 // TMEM holds two accumulator stages (2 x BN fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Ragged M/N/K edges rely on TMA: out-of-bounds loads are zero-filled, out-of-bounds stores are clipped.
+//
+// CL = 2 (large problems): the persistent CTAs run as thread-block clusters of two that walk the SAME n-tile on adjacent
+// m-tiles in lock-step.  Each CTA fetches its own A tile and HALF of the shared B tile, which TMA multicasts into both CTAs'
+// shared memory: per k-block a CTA pulls 32 KB instead of 48 KB out of L2 (the 128 x 256 tile at 1 CTA/SM was limited by
+// L2 -> SM operand bandwidth, 96 B/clk/SM; tensor pipe 72 % active in profiles/r01_ncu_gemm_plain_v4_summary.txt).  A stage
+// is recycled only when BOTH CTAs' MMAs have retired it: tcgen05.commit arrives (multicast) on both CTAs' empty barriers.
 #include "common.cuh"
 #include "../../include/mmsum_b200.h"
 
@@ -60,16 +66,17 @@ struct GemmKernelArgs {
   int k_split;    // > 0: A columns [k_split, K) come from the second A tensor map (concat along K)
 };
 
-__device__ __forceinline__ void decode_tile(const GemmKernelArgs& g, int t, int& mt, int& nt, int& sp) {
-  const int mn = g.m_tiles * g.n_tiles;
+// work unit t -> (m unit, n tile, k split); an m unit is one m-tile (CL = 1) or a pair of adjacent m-tiles (CL = 2)
+__device__ __forceinline__ void decode_tile(const GemmKernelArgs& g, int m_units, int t, int& mu, int& nt, int& sp) {
+  const int mn = m_units * g.n_tiles;
   sp = t / mn;
   const int r = t - sp * mn;
-  if (g.raster_m_fast) { mt = r % g.m_tiles; nt = r / g.m_tiles; }
-  else                 { nt = r % g.n_tiles; mt = r / g.n_tiles; }
+  if (g.raster_m_fast) { mu = r % m_units; nt = r / m_units; }
+  else                 { nt = r % g.n_tiles; mu = r / g.n_tiles; }
 }
 
 // EPI: 0 plain epilogue (alpha, bias, ReLU), 1 = GELU/ReLU with the pre-activation saved to aux, 2 = multiply by act'(aux)
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
@@ -87,14 +94,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = g.m_tiles * g.n_tiles * g.splits;
+  const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;      // position inside the CTA pair
+  const int m_units = (CL == 2) ? (g.m_tiles + 1) / 2 : g.m_tiles;
+  const int total_tiles = m_units * g.n_tiles * g.splits;        // work units of a cluster (CL = 2) / a CTA
+  const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmD);
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < L::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < L::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
       for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * 32); }
       fence_barrier_init();
     }
@@ -104,6 +114,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();     // the peer's barriers are initialised before anything of ours can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
@@ -112,8 +123,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop; lane 0 issues) =====================
     int stage = 0; uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int mt, nt, sp; decode_tile(g, t, mt, nt, sp);
+    for (int t = unit0; t < total_tiles; t += unit_stride) {
+      int mu, nt, sp; decode_tile(g, m_units, t, mu, nt, sp);
+      const int mt = (CL == 2) ? 2 * mu + crank : mu;
       const int m0 = mt * BM, n0 = nt * BN;
       const int k_begin = sp * g.k_per_split;
       const int k_end = min(g.K, k_begin + g.k_per_split);
@@ -130,7 +142,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else {
           tma_load_2d_w(sA, &tmA, &full_bar[stage], k0, m0);
         }
-        if (B_MN) {
+        if (CL == 2) {
+          // this CTA's half of the B tile, delivered to both CTAs of the pair (the other half arrives from the peer)
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j) {
+              const int jj = crank * (BN / 128) + j;
+              tma_load_2d_mc_w(sB + jj * 8192, &tmB, &full_bar[stage], n0 + 64 * jj, k0, (uint16_t)3);
+            }
+          } else {
+            tma_load_2d_mc_w(sB + crank * (BN / 2) * 128, &tmB, &full_bar[stage], k0, n0 + crank * (BN / 2), (uint16_t)3);
+          }
+        } else if (B_MN) {
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) tma_load_2d_w(sB + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, k0);
         } else {
@@ -145,8 +168,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t smem_base = smem_u32(smem);
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int mt, nt, sp; decode_tile(g, t, mt, nt, sp);
+    for (int t = unit0; t < total_tiles; t += unit_stride) {
+      int mu, nt, sp; decode_tile(g, m_units, t, mu, nt, sp);
       const int k_begin = sp * g.k_per_split;
       const int k_end = min(g.K, k_begin + g.k_per_split);
       mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -168,7 +191,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                       bd0 + (uint64_t)((B_MN ? kk * 2048 : kk * 32) >> 4), idesc, accum);
           accum = 1;
         }
-        umma_commit_w(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+        // frees the smem stage once these MMAs retire (in BOTH CTAs of a pair: the peer's next multicast writes here too)
+        if (CL == 2) umma_commit_mc_w(&empty_bar[stage], (uint16_t)3); else umma_commit_w(&empty_bar[stage]);
         if (++stage == L::kStages) { stage = 0; phase ^= 1; }
       }
       umma_commit_w(&tfull_bar[as]);       // accumulator complete
@@ -184,8 +208,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool bias_vec = (g.bias != nullptr) && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
     constexpr int kGroupsPerWarp = BN / 128;      // 64-column groups per warp and tile
     int as = 0; uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int mt, nt, sp; decode_tile(g, t, mt, nt, sp);
+    for (int t = unit0; t < total_tiles; t += unit_stride) {
+      int mu, nt, sp; decode_tile(g, m_units, t, mu, nt, sp);
+      const int mt = (CL == 2) ? 2 * mu + crank : mu;
       const int m0 = mt * BM, n0 = nt * BN;
       const int row = m0 + q * 32 + lane;
       // activation-gradient operand (EPI 2): this warp's share of the tile is fetched before the accumulator is
@@ -324,6 +349,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();     // neither CTA leaves while the peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -398,15 +424,15 @@ static int num_sms() {
   return v;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& td,
                        const CUtensorMap& taux,
                        const GemmKernelArgs& ka, int grid, cudaStream_t stream) {
   using L = GemmSmem<BN>;
   static std::atomic<unsigned long long> attr_set{0};     // one per template instantiation
-  if (int rc = ensure_dyn_smem(gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>, L::kTotal, attr_set)) return rc;
-  cudaError_t le = launch_pdl(gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>, dim3(grid), dim3(kGemmThreads), (size_t)L::kTotal, stream,
-                              ta, ta2, tb, td, taux, ka);
+  if (int rc = ensure_dyn_smem(gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CL>, L::kTotal, attr_set)) return rc;
+  cudaError_t le = launch_pdl_cluster(gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CL>, dim3(grid), dim3(kGemmThreads), (size_t)L::kTotal,
+                                      stream, CL, ta, ta2, tb, td, taux, ka);
   if (le != cudaSuccess) return (int)le;
   MMSUM_CHECK_LAUNCH();
   return 0;
@@ -491,8 +517,13 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
     ta2 = ta;
   }
   if (rc) return rc;
+  // CTA pairs with a multicast B tile for problems that fill the machine with 256-wide tiles (MMSUM_GEMM_CLUSTER=0: off)
+  static const bool cluster_off = [] { const char* e = getenv("MMSUM_GEMM_CLUSTER"); return e && e[0] == '0'; }();
+  const int nsm = num_sms();
+  const long long pairs = (long long)((ka.m_tiles + 1) / 2) * ka.n_tiles * ka.splits;
+  const int cl = (!cluster_off && bn == 256 && ka.m_tiles >= 2 && pairs * 2 >= nsm && (nsm % 2) == 0) ? 2 : 1;
   if (a->b_mn_major) rc = make_tmap(&tb, a->B, 0, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, 64, 64);
-  else               rc = make_tmap(&tb, a->B, 0, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, 64, (uint32_t)bn);
+  else               rc = make_tmap(&tb, a->B, 0, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb * 2, 64, (uint32_t)(bn / cl));
   if (rc) return rc;
   if (a->out_f32) rc = make_tmap(&td, a->D, 1, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 4, 32, 32);
   else            rc = make_tmap(&td, a->D, 0, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 64, 32);
@@ -506,26 +537,34 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
   if (ka.splits > 1 && (a->act != 0 || a->aux_mode != 0)) return MMSUM_ERR_INVALID;
   if (a->out_f32 && (a->act == 1 || a->aux_mode != 0)) return MMSUM_ERR_INVALID;   // fused activations are bf16-output only
   const int total = ka.m_tiles * ka.n_tiles * ka.splits;
-  const int nsm = num_sms();
-  const int grid = total < nsm ? total : nsm;
+  int grid = total < nsm ? total : nsm;
+  if (cl == 2) grid = (int)(pairs * 2 < nsm ? pairs * 2 : nsm);
   const int am = a->a_mn_major ? 1 : 0, bm = a->b_mn_major ? 1 : 0;
   const int epi = a->aux_mode;
-#define MMSUM_GEMM_CASE(BN_, AM_, BM_, EPI_) \
-  if (bn == BN_ && am == AM_ && bm == BM_ && epi == EPI_) \
-    return launch_gemm<BN_, (AM_ != 0), (BM_ != 0), EPI_>(ta, ta2, tb, td, taux, ka, grid, stream);
-  MMSUM_GEMM_CASE(256, 0, 0, 0)
-  MMSUM_GEMM_CASE(256, 0, 1, 0)
-  MMSUM_GEMM_CASE(256, 1, 1, 0)
-  MMSUM_GEMM_CASE(256, 1, 0, 0)
-  MMSUM_GEMM_CASE(128, 0, 0, 0)
-  MMSUM_GEMM_CASE(128, 0, 1, 0)
-  MMSUM_GEMM_CASE(128, 1, 1, 0)
-  MMSUM_GEMM_CASE(128, 1, 0, 0)
+#define MMSUM_GEMM_CASE(BN_, AM_, BM_, EPI_, CL_) \
+  if (bn == BN_ && am == AM_ && bm == BM_ && epi == EPI_ && cl == CL_) \
+    return launch_gemm<BN_, (AM_ != 0), (BM_ != 0), EPI_, CL_>(ta, ta2, tb, td, taux, ka, grid, stream);
+  MMSUM_GEMM_CASE(256, 0, 0, 0, 2)
+  MMSUM_GEMM_CASE(256, 0, 1, 0, 2)
+  MMSUM_GEMM_CASE(256, 1, 1, 0, 2)
+  MMSUM_GEMM_CASE(256, 1, 0, 0, 2)
+  MMSUM_GEMM_CASE(256, 0, 0, 1, 2)
+  MMSUM_GEMM_CASE(256, 0, 1, 1, 2)
+  MMSUM_GEMM_CASE(256, 0, 0, 2, 2)
+  MMSUM_GEMM_CASE(256, 0, 1, 2, 2)
+  MMSUM_GEMM_CASE(256, 0, 0, 0, 1)
+  MMSUM_GEMM_CASE(256, 0, 1, 0, 1)
+  MMSUM_GEMM_CASE(256, 1, 1, 0, 1)
+  MMSUM_GEMM_CASE(256, 1, 0, 0, 1)
+  MMSUM_GEMM_CASE(128, 0, 0, 0, 1)
+  MMSUM_GEMM_CASE(128, 0, 1, 0, 1)
+  MMSUM_GEMM_CASE(128, 1, 1, 0, 1)
+  MMSUM_GEMM_CASE(128, 1, 0, 0, 1)
   // fused-activation epilogues: row-major A (the Linear fprop / dgrad operands), 256-wide tiles
-  MMSUM_GEMM_CASE(256, 0, 0, 1)
-  MMSUM_GEMM_CASE(256, 0, 1, 1)
-  MMSUM_GEMM_CASE(256, 0, 0, 2)
-  MMSUM_GEMM_CASE(256, 0, 1, 2)
+  MMSUM_GEMM_CASE(256, 0, 0, 1, 1)
+  MMSUM_GEMM_CASE(256, 0, 1, 1, 1)
+  MMSUM_GEMM_CASE(256, 0, 0, 2, 1)
+  MMSUM_GEMM_CASE(256, 0, 1, 2, 1)
 #undef MMSUM_GEMM_CASE
   return MMSUM_ERR_INVALID;
 }
