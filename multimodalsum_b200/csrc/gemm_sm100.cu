@@ -517,8 +517,10 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
     ta2 = ta;
   }
   if (rc) return rc;
-  // CTA pairs with a multicast B tile for problems that fill the machine with 256-wide tiles (MMSUM_GEMM_CLUSTER=0: off)
-  static const bool cluster_off = [] { const char* e = getenv("MMSUM_GEMM_CLUSTER"); return e && e[0] == '0'; }();
+  // CTA pairs with a multicast B tile for problems that fill the machine with 256-wide tiles.  Opt-in (MMSUM_GEMM_CLUSTER=1):
+  // measured on B200 it halves the B-operand L2 reads but moves neither the kernel time nor the tensor-pipe activity
+  // (profiles/r02_gemm_cluster_ab.txt: L2 was never the limiter at 31-52 % of its peak), so the simpler launch is the default.
+  static const bool cluster_off = [] { const char* e = getenv("MMSUM_GEMM_CLUSTER"); return !(e && e[0] == '1'); }();
   const int nsm = num_sms();
   const long long pairs = (long long)((ka.m_tiles + 1) / 2) * ka.n_tiles * ka.splits;
   const int cl = (!cluster_off && bn == 256 && ka.m_tiles >= 2 && pairs * 2 >= nsm && (nsm % 2) == 0) ? 2 : 1;
