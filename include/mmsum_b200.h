@@ -106,6 +106,16 @@ int mmsum_beam_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, co
                     int32_t L, const int64_t* cur_dev, int32_t min_length, int32_t ngram, int32_t bos, int32_t eos, int32_t K,
                     float* out_val, int32_t* out_tok, void* stream);
 
+/* Per-business beam update after mmsum_beam_topk (_generate_beam_search :2933-3010, BeamHypotheses.add / is_done
+ * generation_utils.py:962-993): merges the k x K row candidates, admits finished ones (rank < k) to the business' pool, selects
+ * the next k beams, permutes the token histories `ids` in place, writes beam_scores / beam_idx / next_tok.  All state is device
+ * memory (done: 1 byte per business; pool_* as in generation.BeamSearch).  Optional decoder hooks: next_tok32 [B*k] (token input
+ * of the next decode step), hist [B*k, 128] (self-attention slot table, permuted like ids = _reorder_cache :3103-3115). */
+int mmsum_beam_update(const float* cand_val, const int32_t* cand_tok, int64_t* ids, float* beam_scores, uint8_t* done,
+                      float* pool_score, int64_t* pool_tok, int64_t* pool_len, int64_t* pool_n, const int64_t* cur_dev,
+                      int64_t* beam_idx, int64_t* next_tok, int32_t* next_tok32, int32_t* hist, int32_t B, int32_t k, int32_t K,
+                      int32_t L, int32_t eos, int32_t pad, int32_t early_stopping, float length_penalty, void* stream);
+
 /* ---- HBM-bound row kernels (d_model = 1024) ----------------------------------------------------- */
 /* fp32 -> bf16 (weight arena cast, feature cast) */
 int mmsum_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);

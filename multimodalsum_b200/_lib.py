@@ -82,7 +82,7 @@ EXPORTS = [
     "mmsum_embed_ln_fwd", "mmsum_embed_ln_bwd", "mmsum_add_ln_fwd", "mmsum_add_ln_bwd", "mmsum_colsum",
     "mmsum_gate_fwd", "mmsum_gate_bwd_u", "mmsum_gate_bwd_o", "mmsum_ce_fwd_bwd", "mmsum_prep_step",
     "mmsum_table_fwd", "mmsum_table_bits_bwd", "mmsum_grad_sumsq", "mmsum_adamw_step",
-    "mmsum_embed_ln_decode", "mmsum_attn_decode_cross", "mmsum_attn_decode_self", "mmsum_beam_topk",
+    "mmsum_embed_ln_decode", "mmsum_attn_decode_cross", "mmsum_attn_decode_self", "mmsum_beam_topk", "mmsum_beam_update",
 ]
 
 

@@ -140,9 +140,142 @@ beam_topk_kernel(const float* __restrict__ logits, long long ld, int V, const fl
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Per-business beam update: merge the k x K row candidates, move finished hypotheses into the business' pool, pick the next
+// k beams, permute the token histories (and the decoder's self-attention slot table) accordingly.
+// One warp per business; the decisions are a few dozen scalar steps (lane 0), the row copies are warp-wide.
+// (_generate_beam_search, modeling_multimodalsum.py:2933-3010; BeamHypotheses.add / is_done, generation_utils.py:962-993.)
+// ----------------------------------------------------------------------------------------------
+static constexpr int kBuMaxK = 8, kBuMaxL = 160, kBuMaxCand = 16;
+struct BeamUpdateArgs {
+  const float* cand_val; const int* cand_tok;          // [B*k, K]
+  long long* ids;                                      // [B*k, L] token histories (in place)
+  float* beam_scores;                                  // [B*k]
+  unsigned char* done;                                 // [B]
+  float* pool_score; long long* pool_tok; long long* pool_len; long long* pool_n;   // [B,k], [B,k,L], [B,k], [B]
+  const long long* cur_dev;
+  long long* beam_idx; long long* next_tok;            // [B*k] outputs
+  int* next_tok32;                                     // optional [B*k]: the decoder's token input of the next step
+  int* hist;                                           // optional [B*k, 128]: self-attention slot table, permuted like ids
+  int k, K, L, eos, pad, early_stopping;
+  float length_penalty;
+};
+
+__global__ void __launch_bounds__(32) beam_update_kernel(const BeamUpdateArgs a) {
+  __shared__ long long s_ids[kBuMaxK][kBuMaxL];
+  __shared__ int s_hist[kBuMaxK][128];
+  __shared__ float s_cv[kBuMaxK * kBuMaxCand];
+  __shared__ int s_ct[kBuMaxK * kBuMaxCand];
+  __shared__ float s_sel_v[kBuMaxCand];
+  __shared__ int s_sel_t[kBuMaxCand], s_sel_b[kBuMaxCand];
+  __shared__ int s_admit_slot[kBuMaxK], s_admit_src[kBuMaxK], s_n_admit;
+  __shared__ int s_nsrc[kBuMaxK], s_ntok[kBuMaxK];
+  __shared__ float s_nscore[kBuMaxK];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int k = a.k, K = a.K, L = a.L;
+  const int row0 = b * k;
+  const int cur = (int)a.cur_dev[0];
+  for (int i = lane; i < k * L; i += 32) s_ids[i / L][i % L] = a.ids[(long long)row0 * L + i];
+  if (a.hist != nullptr)
+    for (int i = lane; i < k * 128; i += 32) s_hist[i >> 7][i & 127] = a.hist[(long long)row0 * 128 + i];
+  for (int i = lane; i < k * K; i += 32) { s_cv[i] = a.cand_val[(long long)row0 * K + i]; s_ct[i] = a.cand_tok[(long long)row0 * K + i]; }
+  __syncwarp();
+  if (lane == 0) {
+    // ---- the K best of the k x K row candidates, by descending score (rows are sorted: ties go to the lower flat index)
+    for (int r = 0; r < K; ++r) {
+      int best = -1;
+      for (int i = 0; i < k * K; ++i)
+        if (s_ct[i] >= 0 && (best < 0 || s_cv[i] > s_cv[best])) best = i;
+      s_sel_v[r] = s_cv[best]; s_sel_t[r] = s_ct[best]; s_sel_b[r] = best / K;
+      s_ct[best] = -1;
+    }
+    const bool live = a.done[b] == 0;
+    const float norm = powf((float)cur, a.length_penalty);
+    float* ps = a.pool_score + (long long)b * k;
+    long long* pl = a.pool_len + (long long)b * k;
+    int pn = (int)a.pool_n[b];
+    // ---- finished candidates among the first k ranks enter the pool (a full pool admits only a better-than-worst one)
+    int n_admit = 0;
+    for (int r = 0; r < k; ++r) {
+      if (!(live && s_sel_t[r] == a.eos)) continue;
+      const float score = s_sel_v[r] / norm;
+      int slot = -1;
+      if (pn < k) { slot = pn; ++pn; }
+      else {
+        int w = 0;
+        for (int j = 1; j < k; ++j) if (ps[j] < ps[w]) w = j;
+        if (score > ps[w]) slot = w;
+      }
+      if (slot >= 0) {
+        ps[slot] = score; pl[slot] = cur;
+        // an earlier admission of this step into the same slot is superseded
+        for (int q = 0; q < n_admit; ++q) if (s_admit_slot[q] == slot) s_admit_slot[q] = -1;
+        s_admit_slot[n_admit] = slot; s_admit_src[n_admit] = s_sel_b[r]; ++n_admit;
+      }
+    }
+    s_n_admit = n_admit;
+    a.pool_n[b] = pn;
+    // ---- the first k unfinished candidates, in rank order, are the next beams
+    int nb = 0;
+    for (int r = 0; r < K && nb < k; ++r) {
+      if (s_sel_t[r] == a.eos) continue;
+      s_nscore[nb] = s_sel_v[r]; s_ntok[nb] = s_sel_t[r]; s_nsrc[nb] = s_sel_b[r]; ++nb;
+    }
+    for (; nb < k; ++nb) { s_nscore[nb] = -INFINITY; s_ntok[nb] = a.pad; s_nsrc[nb] = nb; }   // cannot happen with K = 2k
+    bool finished = pn >= k;
+    if (finished && !a.early_stopping) {
+      float w = ps[0];
+      for (int j = 1; j < k; ++j) w = fminf(w, ps[j]);
+      finished = w >= s_sel_v[0] / norm;
+    }
+    if (!live) for (int j = 0; j < k; ++j) { s_nscore[j] = 0.f; s_ntok[j] = a.pad; s_nsrc[j] = j; }
+    if (finished) a.done[b] = 1;
+  }
+  __syncwarp();
+  // ---- pool token rows (from the histories as they were before the permutation)
+  for (int q = 0; q < s_n_admit; ++q) {
+    const int slot = s_admit_slot[q];
+    if (slot < 0) continue;
+    long long* dst = a.pool_tok + ((long long)b * k + slot) * L;
+    for (int t = lane; t < L; t += 32) dst[t] = s_ids[s_admit_src[q]][t];
+  }
+  // ---- next beams: scores, source rows, tokens; histories and slot table permuted in place (business-local)
+  for (int j = lane; j < k; j += 32) {
+    a.beam_scores[row0 + j] = s_nscore[j];
+    a.beam_idx[row0 + j] = row0 + s_nsrc[j];
+    a.next_tok[row0 + j] = s_ntok[j];
+    if (a.next_tok32 != nullptr) a.next_tok32[row0 + j] = s_ntok[j];
+  }
+  for (int i = lane; i < k * L; i += 32) {
+    const int j = i / L, t = i % L;
+    a.ids[(long long)(row0 + j) * L + t] = (t == cur) ? (long long)s_ntok[j] : s_ids[s_nsrc[j]][t];
+  }
+  if (a.hist != nullptr)
+    for (int i = lane; i < k * 128; i += 32) a.hist[(long long)(row0 + (i >> 7)) * 128 + (i & 127)] = s_hist[s_nsrc[i >> 7]][i & 127];
+}
+
 }  // namespace mmsum
 
 using namespace mmsum;
+
+extern "C" int mmsum_beam_update(const float* cand_val, const int32_t* cand_tok, int64_t* ids, float* beam_scores, uint8_t* done,
+                                 float* pool_score, int64_t* pool_tok, int64_t* pool_len, int64_t* pool_n, const int64_t* cur_dev,
+                                 int64_t* beam_idx, int64_t* next_tok, int32_t* next_tok32, int32_t* hist, int32_t B, int32_t k,
+                                 int32_t K, int32_t L, int32_t eos, int32_t pad, int32_t early_stopping, float length_penalty,
+                                 void* stream_v) {
+  if (!cand_val || !cand_tok || !ids || !beam_scores || !done || !pool_score || !pool_tok || !pool_len || !pool_n || !cur_dev ||
+      !beam_idx || !next_tok) return MMSUM_ERR_INVALID;
+  if (B <= 0 || k <= 0 || k > kBuMaxK || K < k || K > kBuMaxCand || L < 2 || L > kBuMaxL) return MMSUM_ERR_INVALID;
+  BeamUpdateArgs a;
+  a.cand_val = cand_val; a.cand_tok = cand_tok; a.ids = reinterpret_cast<long long*>(ids); a.beam_scores = beam_scores; a.done = done;
+  a.pool_score = pool_score; a.pool_tok = reinterpret_cast<long long*>(pool_tok); a.pool_len = reinterpret_cast<long long*>(pool_len);
+  a.pool_n = reinterpret_cast<long long*>(pool_n); a.cur_dev = reinterpret_cast<const long long*>(cur_dev);
+  a.beam_idx = reinterpret_cast<long long*>(beam_idx); a.next_tok = reinterpret_cast<long long*>(next_tok); a.next_tok32 = next_tok32;
+  a.hist = hist; a.k = k; a.K = K; a.L = L; a.eos = eos; a.pad = pad; a.early_stopping = early_stopping; a.length_penalty = length_penalty;
+  beam_update_kernel<<<B, 32, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(a);
+  MMSUM_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int mmsum_beam_topk(const float* logits, int64_t ld, int32_t rows, int32_t V, const float* beam_scores,
                                const int64_t* ids, int32_t L, const int64_t* cur_dev, int32_t min_length, int32_t ngram,

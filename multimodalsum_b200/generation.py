@@ -73,7 +73,14 @@ class BeamSearch:
         self.beam_idx = torch.arange(N, device=dev)
         self.next_tok = torch.zeros(N, dtype=torch.long, device=dev)
         self.cand_val = self.cand_tok = None
-        self.use_kernel = True                                # fused candidate-selection kernel on CUDA (tests switch it off)
+        self.use_kernel = True                                # fused beam kernels on CUDA (tests switch them off)
+        self.kernel_path = False                              # set when a step went through the kernels
+        self.dec_ids32 = self.dec_hist = None                 # optional decoder hooks (see attach_decoder)
+
+    def attach_decoder(self, ids32, hist):
+        """The incremental decoder's next-token input [N] (int32) and self-attention slot table [N, 128] (int32): the beam
+        update kernel writes / permutes them directly, so no separate re-ordering pass is needed."""
+        self.dec_ids32, self.dec_hist = ids32, hist
 
     # -- hypothesis pool --------------------------------------------------------------------------------
     def _admit(self, active, score, tokens, length):
@@ -114,10 +121,14 @@ class BeamSearch:
                 self.cand_tok = torch.empty(B * k, 2 * k, device=self.dev, dtype=torch.int32)
             ops.beam_topk(logits, V, self.beam_scores, self.ids, cur, self.min_length, self.ngram, self.bos, self.eos, 2 * k,
                           self.cand_val, self.cand_tok)
-            cs, cj = torch.topk(self.cand_val.view(B, k * 2 * k), 2 * k, dim=1, largest=True, sorted=True)
-            tok = self.cand_tok.view(B, k * 2 * k).gather(1, cj).long()
-            src = self.row0 + cj // (2 * k)
-            return self._update(cs, tok, src)
+            # ... and the per-business bookkeeping (pools, next beams, history / slot-table permutation) in a second kernel
+            ops.beam_update(self.cand_val, self.cand_tok, self.ids, self.beam_scores, self.done, self.pool_score, self.pool_tok,
+                            self.pool_len, self.pool_n, cur, self.beam_idx, self.next_tok, self.dec_ids32, self.dec_hist, B, k,
+                            self.eos, self.pad, self.early_stopping, self.length_penalty)
+            self.kernel_path = True
+            cur.add_(1)
+            self.cur_len += 1
+            return self.beam_idx
         # adjust_logits_during_generation (:3084-3089): only BOS may follow the start token, only EOS may close the frame
         forced_now = (cur == 1) | (cur == L - 1)
         forced_tok = torch.where(cur == 1, self.bos_t, self.eos_t).expand(logits.shape[0], 1)
@@ -425,12 +436,15 @@ class Generator:
         w["rd"].copy_(rd.reshape(-1))
         w["ids"].copy_(bs.ids[:, 0])
 
+        bs.attach_decoder(w["ids"], w["hist"])
+
         def token_step():
             self._decode_launches(st)
             beam_idx = bs.advance(w["logits"])
-            torch.index_select(w["hist"], 0, beam_idx, out=w["hist_alt"])       # _reorder_cache: only the slot table moves
-            w["hist"].copy_(w["hist_alt"])
-            w["ids"].copy_(bs.next_tok)
+            if not bs.kernel_path:              # tensor-op beam update: re-rank the slot table / feed the tokens here
+                torch.index_select(w["hist"], 0, beam_idx, out=w["hist_alt"])   # _reorder_cache: only the slot table moves
+                w["hist"].copy_(w["hist_alt"])
+                w["ids"].copy_(bs.next_tok)
             w["pos_dev"].add_(1)
 
         max_length = kw["max_length"]

@@ -282,6 +282,15 @@ def beam_topk(logits, V, beam_scores, ids, cur_dev, min_length, ngram, bos, eos,
                                      _stream()), "mmsum_beam_topk")
 
 
+def beam_update(cand_val, cand_tok, ids, beam_scores, done, pool_score, pool_tok, pool_len, pool_n, cur_dev, beam_idx, next_tok,
+                next_tok32, hist, B, k, eos, pad, early_stopping, length_penalty):
+    """Per-business beam update of one token (see include/mmsum_b200.h); every argument is device state updated in place."""
+    check(_lib.lib().mmsum_beam_update(_ptr(cand_val), _ptr(cand_tok), _ptr(ids), _ptr(beam_scores), _ptr(done), _ptr(pool_score),
+                                       _ptr(pool_tok), _ptr(pool_len), _ptr(pool_n), _ptr(cur_dev), _ptr(beam_idx), _ptr(next_tok),
+                                       _ptr(next_tok32), _ptr(hist), B, k, cand_val.shape[1], ids.shape[1], eos, pad,
+                                       int(bool(early_stopping)), C.c_float(length_penalty), _stream()), "mmsum_beam_update")
+
+
 def prep_step(reviews, reviews_mask, rating, table_valid, img_mask, **kw):
     a = _lib.PrepArgs()
     for k, v in kw.items():

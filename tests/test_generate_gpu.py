@@ -178,8 +178,9 @@ def test_beam_candidate_kernel_matches_tensor_implementation(k, V, ngram, min_le
         logits.copy_(torch.randn(N, V, device="cuda") * 3)
         logits[:, 2] += 4.0                          # EOS is competitive: hypotheses finish along the way
         logits[:, 3:6] += 6.0                        # a few dominant tokens: repeated n-grams get banned
-        ia = a.advance(logits.clone())
-        ib = b.advance(logits.clone())
+        ia = a.advance(logits)
+        ib = b.advance(logits)
+        assert a.kernel_path and not b.kernel_path
         assert torch.equal(a.done, b.done), step
         live = (~a.done).repeat_interleave(k)
         assert torch.equal(ia[live], ib[live]) and torch.equal(a.ids[live], b.ids[live]), step
