@@ -77,6 +77,22 @@ class BeamSearch:
         self.kernel_path = False                              # set when a step went through the kernels
         self.dec_ids32 = self.dec_hist = None                 # optional decoder hooks (see attach_decoder)
 
+    def reset(self):
+        """Back to the start state, in place (the buffers are baked into a recorded CUDA graph)."""
+        self.ids.fill_(self.pad)
+        self.ids[:, 0] = self.eos
+        self.cur_len = 1
+        self.cur_t.fill_(1)
+        bs = self.beam_scores.view(self.B, self.k)
+        bs.zero_()
+        bs[:, 1:] = -1e9
+        self.done.zero_()
+        self.pool_score.fill_(NEG)
+        self.pool_tok.fill_(self.pad)
+        self.pool_len.zero_()
+        self.pool_n.zero_()
+        self.kernel_path = False
+
     def attach_decoder(self, ids32, hist):
         """The incremental decoder's next-token input [N] (int32) and self-attention slot table [N, 128] (int32): the beam
         update kernel writes / permutes them directly, so no separate re-ordering pass is needed."""
@@ -248,15 +264,24 @@ class Generator:
     def __init__(self, model):
         self.model = model
         self.eng = None
+        self._plans = {}
 
     def _engine(self, device):
-        self.eng = self.model._ensure_engine(device)
+        eng = self.model._ensure_engine(device)
+        if eng is not self.eng:
+            self._plans.clear()               # recorded graphs hold the previous engine's arena pointers
+        self.eng = eng
         return self.eng
 
     # ------------------------------------------------------------------ memory
     @torch.no_grad()
     def encode(self, reviews, reviews_mask, field, field_value, img, img_mask, num_beams):
         """MultimodalSum.get_multimodal_outputs (src/multimodal_train.py:165-193) + the per-layer cross K|V projection."""
+        return self.prepare(self.encode_memory(reviews, reviews_mask, field, field_value, img, img_mask), num_beams)
+
+    @torch.no_grad()
+    def encode_memory(self, reviews, reviews_mask, field, field_value, img, img_mask):
+        """get_multimodal_outputs -> packed cross-attention memory (not yet projected to K|V)."""
         eng = self._engine(reviews.device)
         eng.refresh_bf16_weights()
         B, R, S = reviews.shape
@@ -268,7 +293,7 @@ class Generator:
             imgh = INF.image_forward(eng, img)
             imask = img_mask.reshape(B, -1, 1).expand(-1, -1, imgh.shape[2])
             mem = INF.build_memory(eng, [text, tab.unsqueeze(1), imgh], [reviews_mask, tab_valid.unsqueeze(1), imask])
-        return self.prepare(mem, num_beams)
+        return mem
 
     @torch.no_grad()
     def prepare(self, mem, num_beams):
@@ -419,24 +444,66 @@ class Generator:
         w["hist"].copy_(w["hist_alt"])
 
     # ------------------------------------------------------------------ fused token loop (one CUDA graph per token)
-    @torch.no_grad()
-    def _fused_beam_search(self, st, rd, poll_every=8, **kw):
-        """Decoder step + beam update + cache re-ranking of one token recorded ONCE and replayed: the host issues a single
-        graph launch per token (the reference runs ~47 k eager ops and several host syncs per token, :2857-3010).  The first
-        token runs kernel by kernel (one-time function attributes, allocator warm-up), the capture follows it."""
-        import os
-        cfg, mem = self.eng.cfg, st.mem
+    def _plan(self, mem, k, kw):
+        """Static buffers + the recorded token step for one (memory layout, beam-search setting): the K|V projections of a
+        new memory are written into the plan's buffers and the same CUDA graph is replayed — capture and instantiation
+        (~0.15 s for ~220 nodes) are paid once per shape, not once per generate() call."""
+        cfg = self.eng.cfg
         dev = mem.MEM.device
-        B, k = mem.B, st.beams
-        N = B * k
-        bs = BeamSearch(B, cfg.vocab_size, dev, k, kw["max_length"], kw["min_length"], kw["length_penalty"], kw["no_repeat_ngram_size"],
-                        kw["early_stopping"], cfg.pad_token_id, cfg.bos_token_id, cfg.eos_token_id)
-        st.cws = w = self._decode_ws(st, N, dev)
-        w["fused"] = True
+        key = (mem.B, k, tuple(mem.mods), mem.MEM.shape[0], mem.Et, mem.pres is None, kw["max_length"], kw["min_length"],
+               float(kw["length_penalty"]), kw["no_repeat_ngram_size"], bool(kw["early_stopping"]), str(dev))
+        plan = self._plans.get(key)
+        if plan is not None:
+            return plan
+        D, L = cfg.d_model, cfg.decoder_layers
+        smem = INF.Memory(MEM=mem.MEM[:0], B=mem.B, mods=list(mem.mods), mem_valid=torch.empty_like(mem.mem_valid),
+                          ent_valid=torch.empty_like(mem.ent_valid), inv_n=torch.empty_like(mem.inv_n),
+                          pres=None if mem.pres is None else torch.empty_like(mem.pres), Et=mem.Et,
+                          kv=[torch.empty(mem.MEM.shape[0], 2 * D, device=dev, dtype=torch.bfloat16) for _ in range(L)])
+        st = DecodeState(smem, k)
+        N = mem.B * k
+        st.cws = self._decode_ws(st, N, dev)
+        st.cws["fused"] = True
+        bs = BeamSearch(mem.B, cfg.vocab_size, dev, k, kw["max_length"], kw["min_length"], kw["length_penalty"],
+                        kw["no_repeat_ngram_size"], kw["early_stopping"], cfg.pad_token_id, cfg.bos_token_id, cfg.eos_token_id)
+        bs.attach_decoder(st.cws["ids"], st.cws["hist"])
+        plan = dict(st=st, bs=bs, graph=None, captured=False)
+        if len(self._plans) >= 4:                     # a handful of shapes at most; drop the oldest
+            self._plans.pop(next(iter(self._plans)))
+        self._plans[key] = plan
+        return plan
+
+    @torch.no_grad()
+    def _fused_beam_search(self, mem, rd, poll_every=8, **kw):
+        """Decoder step + beam update + cache re-ranking of one token recorded ONCE and replayed: the host issues a single
+        graph launch per token (the reference runs ~47 k eager ops and several host syncs per token, :2857-3010).  The very
+        first token of a new shape runs kernel by kernel (one-time function attributes, allocator warm-up), the capture
+        follows it; later calls with the same shape replay the graph from the first token on."""
+        import os
+        eng = self.eng
+        cfg = eng.cfg
+        k = kw.pop("num_beams")
+        plan = self._plan(mem, k, kw)
+        st, bs = plan["st"], plan["bs"]
+        w, smem = st.cws, st.mem
+        # ---- this call's memory: validity bookkeeping copied, K|V projected straight into the plan's buffers
+        smem.mem_valid.copy_(mem.mem_valid); smem.ent_valid.copy_(mem.ent_valid); smem.inv_n.copy_(mem.inv_n)
+        if smem.pres is not None:
+            smem.pres.copy_(mem.pres)
+        w["inv_n"].copy_(mem.inv_n.repeat_interleave(k, dim=0))
+        for l in range(cfg.decoder_layers):
+            c = "bart_model.model.decoder.layers.%d.encoder_attn." % l
+            if mem.kv:
+                smem.kv[l].copy_(mem.kv[l])
+            else:
+                ops.gemm(mem.MEM, eng.w16(c + "k_proj.weight", c + "v_proj.weight"), smem.kv[l],
+                         bias=eng.w32(c + "k_proj.bias", c + "v_proj.bias"))
+        # ---- reset the per-call state in place
+        bs.reset()
         w["rd"].copy_(rd.reshape(-1))
         w["ids"].copy_(bs.ids[:, 0])
-
-        bs.attach_decoder(w["ids"], w["hist"])
+        w["pos_dev"].zero_()
+        w["hist"].zero_()
 
         def token_step():
             self._decode_launches(st)
@@ -450,21 +517,22 @@ class Generator:
         max_length = kw["max_length"]
         if max_length <= 1:
             return bs.finalize()
-        token_step()
-        graph = None
-        if bs.cur_len < max_length and os.environ.get("MMSUM_DECODE_GRAPH", "1") != "0":
-            try:
+        if not plan["captured"]:
+            plan["captured"] = True
+            token_step()
+            if bs.cur_len < max_length and os.environ.get("MMSUM_DECODE_GRAPH", "1") != "0":
                 host_len = bs.cur_len
-                g = torch.cuda.CUDAGraph()
-                torch.cuda.synchronize()
-                with torch.cuda.graph(g):
-                    token_step()
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(g):
+                        token_step()
+                    plan["graph"] = g
+                except Exception as e:            # noqa: BLE001 — same kernels, launched one by one
+                    import warnings
+                    warnings.warn("CUDA-graph capture of the token step failed (%s); launching kernel by kernel" % (e,))
                 bs.cur_len = host_len             # the capture ran the Python bookkeeping once without executing anything
-                graph = g
-            except Exception as e:                # noqa: BLE001 — same kernels, launched one by one
-                import warnings
-                warnings.warn("CUDA-graph capture of the token step failed (%s); launching kernel by kernel" % (e,))
-                bs.cur_len = host_len
+        graph = plan["graph"]
         self.last_used_graph = graph is not None
         flag = torch.zeros(1, dtype=torch.bool, pin_memory=True)
         ev = None
@@ -491,15 +559,18 @@ class Generator:
                              no_repeat_ngram_size=3, early_stopping=True, use_cache=True):
         """`bart_model.generate(text_hiddens, ..., rating_diff=..., num_beams=...)` as src/test.py:156-158 calls it."""
         cfg = self.model.cfg
-        st = self.prepare(mem, num_beams)
         B, dev = mem.B, mem.MEM.device
         rd = torch.zeros(B, device=dev) if rating_diff is None else rating_diff.reshape(B).float()
         rd = rd.repeat_interleave(num_beams).contiguous()
         if num_beams > 8:
             use_cache = False                     # the decode attention kernel holds up to 8 beams per business
         if use_cache:
-            return self._fused_beam_search(st, rd, max_length=max_length, min_length=min_length, length_penalty=length_penalty,
-                                           no_repeat_ngram_size=no_repeat_ngram_size, early_stopping=early_stopping)
+            eng = self._engine(dev)
+            eng.refresh_bf16_weights()
+            return self._fused_beam_search(mem, rd, num_beams=num_beams, max_length=max_length, min_length=min_length,
+                                           length_penalty=length_penalty, no_repeat_ngram_size=no_repeat_ngram_size,
+                                           early_stopping=early_stopping)
+        st = self.prepare(mem, num_beams)
         logits_fn, reorder_fn = (lambda ids: self.last_logits(st, ids, rd)), None
         return beam_search(logits_fn, B, cfg.vocab_size, dev, num_beams=num_beams, max_length=max_length, min_length=min_length,
                            length_penalty=length_penalty, no_repeat_ngram_size=no_repeat_ngram_size, early_stopping=early_stopping,
@@ -509,5 +580,5 @@ class Generator:
     def generate(self, reviews, reviews_mask, field, field_value, img, img_mask, rating_diff=None, **kw):
         """get_multimodal_outputs + generate in one call.  use_cache=True: incremental decoding with self-attention K|V
         caches (`step_logits`); False: recompute the whole prefix every step (`last_logits`)."""
-        st = self.encode(reviews, reviews_mask, field, field_value, img, img_mask, kw.get("num_beams", 4))
-        return self.generate_from_memory(st.mem, rating_diff, **kw)
+        mem = self.encode_memory(reviews, reviews_mask, field, field_value, img, img_mask)
+        return self.generate_from_memory(mem, rating_diff, **kw)

@@ -219,7 +219,11 @@ class _BartLMBase(nn.Module, _EngineRoot):
                     length_penalty=1.0 if kw.get("length_penalty") is None else kw["length_penalty"],
                     no_repeat_ngram_size=kw.get("no_repeat_ngram_size") or 0,
                     early_stopping=bool(kw.get("early_stopping")), use_cache=kw.get("use_cache") is not False)
-        return Generator(root).generate_from_memory(mem, rating_diff, **args)
+        gen = getattr(root, "_generator", None)
+        if gen is None:                       # one Generator per model: it caches the recorded token-step graphs per shape
+            gen = Generator(root)
+            object.__setattr__(root, "_generator", gen)
+        return gen.generate_from_memory(mem, rating_diff, **args)
 
 
 class BartForMultiEncConditionalGeneration(_BartLMBase):

