@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--dataset", default=None, choices=["yelp", "amazon"], help="alias of --workload (round-1 flag)")
     ap.add_argument("--businesses", type=int, default=None, help="businesses per GPU (train: 16, generate: 64)")
     ap.add_argument("--max-length", type=int, default=128, help="generate: decoder frame (src/test.py --max_length)")
+    ap.add_argument("--graph", action="store_true", help="train workloads: replay forward / backward from recorded CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the Amazon / generation workloads appended to the default run")
     ap.add_argument("--cpu-seconds", type=float, default=240.0, help="time budget of the reference arm")
@@ -308,6 +309,8 @@ def run_train(args):
             opt[0].step(lr=1e-5)
         return loss
 
+    if args.graph and world == 1:
+        model.enable_cuda_graph()
     step(resident)                                          # builds the engine, arenas and workspaces
     eng = model.engine
     reducer = GradAllReducer(eng) if world > 1 else None    # noqa: F841 (hooks the engine)
@@ -410,6 +413,7 @@ def run_train(args):
     cfg_line = train_config(args, world)
     cfg_line.update({"step": "fwd + bwd%s + fused clip/AdamW" % (" + bucketed NCCL grad all-reduce overlapped with backward" if world > 1 else ""),
                      "parallelism": "dp%d" % world,
+                     "cuda_graph": bool(args.graph and world == 1),
                      "l2_policy": "per-step working set (>25 GB activations + 2.8 GB weights) exceeds the 126 MB L2",
                      "final_loss": final_loss})
     tensor_ms = sum(agg[k][2] for k in TENSOR_KINDS if k in agg) / n_inst

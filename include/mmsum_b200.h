@@ -122,9 +122,12 @@ int mmsum_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 /* out = dropout(LN(E[ids] + P[t+2] + rating_diff[seq]*remb)): BartEncoder.forward modeling_multimodalsum.py:368-372,
  * BartDecoder.forward :588-597, LearnedPositionalEmbedding :961-969.  rating_diff/remb NULL for the encoder. */
+/* Dropout masks are a pure function of (seed, stream_id + 4096 * step, element index); `step_dev` (optional) points to a
+ * device-resident step counter read inside the kernel, so a recorded CUDA graph of the step draws fresh masks at every replay. */
 int mmsum_embed_ln_fwd(const int32_t* ids, const float* E, const float* P, const float* rating_diff, const float* remb,
                        const float* gamma, const float* beta, void* out, float* mean, float* rstd, int32_t rows,
-                       int32_t S, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+                       int32_t S, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, const uint32_t* step_dev,
+                       void* stream);
 /* decode step (eval, one token per hypothesis): as above with S = 1, every row at decoder position pos_dev[0] (device
  * memory, so the launch can be replayed from a CUDA graph); the cached branch of BartDecoder.forward :583-597, :964-965 */
 int mmsum_embed_ln_decode(const int32_t* ids, const float* E, const float* P, const float* rating_diff, const float* remb,
@@ -134,16 +137,18 @@ int mmsum_embed_ln_decode(const int32_t* ids, const float* E, const float* P, co
 int mmsum_embed_ln_bwd(const void* dout, const void* dout2 /* optional addend */, const int32_t* ids, const float* E, const float* P, const float* rating_diff,
                        const float* remb, const float* gamma, const float* mean, const float* rstd, float* dE, float* dP,
                        float* dremb, float* dgamma, float* dbeta, float* dz_scratch, int32_t rows, int32_t S,
-                       int32_t d_model, int32_t pad_id, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+                       int32_t d_model, int32_t pad_id, float p_drop, uint64_t seed, uint32_t stream_id, const uint32_t* step_dev,
+                       void* stream);
 
 /* out = LN(res + dropout(y)): the post-LN residual blocks of EncoderLayer.forward :288-308 / DecoderLayer.forward :442-489
  * (LayerNorm factory :972-980, eps 1e-5).  Dropout masks are a pure function of (seed, stream_id, element). */
 int mmsum_add_ln_fwd(const void* res, const void* y, const float* gamma, const float* beta, void* out, float* mean,
-                     float* rstd, int32_t rows, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+                     float* rstd, int32_t rows, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id,
+                     const uint32_t* step_dev, void* stream);
 /* backward: upstream = d1 (+ d2 if not NULL); dres = dz, dy = dz * mask (may alias dres when p_drop == 0); dgamma/dbeta += */
 int mmsum_add_ln_bwd(const void* d1, const void* d2, const void* res, const void* y, const float* gamma, const float* mean,
                      const float* rstd, void* dres, void* dy, float* dgamma, float* dbeta, int32_t rows, int32_t d_model,
-                     float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+                     float p_drop, uint64_t seed, uint32_t stream_id, const uint32_t* step_dev, void* stream);
 
 /* out[n] += sum_r x[r,n]  (bias gradients) */
 int mmsum_colsum(const void* x, int64_t ld, int32_t rows, int32_t N, float* out, void* stream);

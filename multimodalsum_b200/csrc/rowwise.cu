@@ -12,11 +12,17 @@ static constexpr int D = 1024;          // d_model (fixed by the reference's tab
 static constexpr int VPL = D / 32;      // values per lane = 32
 static constexpr float kEps = 1e-5f;
 
-struct DropCfg { unsigned long long seed; uint32_t stream; uint32_t thr16; float scale; };
-__host__ inline DropCfg make_drop(float p, unsigned long long seed, uint32_t stream) {
-  DropCfg d; d.seed = seed; d.stream = stream;
+// step_dev (optional): device-resident step counter folded into the stream id inside the kernel, so that a recorded CUDA graph
+// of the training step draws fresh masks at every replay (the stream id passed by value would be baked into the graph)
+struct DropCfg { unsigned long long seed; uint32_t stream; uint32_t thr16; float scale; const uint32_t* step_dev; };
+__host__ inline DropCfg make_drop(float p, unsigned long long seed, uint32_t stream, const uint32_t* step_dev = nullptr) {
+  DropCfg d; d.seed = seed; d.stream = stream; d.step_dev = step_dev;
   if (p <= 0.f) { d.thr16 = 65536; d.scale = 1.f; }
   else { uint32_t t = (uint32_t)((1.0 - (double)p) * 65536.0 + 0.5); if (t < 1) t = 1; d.thr16 = t; d.scale = 65536.f / (float)t; }
+  return d;
+}
+__device__ __forceinline__ DropCfg resolve_drop(DropCfg d) {
+  if (d.step_dev != nullptr && d.thr16 < 65536) d.stream += d.step_dev[0] * 4096u;
   return d;
 }
 // dropout multiplier for elements (idx, idx+1) of a tensor; idx even
@@ -92,7 +98,8 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int* __restrict
                                                            const float* __restrict__ remb, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, bf16* __restrict__ out,
                                                            float* __restrict__ mean_o, float* __restrict__ rstd_o,
-                                                           int rows, int S, DropCfg dc, const int* __restrict__ pos_dev) {
+                                                           int rows, int S, DropCfg dc_in, const int* __restrict__ pos_dev) {
+  const DropCfg dc = resolve_drop(dc_in);
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -131,7 +138,8 @@ __global__ void __launch_bounds__(256) embed_ln_bwd_kernel(const bf16* __restric
                                                            const float* __restrict__ gamma, const float* __restrict__ mean_i,
                                                            const float* __restrict__ rstd_i, float* __restrict__ dE,
                                                            float* __restrict__ dz_out, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, int rows, int S, int pad_id, DropCfg dc) {
+                                                           float* __restrict__ dbeta, int rows, int S, int pad_id, DropCfg dc_in) {
+  const DropCfg dc = resolve_drop(dc_in);
   __shared__ float sg[8][D / 4];  // staged reduction of dgamma / dbeta across the block's warps (two passes of D/4... see below)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float ag[VPL], ab[VPL];
@@ -226,9 +234,10 @@ __global__ void __launch_bounds__(256) embed_pos_bwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256, 2) add_ln_fwd_kernel(const bf16* __restrict__ res, const bf16* __restrict__ y,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             bf16* __restrict__ out, float* __restrict__ mean_o,
-                                                            float* __restrict__ rstd_o, int rows, DropCfg dc) {
+                                                            float* __restrict__ rstd_o, int rows, DropCfg dc_in) {
   pdl_launch_dependents();
   pdl_wait();
+  const DropCfg dc = resolve_drop(dc_in);
   const int lane = threadIdx.x & 31;
   const int stride = gridDim.x * (blockDim.x >> 5);
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -292,9 +301,10 @@ __global__ void __launch_bounds__(128, 3) add_ln_bwd_kernel(const bf16* __restri
                                                             const float* __restrict__ gamma, const float* __restrict__ mean_i,
                                                             const float* __restrict__ rstd_i, bf16* __restrict__ dres,
                                                             bf16* __restrict__ dy_out, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int rows, DropCfg dc) {
+                                                            float* __restrict__ dbeta, int rows, DropCfg dc_in) {
   pdl_launch_dependents();
   pdl_wait();
+  const DropCfg dc = resolve_drop(dc_in);
   extern __shared__ float sacc[];                      // [4 warps][2][VPL][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float* sg = sacc + warp * (2 * VPL * 32);
@@ -860,11 +870,11 @@ extern "C" int mmsum_cast_f32_bf16(const float* src, void* dst, int64_t n, void*
 extern "C" int mmsum_embed_ln_fwd(const int32_t* ids, const float* E, const float* P, const float* rating_diff,
                                   const float* remb, const float* gamma, const float* beta, void* out, float* mean,
                                   float* rstd, int32_t rows, int32_t S, int32_t d_model, float p_drop, uint64_t seed,
-                                  uint32_t stream_id, void* stream) {
+                                  uint32_t stream_id, const uint32_t* step_dev, void* stream) {
   if (d_model != D || rows <= 0 || S <= 0 || !ids || !E || !P || !out) return MMSUM_ERR_INVALID;
   embed_ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, STREAM(stream)>>>(ids, E, P, rating_diff, remb, gamma, beta,
                                                                    reinterpret_cast<bf16*>(out), mean, rstd, rows, S,
-                                                                   make_drop(p_drop, seed, stream_id), nullptr);
+                                                                   make_drop(p_drop, seed, stream_id, step_dev), nullptr);
   MMSUM_CHECK_LAUNCH();
   return 0;
 }
@@ -884,12 +894,12 @@ extern "C" int mmsum_embed_ln_bwd(const void* dout, const void* dout2, const int
                                   const float* rating_diff, const float* remb, const float* gamma, const float* mean,
                                   const float* rstd, float* dE, float* dP, float* dremb, float* dgamma, float* dbeta,
                                   float* dz_scratch, int32_t rows, int32_t S, int32_t d_model, int32_t pad_id,
-                                  float p_drop, uint64_t seed, uint32_t stream_id, void* stream) {
+                                  float p_drop, uint64_t seed, uint32_t stream_id, const uint32_t* step_dev, void* stream) {
   if (d_model != D || rows <= 0 || S <= 0 || rows % S || !dz_scratch) return MMSUM_ERR_INVALID;
   embed_ln_bwd_kernel<<<nblocks(rows, 8 * 4, 148 * 4), 256, 0, STREAM(stream)>>>(
       reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(dout2), ids, E, P, rating_diff, remb, gamma, mean,
       rstd, dE, dz_scratch, dgamma, dbeta,
-      rows, S, pad_id, make_drop(p_drop, seed, stream_id));
+      rows, S, pad_id, make_drop(p_drop, seed, stream_id, step_dev));
   MMSUM_CHECK_LAUNCH();
   embed_pos_bwd_kernel<<<dim3(D / 256, S), 256, 0, STREAM(stream)>>>(dz_scratch, rating_diff, dP, dremb, rows / S, S);
   MMSUM_CHECK_LAUNCH();
@@ -898,19 +908,20 @@ extern "C" int mmsum_embed_ln_bwd(const void* dout, const void* dout2, const int
 
 extern "C" int mmsum_add_ln_fwd(const void* res, const void* y, const float* gamma, const float* beta, void* out,
                                 float* mean, float* rstd, int32_t rows, int32_t d_model, float p_drop, uint64_t seed,
-                                uint32_t stream_id, void* stream) {
+                                uint32_t stream_id, const uint32_t* step_dev, void* stream) {
   if (d_model != D || rows <= 0 || !res || !y || !out) return MMSUM_ERR_INVALID;
   MMSUM_LAUNCH_PDL(add_ln_fwd_kernel, nblocks(rows, 8, 148 * 2), 256, 0, STREAM(stream), reinterpret_cast<const bf16*>(res),
                                                                  reinterpret_cast<const bf16*>(y), gamma, beta,
                                                                  reinterpret_cast<bf16*>(out), mean, rstd, rows,
-                                                                 make_drop(p_drop, seed, stream_id));
+                                                                 make_drop(p_drop, seed, stream_id, step_dev));
   MMSUM_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int mmsum_add_ln_bwd(const void* d1, const void* d2, const void* res, const void* y, const float* gamma,
                                 const float* mean, const float* rstd, void* dres, void* dy, float* dgamma, float* dbeta,
-                                int32_t rows, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, void* stream) {
+                                int32_t rows, int32_t d_model, float p_drop, uint64_t seed, uint32_t stream_id, const uint32_t* step_dev,
+                                void* stream) {
   if (d_model != D || rows <= 0 || !d1 || !res || !y || !dres || !dy) return MMSUM_ERR_INVALID;
   if (p_drop > 0.f && dres == dy) return MMSUM_ERR_INVALID;
   static std::atomic<unsigned long long> attr{0};
@@ -918,7 +929,7 @@ extern "C" int mmsum_add_ln_bwd(const void* d1, const void* d2, const void* res,
   MMSUM_LAUNCH_PDL(add_ln_bwd_kernel, nblocks(rows, 4 * 4, 148 * 3), 128, 4 * 2 * VPL * 32 * 4, STREAM(stream), 
       reinterpret_cast<const bf16*>(d1), reinterpret_cast<const bf16*>(d2), reinterpret_cast<const bf16*>(res),
       reinterpret_cast<const bf16*>(y), gamma, mean, rstd, reinterpret_cast<bf16*>(dres), reinterpret_cast<bf16*>(dy),
-      dgamma, dbeta, rows, make_drop(p_drop, seed, stream_id));
+      dgamma, dbeta, rows, make_drop(p_drop, seed, stream_id, step_dev));
   MMSUM_CHECK_LAUNCH();
   return 0;
 }

@@ -108,6 +108,9 @@ class StepEngine:
         self.fwd_generation = 0          # bumped by every forward; backward refuses to run on a stale workspace
         self.dropout = cfg.dropout
         self.grad_ready_hook = None      # callable(lo, hi): gradient arena range [lo, hi) is final (data-parallel buckets)
+        self.graph_mode = False          # replay forward / backward from recorded CUDA graphs (see forward_step)
+        self._graphs = {}
+        self._graph_entry = None
         self._w16_fresh = False          # True only right after a fused optimizer wrote W16 itself
         self._w16_versions = -1
         self.anchor = None
@@ -150,6 +153,7 @@ class StepEngine:
                 p.data = v
                 self.params[n] = p
         self.anchor = torch.zeros(1, device=dev, requires_grad=True)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)     # dropout step counter, incremented by every forward
         self.bound = True
         self._w16_fresh = False
 
@@ -281,7 +285,8 @@ class StepEngine:
 
     # ------------------------------------------------------------------ helpers
     def _sid(self, kind, layer):
-        return (self.step_count * 4096 + kind * 64 + layer) & 0xFFFFFFFF
+        # the step number is added inside the kernels from the device-resident counter `step_dev` (graph-replayable)
+        return kind * 64 + layer
 
     def _self_attn_args(self, w, qkv, out, lse, key_valid, causal, bwd=None):
         D, H, S = self.cfg.d_model, self.cfg.heads, w["S"]
@@ -336,7 +341,77 @@ class StepEngine:
         cnt = ent.sum(dim=1).float()
         w["inv_n"].copy_(torch.where(cnt > 0, 1.0 / cnt.clamp(min=1), torch.zeros_like(cnt))[:, None])
 
-    def forward(self, batch, label_smoothing=0.1, training=True):
+    # ------------------------------------------------------------------ CUDA-graph replay of the step
+    def enable_graph(self, on=True):
+        """Record forward and backward of a step shape once and replay them.  The step takes everything that
+        changes between steps from device memory — inputs are copied into static buffers, the dropout step counter lives on the
+        device, the upstream gradient is a device scalar — so a replay is two graph launches instead of ~940 kernel launches.
+        It pays where the step is launch-bound (the reference's default of ONE business per GPU); at 16 businesses the step is
+        GPU-bound either way.  Semantics in graph mode: gradients are zeroed at the start of every backward (= the
+        `optimizer.zero_grad()` of src/multimodal_train.py:359), and a data-parallel reducer (NCCL inside the backward) keeps the
+        step on plain launches."""
+        self.graph_mode = bool(on)
+        self._graphs = {}
+        self._graph_entry = None
+
+    @staticmethod
+    def _batch_key(batch):
+        return tuple((tuple(t.shape), str(t.dtype)) for t in batch.tensors())
+
+    def forward_step(self, batch, label_smoothing, training):
+        """`forward` behind the autograd node: plain launches, or warm-up -> capture -> replay in graph mode."""
+        self._graph_entry = None
+        if not self.graph_mode or self.grad_ready_hook is not None or self.device.type != "cuda":
+            return self.forward(batch, label_smoothing, training)
+        key = (self._batch_key(batch), bool(training), label_smoothing)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            from .synth import Batch
+            cl = lambda t: None if t is None else t.clone()
+            ent = dict(static=Batch(cl(batch.reviews), cl(batch.reviews_mask), cl(batch.reviews_rating), cl(batch.field),
+                                    [cl(t) for t in batch.field_value], cl(batch.img), cl(batch.img_mask), cl(batch.labels)),
+                       warm=False, gout=torch.ones(1, device=self.device))
+            self._graphs[key] = ent
+        for dst, src in zip(ent["static"].tensors(), batch.tensors()):
+            dst.copy_(src)
+        self.refresh_bf16_weights()                       # host-side decision: stays outside the recorded graph
+        self._graph_entry = ent
+        if not ent["warm"]:                               # first step of a shape: plain launches (one-time attributes, workspaces)
+            ent["warm"] = True
+            ent["eager"] = True
+            return self.forward(ent["static"], label_smoothing, training, refresh=False)
+        ent["eager"] = False
+        if "fwd" not in ent:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self.forward(ent["static"], label_smoothing, training, refresh=False)
+            ent["fwd"] = g
+        else:
+            self.fwd_generation += 1
+            self.step_count += 1
+        ent["fwd"].replay()
+        return self.ws["loss"]
+
+    def backward_step(self, grad_out):
+        ent = self._graph_entry
+        if ent is None or ent.get("eager", True):
+            return self.backward(grad_out)
+        ent["gout"].copy_(grad_out.reshape(1))
+        if "bwd" not in ent:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self.backward(ent["gout"], force_zero=True)
+            ent["bwd"] = g
+        ent["bwd"].replay()
+        for n, p in self.params.items():
+            if p.grad is None:
+                p.grad = self.g32(n)
+
+    def forward(self, batch, label_smoothing=0.1, training=True, refresh=True):
         """batch: synth.Batch on the device.  Returns the scalar loss tensor (fp32, device)."""
         if not self.bound:
             raise RuntimeError("engine.bind(named_parameters) first")
@@ -355,13 +430,15 @@ class StepEngine:
         T, Tt, Tm = w["T"], w["Tt"], w["Tm"]
         w["batch"] = batch                 # backward re-reads the bit-code table fields
         self.step_count += 1
+        self.step_dev.add_(1)
         self.fwd_generation += 1
         self.training = training
         pd = self.dropout if training else 0.0
         self.pd = pd
         self.label_smoothing = label_smoothing
         seed = self.seed
-        self.refresh_bf16_weights()
+        if refresh:
+            self.refresh_bf16_weights()
         bm = "bart_model.model."
         g = ops.gemm
 
@@ -407,7 +484,7 @@ class StepEngine:
             x = w["enc_x0"]
             ops.embed_ln_fwd(w["enc_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"), None, None,
                              self.w32(pre + "layernorm_embedding.weight"), self.w32(pre + "layernorm_embedding.bias"),
-                             x, w["enc_m0"], w["enc_r0"], T, S, pd, seed, self._sid(0, 0))
+                             x, w["enc_m0"], w["enc_r0"], T, S, pd, seed, self._sid(0, 0), step_dev=self.step_dev)
             L_e = cfg.encoder_layers
             for l in range(L_e):
                 a = w["enc"][l]
@@ -425,7 +502,7 @@ class StepEngine:
         ops.embed_ln_fwd(w["dec_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"),
                          w["rating_diff"], self.w32(pre + "rating_embeddings"),
                          self.w32(pre + "layernorm_embedding.weight"), self.w32(pre + "layernorm_embedding.bias"),
-                         x, w["dec_m0"], w["dec_r0"], T, S, pd, seed, self._sid(3, 0))
+                         x, w["dec_m0"], w["dec_r0"], T, S, pd, seed, self._sid(3, 0), step_dev=self.step_dev)
         for l in range(L_d):
             a = w["dec"][l]
             lp = pre + "layers.%d." % l
@@ -447,7 +524,7 @@ class StepEngine:
             else:
                 yc = a["O3"][0]
             ops.add_ln_fwd(a["x1"], yc, self.w32(lp + "encoder_attn_layer_norm.weight"), self.w32(lp + "encoder_attn_layer_norm.bias"),
-                           a["x2"], a["m2"], a["r2"], pd, seed, self._sid(5, l))
+                           a["x2"], a["m2"], a["r2"], pd, seed, self._sid(5, l), step_dev=self.step_dev)
             self._ffn_block_fwd(a, lp, a["x2"], out, "m3", "r3", l, 6)
             x = out
 
@@ -468,7 +545,7 @@ class StepEngine:
         ops.attn_fwd(self._self_attn_args(w, a["qkv"], a["ctx"], a["lse"], key_valid, causal))
         g(a["ctx"], self.w16(s + "out_proj.weight"), a["o"], bias=self.w32(s + "out_proj.bias"))
         ops.add_ln_fwd(x, a["o"], self.w32(lp + "self_attn_layer_norm.weight"), self.w32(lp + "self_attn_layer_norm.bias"),
-                       a["x1"], a["m1"], a["r1"], self.pd, self.seed, self._sid(kind, l))
+                       a["x1"], a["m1"], a["r1"], self.pd, self.seed, self._sid(kind, l), step_dev=self.step_dev)
 
     def _ffn_block_fwd(self, a, lp, xin, out, mk, rk, l, kind):
         g = ops.gemm
@@ -476,7 +553,7 @@ class StepEngine:
           aux_mode=ops.AUX_STORE_PREACT)
         g(a["a"], self.w16(lp + "fc2.weight"), a["f"], bias=self.w32(lp + "fc2.bias"))
         ops.add_ln_fwd(xin, a["f"], self.w32(lp + "final_layer_norm.weight"), self.w32(lp + "final_layer_norm.bias"),
-                       out, a[mk], a[rk], self.pd, self.seed, self._sid(kind, l))
+                       out, a[mk], a[rk], self.pd, self.seed, self._sid(kind, l), step_dev=self.step_dev)
 
     # ------------------------------------------------------------------ backward
     def _wgrad(self, dy, x, gname, gname2=None, col_slice=None):
@@ -520,7 +597,7 @@ class StepEngine:
         df = pool.get() if pd > 0 else dres
         ops.add_ln_bwd(d1, d2, xin, a["f"], self.w32(lp + "final_layer_norm.weight"), a[mk], a[rk], dres, df,
                        self.g32(lp + "final_layer_norm.weight"), self.g32(lp + "final_layer_norm.bias"), pd, self.seed,
-                       self._sid(kind, l))
+                       self._sid(kind, l), step_dev=self.step_dev)
         pool.put(d1, d2)
         self._bias_grad(df, self.g32(lp + "fc2.bias"))
         self._wgrad(df, a["a"], lp + "fc2.weight")
@@ -542,7 +619,7 @@ class StepEngine:
         do = pool.get() if pd > 0 else dres
         ops.add_ln_bwd(d1, d2, a["x"], a["o"], self.w32(lp + "self_attn_layer_norm.weight"), a["m1"], a["r1"], dres, do,
                        self.g32(lp + "self_attn_layer_norm.weight"), self.g32(lp + "self_attn_layer_norm.bias"), pd, self.seed,
-                       self._sid(kind, l))
+                       self._sid(kind, l), step_dev=self.step_dev)
         pool.put(d1, d2)
         self._bias_grad(do, self.g32(s + "out_proj.bias"))
         self._wgrad(do, a["ctx"], s + "out_proj.weight")
@@ -559,7 +636,7 @@ class StepEngine:
         ops.gemm(dqkv, self.w16(s + "q_proj.weight", s + "v_proj.weight"), dx, b_t=True)
         return dres, dx
 
-    def backward(self, grad_out=None):
+    def backward(self, grad_out=None, force_zero=False):
         """Writes every parameter gradient into the fp32 gradient arena (+=) and points `.grad` at it."""
         cfg, w = self.cfg, self.ws
         if w is None:
@@ -572,7 +649,7 @@ class StepEngine:
         bm = "bart_model.model."
         g = ops.gemm
         first = next(iter(self.params.values()))
-        if first.grad is None:
+        if force_zero or first.grad is None:
             self.G32.zero_()
         w["dMEM32"].zero_()
 
@@ -600,7 +677,7 @@ class StepEngine:
             dyc = pool.get() if pd > 0 else dres
             ops.add_ln_bwd(d1, d2, a["x1"], yc, self.w32(lp + "encoder_attn_layer_norm.weight"), a["m2"], a["r2"], dres, dyc,
                            self.g32(lp + "encoder_attn_layer_norm.weight"), self.g32(lp + "encoder_attn_layer_norm.bias"),
-                           pd, seed, self._sid(5, l))
+                           pd, seed, self._sid(5, l), step_dev=self.step_dev)
             pool.put(d1, d2)
             nm = a["A3"].shape[0]
             if gates:
@@ -643,7 +720,7 @@ class StepEngine:
                          w["rating_diff"], self.w32(pre + "rating_embeddings"), self.w32(pre + "layernorm_embedding.weight"),
                          w["dec_m0"], w["dec_r0"], self.g32(bm + "shared.weight"), self.g32(pre + "embed_positions.weight"),
                          self.g32(pre + "rating_embeddings"), self.g32(pre + "layernorm_embedding.weight"),
-                         self.g32(pre + "layernorm_embedding.bias"), w["dz32"], T, S, cfg.pad_token_id, pd, seed, self._sid(3, 0))
+                         self.g32(pre + "layernorm_embedding.bias"), w["dz32"], T, S, cfg.pad_token_id, pd, seed, self._sid(3, 0), step_dev=self.step_dev)
         pool.put(d1, d2)
         self._ready(pre + "embed_positions.weight")
 
@@ -686,7 +763,7 @@ class StepEngine:
             ops.embed_ln_bwd(d1, d2, w["enc_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"), None, None,
                              self.w32(pre + "layernorm_embedding.weight"), w["enc_m0"], w["enc_r0"], self.g32(bm + "shared.weight"),
                              self.g32(pre + "embed_positions.weight"), None, self.g32(pre + "layernorm_embedding.weight"),
-                             self.g32(pre + "layernorm_embedding.bias"), w["dz32"], T, S, cfg.pad_token_id, pd, seed, self._sid(0, 0))
+                             self.g32(pre + "layernorm_embedding.bias"), w["dz32"], T, S, cfg.pad_token_id, pd, seed, self._sid(0, 0), step_dev=self.step_dev)
             pool.put(d1, d2)
         self._ready(bm + "shared.weight")
         for n, p in self.params.items():

@@ -51,6 +51,12 @@ class _EngineRoot:
             if m is not self:
                 object.__setattr__(m, "_root_ref", ref)
 
+    def enable_cuda_graph(self, on=True):
+        """Replay the training step from recorded CUDA graphs (engine.StepEngine.enable_graph); call after `.cuda()`."""
+        dev = next(self.parameters()).device
+        self._ensure_engine(dev).enable_graph(on)
+        return self
+
     def _ensure_engine(self, device):
         device = torch.device(device)
         if getattr(self, "engine", None) is None:
@@ -358,7 +364,7 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, module, batch, label_smoothing):
         eng = module.engine
-        loss = eng.forward(batch, label_smoothing, training=module.training)
+        loss = eng.forward_step(batch, label_smoothing, module.training)
         ctx.engine = eng
         ctx.generation = eng.fwd_generation
         return loss.reshape(()).clone()
@@ -369,7 +375,7 @@ class _StepFn(torch.autograd.Function):
         if ctx.generation != eng.fwd_generation:
             raise RuntimeError("backward() of a stale step: another forward ran on this model since this loss was computed "
                                "(the engine keeps the activations of ONE step); call backward before the next forward")
-        eng.backward(grad_out.contiguous().float())
+        eng.backward_step(grad_out.contiguous().float())
         return None, None, None, None
 
 

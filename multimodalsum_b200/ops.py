@@ -131,47 +131,47 @@ def cast_bf16(src, dst):
     return dst
 
 
-def embed_ln_fwd(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, rows, S, p_drop, seed, sid):
+def embed_ln_fwd(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, rows, S, p_drop, seed, sid, step_dev=None):
     # algorithmic bytes: one fp32 table row read + one bf16 row written per token (positions / LN parameters stay in L2)
-    _timed("embed_ln_fwd", rows * E.shape[1] * 6.0, lambda: _embed_ln_fwd(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, rows, S, p_drop, seed, sid))
+    _timed("embed_ln_fwd", rows * E.shape[1] * 6.0, lambda: _embed_ln_fwd(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, rows, S, p_drop, seed, sid, step_dev))
 
 
-def _embed_ln_fwd(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, rows, S, p_drop, seed, sid):
+def _embed_ln_fwd(ids, E, P, rating_diff, remb, gamma, beta, out, mean, rstd, rows, S, p_drop, seed, sid, step_dev):
     check(_lib.lib().mmsum_embed_ln_fwd(_ptr(ids), _ptr(E), _ptr(P), _ptr(rating_diff), _ptr(remb), _ptr(gamma), _ptr(beta),
                                         _ptr(out), _ptr(mean), _ptr(rstd), rows, S, E.shape[1], C.c_float(p_drop),
-                                        C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_embed_ln_fwd")
+                                        C.c_uint64(seed), C.c_uint32(sid), _ptr(step_dev), _stream()), "mmsum_embed_ln_fwd")
 
 
 def embed_ln_bwd(dout, dout2, ids, E, P, rating_diff, remb, gamma, mean, rstd, dE, dP, dremb, dgamma, dbeta, dz, rows, S,
-                 pad_id, p_drop, seed, sid):
+                 pad_id, p_drop, seed, sid, step_dev=None):
     check(_lib.lib().mmsum_embed_ln_bwd(_ptr(dout), _ptr(dout2), _ptr(ids), _ptr(E), _ptr(P), _ptr(rating_diff), _ptr(remb),
                                         _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dE), _ptr(dP), _ptr(dremb), _ptr(dgamma),
                                         _ptr(dbeta), _ptr(dz), rows, S, E.shape[1], pad_id, C.c_float(p_drop),
-                                        C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_embed_ln_bwd", 2)
+                                        C.c_uint64(seed), C.c_uint32(sid), _ptr(step_dev), _stream()), "mmsum_embed_ln_bwd", 2)
 
 
-def add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid):
+def add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid, step_dev=None):
     rows, d = res.shape
-    _timed("add_ln_fwd", 3.0 * rows * d * 2, lambda: _add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid))
+    _timed("add_ln_fwd", 3.0 * rows * d * 2, lambda: _add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid, step_dev))
 
 
-def _add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid):
+def _add_ln_fwd(res, y, gamma, beta, out, mean, rstd, p_drop, seed, sid, step_dev):
     rows, d = res.shape
     check(_lib.lib().mmsum_add_ln_fwd(_ptr(res), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(out), _ptr(mean), _ptr(rstd), rows, d,
-                                      C.c_float(p_drop), C.c_uint64(seed), C.c_uint32(sid), _stream()), "mmsum_add_ln_fwd")
+                                      C.c_float(p_drop), C.c_uint64(seed), C.c_uint32(sid), _ptr(step_dev), _stream()), "mmsum_add_ln_fwd")
 
 
-def add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid):
+def add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid, step_dev=None):
     rows, d = res.shape
     n_mats = 3 + (1 if d2 is not None else 0) + 1 + (1 if dy.data_ptr() != dres.data_ptr() else 0)   # d1 (+d2), res, y in; dres (+dy) out
-    _timed("add_ln_bwd", float(n_mats) * rows * d * 2, lambda: _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid))
+    _timed("add_ln_bwd", float(n_mats) * rows * d * 2, lambda: _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid, step_dev))
 
 
-def _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid):
+def _add_ln_bwd(d1, d2, res, y, gamma, mean, rstd, dres, dy, dgamma, dbeta, p_drop, seed, sid, step_dev):
     rows, d = res.shape
     check(_lib.lib().mmsum_add_ln_bwd(_ptr(d1), _ptr(d2), _ptr(res), _ptr(y), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres),
                                       _ptr(dy), _ptr(dgamma), _ptr(dbeta), rows, d, C.c_float(p_drop), C.c_uint64(seed),
-                                      C.c_uint32(sid), _stream()), "mmsum_add_ln_bwd")
+                                      C.c_uint32(sid), _ptr(step_dev), _stream()), "mmsum_add_ln_bwd")
 
 
 def colsum(x, out):
