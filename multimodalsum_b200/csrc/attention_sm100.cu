@@ -767,6 +767,275 @@ attn_fwd_tc2_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p
 }
 
 // ----------------------------------------------------------------------------------------------
+// forward, version 3 — two INDEPENDENT CTAs per SM instead of two coupled softmax groups in one CTA
+//   v2's two groups share one MMA warp that issues in order and ONE output accumulator: P V of item i+1 waits for the
+//   read-out of O_i, so the groups run almost serially (measured ~4.1 k clk per item against ~4.7 k for a single group).
+//   Here a CTA is a single chain (4 softmax warps, thread = query row; 256 TMEM columns; one Q / K / V stage, 69 KB smem) and
+//   TWO such CTAs are resident per SM, each with its own MMA warp, score buffer and output accumulator; they interfere only
+//   through the shared pipes, and one CTA's set-up / tear-down overlaps the other's items.
+//   TMEM columns: scores [0, 208); P (bf16) over the scores' lower half [0, 104); O at [192, 256) — it overlaps score columns
+//   only of 208-wide (image) entities, and only after their exp pass has consumed them.
+// ----------------------------------------------------------------------------------------------
+static constexpr int kF3Threads = 64 + 4 * 32;
+static constexpr uint32_t kF3ColO = 192;
+struct Fwd3Smem {
+  uint8_t q[SQ * 128];
+  uint8_t k[kKVStageBytes];
+  uint8_t v[kKVStageBytes];
+  uint32_t kmask[kMaxEnt][8];
+  EntItem items[kMaxEnt];
+  uint64_t q_full, q_empty, k_full, k_empty, v_full, v_empty, s_full, p_full, o_full, o_free;
+  uint32_t tmem_slot;
+  int n_items;
+};
+__device__ __forceinline__ void f3_mask_bar() { asm volatile("bar.sync 2, 160;" ::: "memory"); }   // warps 1..5
+__device__ __forceinline__ void f3_build_masks(const MmsumAttnArgs& p, EntItem* items, int n_items, uint32_t (*kmask)[8],
+                                               int w, int lane) {   // w = warp - 1 in [0, 5)
+  for (int idx = w; idx < n_items * 7; idx += 5) {
+    const int i = idx / 7, c = idx - i * 7;
+    const uint32_t wd = chunk_word(p, items[i], c, lane);
+    if (lane == 0) kmask[i][c] = wd;
+  }
+  f3_mask_bar();
+  const int i = w * 32 + lane;
+  if (i < n_items) {
+    int last = 0;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) { const uint32_t wd = kmask[i][c]; if (wd) last = c * 32 + 32 - __clz(wd); }
+    const int n16 = (last + 15) & ~15;
+    items[i].n16 = n16 < 16 ? 16 : n16;
+  }
+  f3_mask_bar();
+}
+
+__global__ void __launch_bounds__(kF3Threads, 2)
+attn_fwd_tc3_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p, const int head_mode) {
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();
+  Fwd3Smem& sm = *reinterpret_cast<Fwd3Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // head_mode = heads per CTA (self-attention: the CTA's items are `head_mode` consecutive heads of one sequence); 0 = the
+  // items are the entities of one (sequence, head)
+  const int parts = head_mode ? p.H / head_mode : 1;
+  const int part = head_mode ? (int)(blockIdx.x % parts) : 0;
+  const int sidx = head_mode ? (int)(blockIdx.x / parts) : (int)blockIdx.x;
+  const int tgt = sidx % p.R;
+  const int h = head_mode ? 0 : (int)((sidx / p.R) % p.H);
+  const int biz = head_mode ? (int)(sidx / p.R) : (int)(sidx / (p.R * p.H));
+  const int qseq = biz * p.R + tgt;
+  const int qrow0 = qseq * SQ;
+  auto item_head = [&](int i) { return head_mode ? part * head_mode + i : h; };
+
+  if (warp == 0) {
+    int n = build_ent_items(p, qseq, sm.items, lane);
+    if (head_mode) {                       // replicate the single entity once per head
+      __syncwarp();
+      if (n > 0) {
+        const EntItem it0 = sm.items[0];
+        __syncwarp();
+        if (lane < head_mode) sm.items[lane] = it0;
+        n = head_mode;
+      }
+    }
+    if (lane == 0) sm.n_items = n;
+  }
+  if (threadIdx.x == 32) {
+    mbar_init(&sm.q_full, 1); mbar_init(&sm.q_empty, 1);
+    mbar_init(&sm.k_full, 1); mbar_init(&sm.k_empty, 1);
+    mbar_init(&sm.v_full, 1); mbar_init(&sm.v_empty, 1);
+    mbar_init(&sm.s_full, 1); mbar_init(&sm.p_full, 128); mbar_init(&sm.o_full, 1); mbar_init(&sm.o_free, 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.q);
+  }
+  // V rows beyond an entity's key count are multiplied by P = 0: they must hold finite values, never stale NaN bits
+  for (int i = threadIdx.x; i < kKVStageBytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sm.v)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 1) { tmem_alloc(&sm.tmem_slot, 256); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_slot;
+  const int n_items = sm.n_items;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (!head_mode) {
+        mbar_expect_tx(&sm.q_full, SQ * 128);
+        tma_load_2d(sm.q, &maps.q, &sm.q_full, p.q_col + h * HD, qrow0);
+      }
+      for (int i = 0; i < n_items; ++i) {
+        if (head_mode) {
+          mbar_wait(&sm.q_empty, (i & 1) ^ 1);
+          mbar_expect_tx(&sm.q_full, SQ * 128);
+          tma_load_2d(sm.q, &maps.q, &sm.q_full, p.q_col + item_head(i) * HD, qrow0);
+        }
+        mbar_wait(&sm.k_empty, (i & 1) ^ 1);
+        const EntItem it = sm.items[i];
+        mbar_expect_tx(&sm.k_full, it.nkeys * 128);
+        tma_load_2d(sm.k, &maps.kv[it.mod], &sm.k_full, p.k_col + item_head(i) * HD, it.kv_row0);
+      }
+    } else if (lane == 1) {
+      for (int i = 0; i < n_items; ++i) {
+        mbar_wait(&sm.v_empty, (i & 1) ^ 1);
+        const EntItem it = sm.items[i];
+        mbar_expect_tx(&sm.v_full, it.nkeys * 128);
+        tma_load_2d(sm.v, &maps.kv[it.mod], &sm.v_full, p.v_col + item_head(i) * HD, it.kv_row0);
+      }
+    }
+  } else if (warp == 1) {
+    f3_build_masks(p, sm.items, n_items, sm.kmask, 0, lane);
+    if (n_items > 0) {   // whole warp runs the issue loop; elect.sync picks the issuing lane per instruction
+      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sm.q), 16, 1024);
+      const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sm.k), 16, 1024);
+      const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sm.v), 8192, 1024);
+      if (!head_mode) mbar_wait(&sm.q_full, 0);
+      auto issue_s = [&](int i) {
+        const EntItem it = sm.items[i];
+        if (head_mode) mbar_wait(&sm.q_full, i & 1);
+        mbar_wait(&sm.k_full, i & 1);
+        // the output accumulator overlaps the score columns of entities wider than 192 keys: wait for its read-out
+        if (i > 0 && it.n16 > (int)kF3ColO) mbar_wait(&sm.o_free, (i - 1) & 1);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(128, it.n16, 0, 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_w(tmem, desc_adv(qdesc, kk * 32), desc_adv(kdesc, kk * 32), idesc, kk > 0);
+        umma_commit_w(&sm.s_full);
+        umma_commit_w(&sm.k_empty);
+        if (head_mode) umma_commit_w(&sm.q_empty);
+      };
+      issue_s(0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+      for (int i = 0; i < n_items; ++i) {
+        const EntItem it = sm.items[i];
+        mbar_wait(&sm.v_full, i & 1);
+        mbar_wait(&sm.p_full, i & 1);                        // P (bf16) now sits where the scores were
+        if (i > 0) mbar_wait(&sm.o_free, (i - 1) & 1);       // the previous entity's O has been read out
+        tc_fence_after();
+        const int nk = it.n16 >> 4;
+#pragma unroll
+        for (int kk = 0; kk < kMaxKeys / 16; ++kk)
+          if (kk < nk) umma_bf16_ts_w(tmem + kF3ColO, tmem + kk * 8, desc_adv(vdesc, kk * 2048), idesc_o, kk > 0);
+        umma_commit_w(&sm.v_empty);
+        umma_commit_w(&sm.o_full);
+        if (i + 1 < n_items) issue_s(i + 1);                 // overwrites the score buffer: ordered after P V above
+      }
+    }
+  } else {
+    // ===================== softmax warps: thread = one query row =====================
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const float sc = p.scale * kLog2e;
+    float acc[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    bf16* Og = reinterpret_cast<bf16*>(p.O);
+    auto store_out = [&](int m, int head) {        // acc -> bf16 output row, then reset
+      bf16* dst = Og + p.mods[m].o_off + (long long)(qrow0 + row) * p.ldo + head * HD;
+#pragma unroll
+      for (int j = 0; j < HD / 8; ++j) {
+        uint4 u;
+        u.x = pack_bf16(acc[j * 8 + 0], acc[j * 8 + 1]); u.y = pack_bf16(acc[j * 8 + 2], acc[j * 8 + 3]);
+        u.z = pack_bf16(acc[j * 8 + 4], acc[j * 8 + 5]); u.w = pack_bf16(acc[j * 8 + 6], acc[j * 8 + 7]);
+        *reinterpret_cast<uint4*>(dst + j * 8) = u;
+      }
+#pragma unroll
+      for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    };
+    int cur_mod = 0;
+    f3_build_masks(p, sm.items, n_items, sm.kmask, warp - 1, lane);
+    const uint32_t scol = tmem + lane_off;
+    for (int i = 0; i < n_items; ++i) {
+      const EntItem it = sm.items[i];
+      const int head = item_head(i);
+      const int nchunk = (it.n16 + 31) >> 5;
+      const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
+      if (!head_mode) { while (cur_mod < it.mod) { store_out(cur_mod, h); ++cur_mod; } }
+      mbar_wait(&sm.s_full, i & 1);
+      tc_fence_after();
+      // ---- row max ----
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+      for (int c = 0; c < nchunk; ++c) {
+        uint32_t wd = sm.kmask[i][c];
+        if (p.causal) wd = causal_word(wd, row, c);
+        uint32_t r[32];
+        tmem_ld_32x32(scol + c * 32, r);
+        tmem_ld_wait();
+        if (__all_sync(0xffffffffu, wd == 0xffffffffu)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx4[j & 3] = ((wd >> j) & 1u) ? fmaxf(mx4[j & 3], __uint_as_float(r[j])) : mx4[j & 3];
+        }
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float msc = (mx == -INFINITY) ? 0.f : mx * sc;
+      // ---- P = exp2(s*sc - m) written back over the scores as packed bf16; row sum ----
+      f32x2 l2[2] = {splat2(0.f), splat2(0.f)};
+      const f32x2 sc2 = splat2(sc), nmsc2 = splat2(-msc);
+#pragma unroll 1
+      for (int c = 0; c < nchunk; ++c) {
+        uint32_t wd = sm.kmask[i][c];
+        if (p.causal) wd = causal_word(wd, row, c);
+        uint32_t r[32], pk[16];
+        tmem_ld_32x32(scol + c * 32, r);
+        tmem_ld_wait();
+        auto body = [&](auto tag) {
+          constexpr bool kFull = decltype(tag)::value;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float a0, a1;
+            unpack2(fma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, nmsc2), a0, a1);
+            float e0 = ex2(a0), e1 = ex2(a1);
+            if constexpr (!kFull) { e0 = ((wd >> j) & 1u) ? e0 : 0.f; e1 = ((wd >> (j + 1)) & 1u) ? e1 : 0.f; }
+            l2[(j >> 1) & 1] = add2(l2[(j >> 1) & 1], pack2(e0, e1));
+            pk[j >> 1] = pack_bf16(e0, e1);
+          }
+        };
+        if (__all_sync(0xffffffffu, wd == 0xffffffffu)) body(std::true_type{}); else body(std::false_type{});
+        tmem_st_32x16(scol + c * 16, pk);          // columns [16c, 16c+16) lie inside score chunks this thread has consumed
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&sm.p_full);
+      float l4[4];
+      unpack2(l2[0], l4[0], l4[1]);
+      unpack2(l2[1], l4[2], l4[3]);
+      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      p.LSE[(((long long)qseq * p.H + head) * p.E_total + it.ent) * SQ + row] = (l > 0.f) ? (msc + __log2f(l)) : INFINITY;
+      const float wgt = (l > 0.f) ? __fdividef(inv_n, l) : 0.f;
+      // ---- this entity's O = P V: fold into the register accumulators ----
+      mbar_wait(&sm.o_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + lane_off + kF3ColO + hh * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[hh * 32 + j] = fmaf(wgt, __uint_as_float(r[j]), acc[hh * 32 + j]);
+      }
+      tc_fence_before();
+      mbar_arrive(&sm.o_free);
+      if (head_mode) store_out(0, head);
+    }
+    if (head_mode) {
+      if (n_items == 0) for (int hh = 0; hh < head_mode; ++hh) store_out(0, item_head(hh));   // null entity: zero rows
+    } else {
+      while (cur_mod < p.n_mod) { store_out(cur_mod, h); ++cur_mod; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// ----------------------------------------------------------------------------------------------
 // backward, part 1 — one CTA per (sequence, head): dQ and DELTA
 //   per entity:  S = Q K^T and dP' = dA V^T into TMEM;  P = exp2(sc*S - LSE) (kept in registers as bf16),
 //   delta' = rowsum(P o dP');  dS = scale*inv_n * P o (dP' - delta') -> bf16 smem;  dQ += dS K  (TMEM, all entities)
@@ -1511,7 +1780,15 @@ extern "C" int mmsum_attn_fwd(const MmsumAttnArgs* a, void* stream_v) {
   // self-attention shape (one modality, one entity per sequence, no leave-one-out): heads become the CTA's items
   const int head_mode = (a->n_mod == 1 && a->mods[0].E == 1 && !a->mods[0].loo && a->H <= kMaxEnt && a->n_qseq >= 64) ? 1 : 0;
   static const bool use_v1 = (getenv("MMSUM_ATTN_FWD_V1") != nullptr);   // A/B switch: the first forward kernel
-  if (use_v1) {
+  static const bool use_v2 = (getenv("MMSUM_ATTN_FWD_V2") != nullptr);   // A/B switch: two coupled groups in one CTA
+  if (!use_v1 && !use_v2) {
+    const int smem3 = (int)sizeof(Fwd3Smem) + 1024;
+    static std::atomic<unsigned long long> attr3{0};
+    if (int rc = ensure_dyn_smem(attn_fwd_tc3_kernel, smem3, attr3)) return rc;
+    // self-attention: two CTAs per sequence (half of the heads each) so that both CTA slots of every SM are used
+    const int hpc = head_mode ? ((a->H % 2 == 0 && a->n_qseq <= 2 * kNumSMs) ? a->H / 2 : a->H) : 0;
+    MMSUM_LAUNCH_PDL(attn_fwd_tc3_kernel, head_mode ? a->n_qseq * (a->H / hpc) : a->n_qseq * a->H, kF3Threads, smem3, stream, mp, *a, hpc);
+  } else if (use_v1) {
     MMSUM_LAUNCH_PDL(attn_fwd_tc_kernel, head_mode ? a->n_qseq : a->n_qseq * a->H, kAttnThreads, smem, stream, mp, *a, head_mode);
   } else {
     const int smem2 = (int)sizeof(Fwd2Smem) + 1024;
