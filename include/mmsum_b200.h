@@ -83,6 +83,12 @@ typedef struct MmsumAttnArgs {
 } MmsumAttnArgs;
 int mmsum_attn_fwd(const MmsumAttnArgs* args, void* stream);
 int mmsum_attn_bwd(const MmsumAttnArgs* args, void* stream); /* dQ/DELTA pass, then dK/dV pass */
+/* A/B switch of the forward kernel: 0 = default (environment MMSUM_ATTN_FWD_V1 / _V2 may override), 1..3 = that version. */
+int mmsum_attn_set_fwd_variant(int32_t variant);
+/* Test aid: one CTA per SM fills its shared memory and all 512 tensor-memory columns with NaN bit patterns.  A kernel that
+ * consumes stale on-chip state (0 * stale, unwritten accumulator columns) produces non-finite or run-dependent results when it
+ * is launched after this one (tests/test_kernels_gpu.py::test_kernels_ignore_stale_onchip_state). */
+int mmsum_debug_poison(void* stream);
 
 /* ---- decode-step attention (beam search, BASELINE config 5) ------------------------------------------
  * Replaces the cached branch of SelfAttention.get_head_output (src/transformer/modeling_multimodalsum.py:774-815, 889-920)

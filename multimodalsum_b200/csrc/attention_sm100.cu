@@ -1264,9 +1264,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           for (int j = 0; j < 16; j += 2) {
             float p0 = ex2(fmaf(__uint_as_float(rs[j]), sc, -lse));
             float p1 = ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse));
-            if constexpr (!kFull) { p0 = ((w16 >> j) & 1u) ? p0 : 0.f; p1 = ((w16 >> (j + 1)) & 1u) ? p1 : 0.f; }
-            dl4[(j >> 1) & 3] = fmaf(p0, __uint_as_float(rd[j]), dl4[(j >> 1) & 3]);
-            dl4[(j >> 1) & 3] = fmaf(p1, __uint_as_float(rd[j + 1]), dl4[(j >> 1) & 3]);
+            float d0 = __uint_as_float(rd[j]), d1 = __uint_as_float(rd[j + 1]);
+            // masked columns: the score tile's columns beyond n16 were never written by this entity's MMAs (stale tensor
+            // memory, possibly NaN patterns), so both factors are SELECTED to zero — 0 * stale is not 0
+            if constexpr (!kFull) {
+              const bool b0 = (w16 >> j) & 1u, b1 = (w16 >> (j + 1)) & 1u;
+              p0 = b0 ? p0 : 0.f; p1 = b1 ? p1 : 0.f;
+              d0 = b0 ? d0 : 0.f; d1 = b1 ? d1 : 0.f;
+            }
+            dl4[(j >> 1) & 3] = fmaf(p0, d0, dl4[(j >> 1) & 3]);
+            dl4[(j >> 1) & 3] = fmaf(p1, d1, dl4[(j >> 1) & 3]);
             pk[j >> 1] = pack_bf16(p0, p1);
           }
         };
@@ -1671,6 +1678,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
           po[e2] = pack_bf16(p0, p1);
           float s0, s1;
           unpack2(mul2(pack2(p0, p1), fma2(pack2(__uint_as_float(rd[j]), __uint_as_float(rd[j + 1])), scale2, nd[e2])), s0, s1);
+          // invalid key rows (null entity of a packed tile, pad keys): the forward never wrote their LSE / DELTA rows, which may
+          // hold NaN patterns — select, 0 * stale is not 0
+          if constexpr (!kFull) { s0 = ((wd >> j) & 1u) ? s0 : 0.f; s1 = ((wd >> (j + 1)) & 1u) ? s1 : 0.f; }
           dso[e2] = pack_bf16(s0, s1);
         }
         const int chunk = cg * 4 + g8;
@@ -1769,6 +1779,41 @@ static int build_maps(const MmsumAttnArgs* a, AttnMaps* mp, bool bwd) {
 
 using namespace mmsum;
 
+// A/B and debugging switches ------------------------------------------------------------------
+static std::atomic<int> g_fwd_variant{0};   // 0 = environment / default, 1..3 = forward kernel version
+extern "C" int mmsum_attn_set_fwd_variant(int v) { g_fwd_variant.store(v); return 0; }
+
+// Fills every SM's shared memory and tensor memory with NaN bit patterns: a kernel that consumes stale on-chip state shows up as
+// non-finite / run-to-run different output when launched after this one (tools/gpu_attn_determinism.py).
+__global__ void __launch_bounds__(128, 1) debug_poison_kernel(int smem_words) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t slot;
+  uint32_t* w = reinterpret_cast<uint32_t*>(smem_raw);
+  for (int i = threadIdx.x; i < smem_words; i += blockDim.x) w[i] = 0xffffffffu;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot + ((uint32_t)(warp * 32) << 16);
+  uint32_t r[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) r[j] = 0xffffffffu;
+  for (int c = 0; c < 512; c += 16) tmem_st_32x16(tmem + c, r);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(slot, 512); }
+}
+extern "C" int mmsum_debug_poison(void* stream_v) {
+  const int bytes = 200 * 1024;
+  static std::atomic<unsigned long long> attr{0};
+  if (int rc = ensure_dyn_smem(debug_poison_kernel, bytes, attr)) return rc;
+  debug_poison_kernel<<<kNumSMs, 128, bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(bytes / 4);
+  MMSUM_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int mmsum_attn_fwd(const MmsumAttnArgs* a, void* stream_v) {
   if (int rc = validate_tc(a, false)) return rc;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
@@ -1779,8 +1824,10 @@ extern "C" int mmsum_attn_fwd(const MmsumAttnArgs* a, void* stream_v) {
   if (int rc = ensure_dyn_smem(attn_fwd_tc_kernel, smem, attr)) return rc;
   // self-attention shape (one modality, one entity per sequence, no leave-one-out): heads become the CTA's items
   const int head_mode = (a->n_mod == 1 && a->mods[0].E == 1 && !a->mods[0].loo && a->H <= kMaxEnt && a->n_qseq >= 64) ? 1 : 0;
-  static const bool use_v1 = (getenv("MMSUM_ATTN_FWD_V1") != nullptr);   // A/B switch: the first forward kernel
-  static const bool use_v2 = (getenv("MMSUM_ATTN_FWD_V2") != nullptr);   // A/B switch: two coupled groups in one CTA
+  static const bool env_v1 = (getenv("MMSUM_ATTN_FWD_V1") != nullptr);   // A/B switch: the first forward kernel
+  static const bool env_v2 = (getenv("MMSUM_ATTN_FWD_V2") != nullptr);   // A/B switch: two coupled groups in one CTA
+  const int variant = g_fwd_variant.load();
+  const bool use_v1 = variant ? variant == 1 : env_v1, use_v2 = variant ? variant == 2 : env_v2;
   if (!use_v1 && !use_v2) {
     const int smem3 = (int)sizeof(Fwd3Smem) + 1024;
     static std::atomic<unsigned long long> attr3{0};

@@ -356,6 +356,114 @@ def test_multi_entity_cross_attention_fwd_bwd():
     _close(dkv[:, D:], kvf.grad[:, D:], 2e-2, "cross dv")
 
 
+def _stale_state_cross_case(seed):
+    """Multi-entity cross-attention with null images inside packed dK/dV tiles, ragged reviews and a masked table."""
+    torch.manual_seed(seed)
+    B, R, S, H, hd, F_, n_img, ik = 3, 4, 128, 16, 64, 47, 3, 196
+    N, T = B * R, B * R * S
+    Tm = T + B * F_ + B * n_img * ik
+    Et = R + 1 + n_img
+    dev = _dev()
+    qc = torch.randn(T, D, device=dev).to(torch.bfloat16)
+    kv = torch.randn(Tm, 2 * D, device=dev).to(torch.bfloat16)
+    lens = torch.randint(30, S + 1, (B, R), device=dev)
+    tvalid = torch.arange(S, device=dev)[None, None, :] < lens[:, :, None]
+    tabvalid = torch.rand(B, 1, F_, device=dev) > 0.3
+    tabvalid[:, :, 0] = True
+    imask = torch.tensor([[True, False, False], [False, False, False], [False, True, True]], device=dev)
+    ivalid = imask[:, :, None].expand(B, n_img, ik)
+    mem_valid = torch.cat([tvalid.reshape(-1), tabvalid.reshape(-1), ivalid.reshape(-1)]).to(torch.uint8)
+    ent_valid = torch.cat([tvalid.any(-1), tabvalid.any(-1), imask], dim=1).to(torch.uint8).contiguous()
+    inv_n = torch.zeros(N, 3, device=dev)
+    ni = imask.sum(1).float()
+    inv_n[:, 0] = 1.0 / (R - 1)
+    inv_n[:, 1] = 1.0
+    inv_n[:, 2] = torch.where(ni > 0, 1.0 / ni.clamp(min=1), torch.zeros_like(ni)).repeat_interleave(R)
+    mods = [(0, 0, R, S, 1, 0), (T, T * D, 1, F_, 0, R), (T + B * F_, 2 * T * D, n_img, ik, 0, R + 1)]
+    kw = dict(Q=qc, ldq=D, q_col=0, KV=kv, ldkv=2 * D, k_col=0, v_col=D, ldo=D, key_valid=mem_valid, ent_valid=ent_valid,
+              inv_n=inv_n, n_qseq=N, H=H, R=R, causal=0, E_total=Et, scale=hd ** -0.5, mods=mods)
+    dA3 = torch.randn(3, T, D, device=dev).to(torch.bfloat16)
+    return kw, dA3, (N, H, Et, S, T, Tm)
+
+
+@pytest.mark.parametrize("variant", [0, 2])
+def test_kernels_ignore_stale_onchip_state(variant):
+    """Masked score columns, pad keys and null entities are handled by SELECTING zeros, never by multiplying stale data by
+    zero: with every SM's shared / tensor memory and every unwritten LSE / DELTA row filled with NaN patterns before each
+    launch, forward and backward attention (deterministic kernels, no atomics) and a ragged GEMM must return exactly the
+    bits of an unpoisoned run.  (Found in round 2: 0 * stale dP' columns beyond n16 in the dQ kernel, and 0 * DELTA of a
+    null image inside a packed dK/dV tile, turned every gradient into NaN depending on which kernel ran before.)"""
+    ops = _ops()
+    ops.set_attn_fwd_variant(variant)
+    try:
+        kw, dA3, (N, H, Et, S, T, Tm) = _stale_state_cross_case(21)
+        dev = _dev()
+
+        def run(poisoned):
+            fill = float("nan") if poisoned else 0.0
+            A3 = torch.full((3, T, D), fill, device=dev, dtype=torch.bfloat16)
+            lse = torch.full((N, H, Et, S), fill, device=dev)
+            delta = torch.full((N, H, Et, S), fill, device=dev)
+            dqc = torch.full((T, D), fill, device=dev, dtype=torch.bfloat16)
+            dkv = torch.full((Tm, 2 * D), fill, device=dev, dtype=torch.bfloat16)
+            if poisoned:
+                ops.debug_poison()
+            ops.attn_fwd(ops.attn_args(O=A3, LSE=lse, **kw))
+            if poisoned:
+                ops.debug_poison()
+            ops.attn_bwd(ops.attn_args(O=dA3, LSE=lse, DELTA=delta, dQ=dqc, lddq=D, dq_col=0, dKV=dkv, lddkv=2 * D, dk_col=0,
+                                       dv_col=D, **kw))
+            torch.cuda.synchronize()
+            return A3, dqc, dkv
+
+        clean = run(False)
+        for _ in range(2):
+            dirty = run(True)
+            for nm, a, b in zip(("out", "dq", "dkv"), clean, dirty):
+                assert torch.isfinite(b.float()).all(), nm
+                assert torch.equal(a, b), nm
+    finally:
+        ops.set_attn_fwd_variant(0)
+    # causal self-attention with pad keys, entity mode (6 sequences) and head mode (72)
+    for n_seq in (6, 72):
+        torch.manual_seed(5)
+        N, H, S, hd = n_seq, 16, 128, 64
+        T = N * S
+        qkv = torch.randn(T, 3 * D, device=_dev()).to(torch.bfloat16)
+        lens = torch.randint(20, S + 1, (N,), device=_dev())
+        kvalid = (torch.arange(S, device=_dev())[None, :] < lens[:, None]).reshape(-1).to(torch.uint8)
+        dctx = torch.randn(T, D, device=_dev()).to(torch.bfloat16)
+        res = []
+        for poisoned in (False, True):
+            fill = float("nan") if poisoned else 0.0
+            ctx = torch.full((T, D), fill, device=_dev(), dtype=torch.bfloat16)
+            lse = torch.full((N, H, 1, S), fill, device=_dev())
+            delta = torch.full((N, H, 1, S), fill, device=_dev())
+            dqkv = torch.full((T, 3 * D), fill, device=_dev(), dtype=torch.bfloat16)
+            kw = dict(Q=qkv, ldq=3 * D, q_col=0, KV=qkv, ldkv=3 * D, k_col=D, v_col=2 * D, ldo=D, LSE=lse, key_valid=kvalid,
+                      ent_valid=None, inv_n=None, n_qseq=N, H=H, R=1, causal=1, E_total=1, scale=hd ** -0.5, mods=[(0, 0, 1, S, 0, 0)])
+            if poisoned:
+                ops.debug_poison()
+            ops.attn_fwd(ops.attn_args(O=ctx, **kw))
+            if poisoned:
+                ops.debug_poison()
+            ops.attn_bwd(ops.attn_args(O=dctx, DELTA=delta, dQ=dqkv, lddq=3 * D, dq_col=0, dKV=dqkv, lddkv=3 * D, dk_col=D,
+                                       dv_col=2 * D, **kw))
+            torch.cuda.synchronize()
+            res.append((ctx, dqkv))
+        for nm, a, b in zip(("self out", "self dqkv"), res[0], res[1]):
+            assert torch.isfinite(b.float()).all(), (nm, n_seq)
+            assert torch.equal(a, b), (nm, n_seq)
+    # ragged GEMM (TMA zero fill on M, N and K edges), bf16 and fp32-accumulating outputs
+    torch.manual_seed(6)
+    A = torch.randn(1000, 520, device=_dev()).to(torch.bfloat16)
+    Bm = torch.randn(776, 520, device=_dev()).to(torch.bfloat16)
+    ref = ops.gemm(A, Bm)
+    ops.debug_poison()
+    got = ops.gemm(A, Bm)
+    assert torch.equal(ref, got)
+
+
 # ------------------------------------------------------------------ decode-step attention
 @pytest.mark.parametrize("beams,Sk_text", [(4, 158), (1, 128), (8, 208)])
 def test_decode_cross_attention(beams, Sk_text):
