@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmsum_b200.so")
+# MMSUM_LIB_PATH: A/B tooling only (tools/ab_lib.sh builds a second library from another revision of csrc/)
+LIB_PATH = os.environ.get("MMSUM_LIB_PATH") or os.path.join(_HERE, "libmmsum_b200.so")
 
 _lib = None
 

@@ -25,6 +25,17 @@
 #include "common.cuh"
 #include "../../include/mmsum_b200.h"
 
+// compile-time experiment switches (tools/ab_variants.sh builds one library per setting for same-box A/B timing)
+#ifndef MMSUM_DQ_PREFETCH
+#define MMSUM_DQ_PREFETCH 1
+#endif
+#ifndef MMSUM_DQ_PACKED
+#define MMSUM_DQ_PACKED 0
+#endif
+#ifndef MMSUM_DKV_TS
+#define MMSUM_DKV_TS 1     // dK/dV kernel: P^T / dS^T stay in tensor memory as the A operands of the dV / dK products
+#endif
+
 namespace mmsum {
 
 static constexpr int SQ = 128;
@@ -1232,6 +1243,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
         *reinterpret_cast<uint4*>(dQg + j * 8) = u;
       }
     };
+    // LSE / 1/n of an item are fetched one item ahead: as plain loads at the top of the item their global latency (~500 clk)
+    // sat in front of pass 1 of every item
+    auto lse_index = [&](int i) { return (((long long)qseq * p.H + item_head(i)) * p.E_total + sm.items[i].ent) * SQ + row; };
+    float lse_nx = 0.f, invn_nx = 1.f;
+#if MMSUM_DQ_PREFETCH
+    if (n_items > 0) {
+      lse_nx = p.LSE[lse_index(0)];
+      if (p.inv_n) invn_nx = p.inv_n[(long long)qseq * p.n_mod + sm.items[0].mod];
+    }
+#endif
     for (int i = 0; i < n_items; ++i) {
       const EntItem it = sm.items[i];
       const int par = i & 1;
@@ -1241,9 +1262,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       wd[0] = has[0] ? sm.kmask[i][cg] : 0u;
       wd[1] = has[1] ? sm.kmask[i][cg + 4] : 0u;
       if (p.causal) { wd[0] = causal_word(wd[0], row, cg); wd[1] = causal_word(wd[1], row, cg + 4); }
-      const long long li = (((long long)qseq * p.H + item_head(i)) * p.E_total + it.ent) * SQ + row;
+      const long long li = lse_index(i);
+#if MMSUM_DQ_PREFETCH
+      const float lse = lse_nx;
+      const float inv_n = invn_nx;
+      if (i + 1 < n_items) {
+        lse_nx = p.LSE[lse_index(i + 1)];
+        if (p.inv_n) invn_nx = p.inv_n[(long long)qseq * p.n_mod + sm.items[i + 1].mod];
+      }
+#else
       const float lse = p.LSE[li];
       const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
+#endif
       if (threadIdx.x == 64) TRACE(3, 5 * i);
       mbar_wait(&sm.sdp_full, i & 1);
       if (threadIdx.x == 64) TRACE(3, 5 * i + 1);
@@ -1254,7 +1284,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       // (entities of <= 4 chunks keep dP' in registers across the delta exchange and release both after pass 1), so
       // the next entity's Q K^T / dA V^T overlap this entity's softmax work.
       const float wgt = p.scale * inv_n;
+#if MMSUM_DQ_PACKED
+      f32x2 dl2[2] = {splat2(0.f), splat2(0.f)};
+      const f32x2 sc2 = splat2(sc), nlse2 = splat2(-lse), wgt2 = splat2(wgt);
+#else
       float dl4[4] = {0.f, 0.f, 0.f, 0.f};
+#endif
       // half = 16 score columns: bits [16*half, +16) of the chunk's mask word, packed P words [8*half, +8)
       auto pass1 = [&](const uint32_t w16, const uint32_t (&rs)[16], const uint32_t (&rd)[16], uint32_t (&pk)[8]) {
         // two copies of the loop (warp-uniform choice): predicated-off mask code would still take issue slots
@@ -1262,8 +1297,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           constexpr bool kFull = decltype(tag)::value;
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
+            // packed fp32 pairs (FFMA2): the softmax warps are issue-bound, two lanes per instruction count
+#if MMSUM_DQ_PACKED
+            float a0, a1;
+            unpack2(fma2(pack2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), sc2, nlse2), a0, a1);
+            float p0 = ex2(a0), p1 = ex2(a1);
+#else
             float p0 = ex2(fmaf(__uint_as_float(rs[j]), sc, -lse));
             float p1 = ex2(fmaf(__uint_as_float(rs[j + 1]), sc, -lse));
+#endif
             float d0 = __uint_as_float(rd[j]), d1 = __uint_as_float(rd[j + 1]);
             // masked columns: the score tile's columns beyond n16 were never written by this entity's MMAs (stale tensor
             // memory, possibly NaN patterns), so both factors are SELECTED to zero — 0 * stale is not 0
@@ -1272,14 +1314,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
               p0 = b0 ? p0 : 0.f; p1 = b1 ? p1 : 0.f;
               d0 = b0 ? d0 : 0.f; d1 = b1 ? d1 : 0.f;
             }
+#if MMSUM_DQ_PACKED
+            dl2[(j >> 1) & 1] = fma2(pack2(p0, p1), pack2(d0, d1), dl2[(j >> 1) & 1]);
+#else
             dl4[(j >> 1) & 3] = fmaf(p0, d0, dl4[(j >> 1) & 3]);
             dl4[(j >> 1) & 3] = fmaf(p1, d1, dl4[(j >> 1) & 3]);
+#endif
             pk[j >> 1] = pack_bf16(p0, p1);
           }
         };
         if (__all_sync(0xffffffffu, w16 == 0xffffu)) body(std::true_type{}); else body(std::false_type{});
       };
       auto exchange_delta = [&]() {
+#if MMSUM_DQ_PACKED
+        float dl4[4];
+        unpack2(dl2[0], dl4[0], dl4[1]);
+        unpack2(dl2[1], dl4[2], dl4[3]);
+#endif
         sm.red_delta[par][cg][row] = (dl4[0] + dl4[1]) + (dl4[2] + dl4[3]);
         if (threadIdx.x == 64) TRACE(3, 5 * i + 2);
         soft_bar();
@@ -1291,6 +1342,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       };
       auto pass2 = [&](const int c, const int half, const float dw, const uint32_t (&rd)[16], const uint32_t (&pk)[8]) {
         uint8_t* atom = sm.ds + row * 128 + (c >> 1) * (SQ * 128);
+#if MMSUM_DQ_PACKED
+        const f32x2 ndw2 = splat2(-dw);
+#endif
 #pragma unroll
         for (int g8 = 0; g8 < 2; ++g8) {
           uint32_t o[4];
@@ -1298,7 +1352,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           for (int e = 0; e < 4; ++e) {
             const float2 pr = unpack_bf16(pk[g8 * 4 + e]);
             const int j = g8 * 8 + 2 * e;
+#if MMSUM_DQ_PACKED
+            float s0, s1;
+            unpack2(mul2(pack2(pr.x, pr.y), fma2(pack2(__uint_as_float(rd[j]), __uint_as_float(rd[j + 1])), wgt2, ndw2)), s0, s1);
+            o[e] = pack_bf16(s0, s1);
+#else
             o[e] = pack_bf16(pr.x * fmaf(__uint_as_float(rd[j]), wgt, -dw), pr.y * fmaf(__uint_as_float(rd[j + 1]), wgt, -dw));
+#endif
           }
           const int chunk = (c & 1) * 4 + half * 2 + g8;
           *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -1414,17 +1474,24 @@ __host__ __device__ inline int mod_tiles(const MmsumAttnMod& md) {
   return mod_packed(md) ? (md.E * md.Sk + SQ - 1) / SQ : md.E * ((md.Sk + SQ - 1) / SQ);
 }
 
+#if MMSUM_DKV_TS
+static constexpr int kKvStages = 4;                 // Q / dA ring depth (the P^T / dS^T tiles no longer take shared memory)
+#else
+static constexpr int kKvStages = 2;
+#endif
 struct BwdKVSmem {
   uint8_t k[SQ * 128];
   uint8_t v[SQ * 128];
-  uint8_t q[2][QH * 128];      // Q / dA rows of the step's 64 queries (2-deep ring)
-  uint8_t da[2][QH * 128];
+  uint8_t q[kKvStages][QH * 128];      // Q / dA rows of the step's 64 queries (ring)
+  uint8_t da[kKvStages][QH * 128];
+#if !MMSUM_DKV_TS
   uint8_t pt[SQ * 128];        // Pn^T  [128 keys][64 queries] bf16, K-major A operand
   uint8_t dst[SQ * 128];       // dS^T
+#endif
   float lse[2][2][QH];         // raw LSE / DELTA rows of the current and the next step (cp.async staged), for the (up to)
   float dlt[2][2][QH];         // two entities a packed tile straddles
   float lg_invn[32];           // log2(1/n) of every target for this modality
-  uint64_t kv_full, kv_free, qd_full[2], qd_empty[2], sdp_full, sdp_empty, pds_full, pds_free;
+  uint64_t kv_full, kv_free, qd_full[kKvStages], qd_empty[kKvStages], sdp_full, sdp_empty, pds_full, pds_free;
   uint32_t tmem_slot;
 };
 static constexpr uint32_t kColST = 0, kColDPT = 64, kColDK = 128, kColDV = 192;
@@ -1503,7 +1570,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
 
   if (threadIdx.x == 0) {
     mbar_init(&sm.kv_full, 1); mbar_init(&sm.kv_free, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&sm.qd_full[s], 1); mbar_init(&sm.qd_empty[s], 1); }
+    for (int s = 0; s < kKvStages; ++s) { mbar_init(&sm.qd_full[s], 1); mbar_init(&sm.qd_empty[s], 1); }
     mbar_init(&sm.sdp_full, 1); mbar_init(&sm.sdp_empty, kKvSoftThreads);
     mbar_init(&sm.pds_full, kKvSoftThreads); mbar_init(&sm.pds_free, 1);
     fence_barrier_init();
@@ -1529,9 +1596,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
         tma_load_2d(sm.k, &kv128, &sm.kv_full, p.k_col + h * HD, kvrow0);
         tma_load_2d(sm.v, &kv128, &sm.kv_full, p.v_col + h * HD, kvrow0);
         for (int s = 0; s < n_steps; ++s) {
-          const int g = g0 + s, st = g & 1;
+          const int g = g0 + s, st = g % kKvStages;
           const int qrow0 = (biz * p.R + step_target(s)) * SQ + (s & 1) * QH;
-          mbar_wait(&sm.qd_empty[st], ((g >> 1) & 1) ^ 1);
+          mbar_wait(&sm.qd_empty[st], ((g / kKvStages) & 1) ^ 1);
           mbar_expect_tx(&sm.qd_full[st], 2 * QH * 128);
           tma_load_2d(sm.q[st], &q64, &sm.qd_full[st], p.q_col + h * HD, qrow0);
           tma_load_2d(sm.da[st], &do64, &sm.qd_full[st], h * HD, (int)(md.o_off / p.ldo) + qrow0);
@@ -1541,23 +1608,26 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
   } else if (warp == 1) {
     {   // whole warp runs the issue loop; elect.sync picks the issuing lane per instruction
       const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sm.k), 16, 1024), vdesc = umma_smem_desc_sw128(smem_u32(sm.v), 16, 1024);
+#if !MMSUM_DKV_TS
       const uint64_t ptdesc = umma_smem_desc_sw128(smem_u32(sm.pt), 16, 1024), dstdesc = umma_smem_desc_sw128(smem_u32(sm.dst), 16, 1024);
-      const uint64_t qdesc_k[2] = {umma_smem_desc_sw128(smem_u32(sm.q[0]), 16, 1024), umma_smem_desc_sw128(smem_u32(sm.q[1]), 16, 1024)};
-      const uint64_t qdesc_mn[2] = {umma_smem_desc_sw128(smem_u32(sm.q[0]), 8192, 1024), umma_smem_desc_sw128(smem_u32(sm.q[1]), 8192, 1024)};
-      const uint64_t dadesc_k[2] = {umma_smem_desc_sw128(smem_u32(sm.da[0]), 16, 1024), umma_smem_desc_sw128(smem_u32(sm.da[1]), 16, 1024)};
-      const uint64_t dadesc_mn[2] = {umma_smem_desc_sw128(smem_u32(sm.da[0]), 8192, 1024), umma_smem_desc_sw128(smem_u32(sm.da[1]), 8192, 1024)};
+#endif
+      // stage descriptors: the stages are QH*128 bytes apart, so stage st = stage 0 advanced by st * QH*128 bytes
+      const uint64_t qdesc_k0 = umma_smem_desc_sw128(smem_u32(sm.q[0]), 16, 1024), qdesc_mn0 = umma_smem_desc_sw128(smem_u32(sm.q[0]), 8192, 1024);
+      const uint64_t dadesc_k0 = umma_smem_desc_sw128(smem_u32(sm.da[0]), 16, 1024), dadesc_mn0 = umma_smem_desc_sw128(smem_u32(sm.da[0]), 8192, 1024);
       const uint32_t idesc_s = umma_idesc_bf16(128, QH, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
       const int g_total = (h_end - h_begin) * n_steps;
       auto issue_sdp = [&](int s) {        // s = global step; the first step of a head waits for that head's K / V
-        const int st = s & 1;
+        const int st = s % kKvStages;
         if (s % n_steps == 0) mbar_wait(&sm.kv_full, (s / n_steps) & 1);
-        mbar_wait(&sm.qd_full[st], (s >> 1) & 1);
+        mbar_wait(&sm.qd_full[st], (s / kKvStages) & 1);
         if (lane == 0) TRACE(5, 4 * s);
+#if !MMSUM_DKV_TS
         mbar_wait(&sm.sdp_empty, (s & 1) ^ 1);
+#endif
         if (lane == 0) TRACE(5, 4 * s + 1);
         tc_fence_after();
-        const uint64_t qd = st ? qdesc_k[1] : qdesc_k[0], dd = st ? dadesc_k[1] : dadesc_k[0];
+        const uint64_t qd = desc_adv(qdesc_k0, st * (QH * 128)), dd = desc_adv(dadesc_k0, st * (QH * 128));
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16_w(tmem + kColST, desc_adv(kdesc, kk * 32), desc_adv(qd, kk * 32), idesc_s, kk > 0);
@@ -1567,21 +1637,39 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
         umma_commit_w(&sm.sdp_full);
         if (s % n_steps == n_steps - 1) umma_commit_w(&sm.kv_free);   // last reader of this head's K / V tiles
       };
+#if MMSUM_DKV_TS
+      // P^T / dS^T overwrite the score columns they were computed from and feed the dV / dK products straight out of tensor
+      // memory, so the next step's S^T / dP^T products can only follow this step's dV / dK (issue order = execution order):
+      // one serial chain per CTA, the co-resident CTA fills the gaps.
+      for (int s = 0; s < g_total; ++s) {
+        issue_sdp(s);
+#else
       issue_sdp(0);
       for (int s = 0; s < g_total; ++s) {
         if (s + 1 < g_total) issue_sdp(s + 1);
-        const int st = s & 1;
+#endif
+        const int st = s % kKvStages;
         const uint32_t first = (s % n_steps == 0) ? 0u : 1u;     // first step of a head starts fresh dK / dV accumulators
         mbar_wait(&sm.pds_full, s & 1);
         if (lane == 0) TRACE(5, 4 * s + 2);
         tc_fence_after();
-        const uint64_t qd = st ? qdesc_mn[1] : qdesc_mn[0], dd = st ? dadesc_mn[1] : dadesc_mn[0];
+        const uint64_t qd = desc_adv(qdesc_mn0, st * (QH * 128)), dd = desc_adv(dadesc_mn0, st * (QH * 128));
+#if MMSUM_DKV_TS
+        // k-step kk = 16 queries = 8 packed columns; queries 32cg + [0, 32) sit at columns 32cg + [0, 16) of their score tile
+#pragma unroll
+        for (int kk = 0; kk < QH / 16; ++kk)   // contraction over the step's 64 queries
+          umma_bf16_ts_w(tmem + kColDV, tmem + kColST + (kk >> 1) * 32 + (kk & 1) * 8, desc_adv(dd, kk * 2048), idesc_o, (kk > 0) ? 1u : first);
+#pragma unroll
+        for (int kk = 0; kk < QH / 16; ++kk)
+          umma_bf16_ts_w(tmem + kColDK, tmem + kColDPT + (kk >> 1) * 32 + (kk & 1) * 8, desc_adv(qd, kk * 2048), idesc_o, (kk > 0) ? 1u : first);
+#else
 #pragma unroll
         for (int kk = 0; kk < QH / 16; ++kk)   // contraction over the step's 64 queries
           umma_bf16_w(tmem + kColDV, desc_adv(ptdesc, kk * 32), desc_adv(dd, kk * 2048), idesc_o, (kk > 0) ? 1u : first);
 #pragma unroll
         for (int kk = 0; kk < QH / 16; ++kk)
           umma_bf16_w(tmem + kColDK, desc_adv(dstdesc, kk * 32), desc_adv(qd, kk * 2048), idesc_o, (kk > 0) ? 1u : first);
+#endif
         if (lane == 0) TRACE(5, 4 * s + 3);
         umma_commit_w(&sm.qd_empty[st]);
         umma_commit_w(&sm.pds_free);
@@ -1597,8 +1685,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
     const float sc = p.scale * kLog2e;
     const int slot = (packed && key0 + row >= md.Sk) ? 1 : 0;  // which of the tile's two entities owns this key row
     const bool kvalid = (row < nkeys) && (slot ? ok_hi : ok_lo) && (p.key_valid == nullptr || p.key_valid[(long long)kvrow0 + row] != 0);
+#if !MMSUM_DKV_TS
     uint8_t* patom = sm.pt + row * 128;
     uint8_t* datom = sm.dst + row * 128;
+#endif
     auto lse_index = [&](int h, int s, int ent) {
       return (((long long)(biz * p.R + step_target(s)) * p.H + h) * p.E_total + md.ent_base + ent) * SQ + (s & 1) * QH + (sw * 32 + lane);
     };
@@ -1644,18 +1734,24 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
       tmem_ld_32x32(tmem + lane_off + kColST + cg * 32, rs);
       tmem_ld_32x32(tmem + lane_off + kColDPT + cg * 32, rd);
       tmem_ld_wait();
+#if !MMSUM_DKV_TS
       // S^T / dP^T now live in registers: hand the TMEM columns back so the next step's products overlap this one
       tc_fence_before();
       mbar_arrive(&sm.sdp_empty);
+#endif
       if (threadIdx.x == 64) TRACE(6, 6 * s + 3);
       const f32x2 lg2 = splat2(lg), m1 = splat2(-1.f), sc2 = splat2(sc), scale2 = splat2(p.scale), nscale2 = splat2(-p.scale);
       // the P^T / dS^T tiles of the previous step must have been consumed by its dV / dK products (they were issued
       // while this step waited for its scores, so this wait is short; it lets every group be stored as it is formed)
+#if !MMSUM_DKV_TS
       if (g > 0) mbar_wait(&sm.pds_free, (g - 1) & 1);
+#endif
       if (threadIdx.x == 64) TRACE(6, 6 * s + 4);
-      // two copies of the loop (warp-uniform choice): predicated-off mask code would still take issue slots
+      // three copies of the loop (warp-uniform choice; predicated-off mask code would still take issue slots):
+      //   0 = every score valid;  1 = per-element mask (causal);  2 = the thread's key row is valid or not as a whole (pad keys,
+      //   null entity of a packed tile): computed like 0, the packed words are selected at the end (1 instead of 2 selects per score)
       auto body = [&](auto tag) {
-      constexpr bool kFull = decltype(tag)::value;
+      constexpr int kMode = decltype(tag)::value;
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {
         uint32_t po[4], dso[4];
@@ -1674,23 +1770,38 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
           float a0, a1;
           unpack2(fma2(pack2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), sc2, nl[e2]), a0, a1);
           float p0 = ex2(a0), p1 = ex2(a1);
-          if constexpr (!kFull) { p0 = ((wd >> j) & 1u) ? p0 : 0.f; p1 = ((wd >> (j + 1)) & 1u) ? p1 : 0.f; }
+          if constexpr (kMode == 1) { p0 = ((wd >> j) & 1u) ? p0 : 0.f; p1 = ((wd >> (j + 1)) & 1u) ? p1 : 0.f; }
           po[e2] = pack_bf16(p0, p1);
           float s0, s1;
           unpack2(mul2(pack2(p0, p1), fma2(pack2(__uint_as_float(rd[j]), __uint_as_float(rd[j + 1])), scale2, nd[e2])), s0, s1);
           // invalid key rows (null entity of a packed tile, pad keys): the forward never wrote their LSE / DELTA rows, which may
           // hold NaN patterns — select, 0 * stale is not 0
-          if constexpr (!kFull) { s0 = ((wd >> j) & 1u) ? s0 : 0.f; s1 = ((wd >> (j + 1)) & 1u) ? s1 : 0.f; }
+          if constexpr (kMode == 1) { s0 = ((wd >> j) & 1u) ? s0 : 0.f; s1 = ((wd >> (j + 1)) & 1u) ? s1 : 0.f; }
           dso[e2] = pack_bf16(s0, s1);
+          if constexpr (kMode == 2) { po[e2] = wd ? po[e2] : 0u; dso[e2] = wd ? dso[e2] : 0u; }
         }
+#if MMSUM_DKV_TS
+        // packed bf16 pairs back over the thread's own score columns (4 words = 8 queries): A operands of dV += Pn^T dA and
+        // dK += dS^T Q, read by the tensor core straight from tensor memory
+        tmem_st_32x4(tmem + lane_off + kColST + cg * 32 + g8 * 4, po);
+        tmem_st_32x4(tmem + lane_off + kColDPT + cg * 32 + g8 * 4, dso);
+#else
         const int chunk = cg * 4 + g8;
         *reinterpret_cast<uint4*>(patom + ((chunk ^ (row & 7)) << 4)) = make_uint4(po[0], po[1], po[2], po[3]);
         *reinterpret_cast<uint4*>(datom + ((chunk ^ (row & 7)) << 4)) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
+#endif
       }
       };
-      if (__all_sync(0xffffffffu, wd == 0xffffffffu)) body(std::true_type{}); else body(std::false_type{});
+      if (__all_sync(0xffffffffu, wd == 0xffffffffu)) body(std::integral_constant<int, 0>{});
+      else if (p.causal) body(std::integral_constant<int, 1>{});
+      else body(std::integral_constant<int, 2>{});
       if (threadIdx.x == 64) TRACE(6, 6 * s + 5);
+#if MMSUM_DKV_TS
+      tmem_st_wait();
+      tc_fence_before();
+#else
       fence_proxy_async_smem();
+#endif
       mbar_arrive(&sm.pds_full);
     }
     mbar_wait(&sm.pds_free, (g0 + n_steps - 1) & 1);
