@@ -32,6 +32,9 @@
 #ifndef MMSUM_DQ_PACKED
 #define MMSUM_DQ_PACKED 0
 #endif
+#ifndef MMSUM_TAIL16
+#define MMSUM_TAIL16 1     // forward v3 / dQ: the last 16 score columns of an entity with n16 % 32 == 16 are not processed as a
+#endif                     // full 32-column chunk (no exp2 / TMEM traffic for columns that do not exist)
 #ifndef MMSUM_DKV_TS
 #define MMSUM_DKV_TS 1     // dK/dV kernel: P^T / dS^T stay in tensor memory as the A operands of the dV / dK products
 #endif
@@ -968,38 +971,52 @@ attn_fwd_tc3_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p
       mbar_wait(&sm.s_full, i & 1);
       tc_fence_after();
       // ---- row max ----
+#if MMSUM_TAIL16
+      const int nfull = it.n16 >> 5;                 // 32-column chunks; an odd 16-column tail is handled on its own
+      const bool tail = (it.n16 & 16) != 0;
+#else
+      const int nfull = nchunk;
+      const bool tail = false;
+#endif
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-      for (int c = 0; c < nchunk; ++c) {
+      auto max_part = [&](auto ntag, int c) {
+        constexpr int NC = decltype(ntag)::value;
         uint32_t wd = sm.kmask[i][c];
         if (p.causal) wd = causal_word(wd, row, c);
-        uint32_t r[32];
-        tmem_ld_32x32(scol + c * 32, r);
+        constexpr uint32_t kAll = NC == 32 ? 0xffffffffu : 0xffffu;
+        wd &= kAll;
+        uint32_t r[NC];
+        if constexpr (NC == 32) tmem_ld_32x32(scol + c * 32, r); else tmem_ld_32x16(scol + c * 32, r);
         tmem_ld_wait();
-        if (__all_sync(0xffffffffu, wd == 0xffffffffu)) {
+        if (__all_sync(0xffffffffu, wd == kAll)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(r[j]));
+          for (int j = 0; j < NC; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(r[j]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx4[j & 3] = ((wd >> j) & 1u) ? fmaxf(mx4[j & 3], __uint_as_float(r[j])) : mx4[j & 3];
+          for (int j = 0; j < NC; ++j) mx4[j & 3] = ((wd >> j) & 1u) ? fmaxf(mx4[j & 3], __uint_as_float(r[j])) : mx4[j & 3];
         }
-      }
+      };
+#pragma unroll 1
+      for (int c = 0; c < nfull; ++c) max_part(std::integral_constant<int, 32>{}, c);
+      if (tail) max_part(std::integral_constant<int, 16>{}, nfull);
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float msc = (mx == -INFINITY) ? 0.f : mx * sc;
       // ---- P = exp2(s*sc - m) written back over the scores as packed bf16; row sum ----
       f32x2 l2[2] = {splat2(0.f), splat2(0.f)};
       const f32x2 sc2 = splat2(sc), nmsc2 = splat2(-msc);
-#pragma unroll 1
-      for (int c = 0; c < nchunk; ++c) {
+      auto exp_part = [&](auto ntag, int c) {
+        constexpr int NC = decltype(ntag)::value;
         uint32_t wd = sm.kmask[i][c];
         if (p.causal) wd = causal_word(wd, row, c);
-        uint32_t r[32], pk[16];
-        tmem_ld_32x32(scol + c * 32, r);
+        constexpr uint32_t kAll = NC == 32 ? 0xffffffffu : 0xffffu;
+        wd &= kAll;
+        uint32_t r[NC], pk[NC / 2];
+        if constexpr (NC == 32) tmem_ld_32x32(scol + c * 32, r); else tmem_ld_32x16(scol + c * 32, r);
         tmem_ld_wait();
         auto body = [&](auto tag) {
           constexpr bool kFull = decltype(tag)::value;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
+          for (int j = 0; j < NC; j += 2) {
             float a0, a1;
             unpack2(fma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, nmsc2), a0, a1);
             float e0 = ex2(a0), e1 = ex2(a1);
@@ -1008,9 +1025,13 @@ attn_fwd_tc3_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p
             pk[j >> 1] = pack_bf16(e0, e1);
           }
         };
-        if (__all_sync(0xffffffffu, wd == 0xffffffffu)) body(std::true_type{}); else body(std::false_type{});
-        tmem_st_32x16(scol + c * 16, pk);          // columns [16c, 16c+16) lie inside score chunks this thread has consumed
-      }
+        if (__all_sync(0xffffffffu, wd == kAll)) body(std::true_type{}); else body(std::false_type{});
+        // columns [16c, 16c + NC/2) lie inside score chunks this thread has consumed
+        if constexpr (NC == 32) tmem_st_32x16(scol + c * 16, pk); else tmem_st_32x8(scol + c * 16, pk);
+      };
+#pragma unroll 1
+      for (int c = 0; c < nfull; ++c) exp_part(std::integral_constant<int, 32>{}, c);
+      if (tail) exp_part(std::integral_constant<int, 16>{}, nfull);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&sm.p_full);
@@ -1364,14 +1385,24 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           *reinterpret_cast<uint4*>(atom + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       };
+      // 16-column halves beyond the entity's n16 (the tail of the last chunk when n16 % 32 == 16): the dQ product never reads
+      // them, so they are neither loaded nor computed nor stored
+#if MMSUM_TAIL16
+      const bool live[2][2] = {{cg * 32 < it.n16, cg * 32 + 16 < it.n16}, {(cg + 4) * 32 < it.n16, (cg + 4) * 32 + 16 < it.n16}};
+#else
+      const bool live[2][2] = {{has[0], has[0]}, {has[1], has[1]}};
+#endif
       if (nchunk <= 4) {
         uint32_t pk[2][8] = {}, rda[16] = {}, rdb[16] = {};
-        if (has[0]) {
+        if (live[0][0]) {
           uint32_t rs[16];
           tmem_ld_32x16(tmem + lane_off + kColS0 + cg * 32, rs);
           tmem_ld_32x16(tmem + lane_off + kColDP + cg * 32, rda);
           tmem_ld_wait();
           pass1(wd[0] & 0xffffu, rs, rda, pk[0]);
+        }
+        if (live[0][1]) {
+          uint32_t rs[16];
           tmem_ld_32x16(tmem + lane_off + kColS0 + cg * 32 + 16, rs);
           tmem_ld_32x16(tmem + lane_off + kColDP + cg * 32 + 16, rdb);
           tmem_ld_wait();
@@ -1385,7 +1416,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           mbar_wait(&sm.ds_free, (i - 1) & 1);
           if (head_mode) { tc_fence_after(); store_dq(i - 1); tc_fence_before(); }   // ... and the previous head's dQ is final
         }
-        if (has[0]) { pass2(cg, 0, dw, rda, pk[0]); pass2(cg, 1, dw, rdb, pk[1]); }
+        if (live[0][0]) pass2(cg, 0, dw, rda, pk[0]);
+        if (live[0][1]) pass2(cg, 1, dw, rdb, pk[1]);
       } else {
         uint32_t pk[4][8] = {};
 #pragma unroll
@@ -1393,11 +1425,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           if (has[t]) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              uint32_t rs[16], rd[16];
-              tmem_ld_32x16(tmem + lane_off + kColS0 + (cg + 4 * t) * 32 + half * 16, rs);
-              tmem_ld_32x16(tmem + lane_off + kColDP + (cg + 4 * t) * 32 + half * 16, rd);
-              tmem_ld_wait();
-              pass1((wd[t] >> (16 * half)) & 0xffffu, rs, rd, pk[t * 2 + half]);
+              if (live[t][half]) {
+                uint32_t rs[16], rd[16];
+                tmem_ld_32x16(tmem + lane_off + kColS0 + (cg + 4 * t) * 32 + half * 16, rs);
+                tmem_ld_32x16(tmem + lane_off + kColDP + (cg + 4 * t) * 32 + half * 16, rd);
+                tmem_ld_wait();
+                pass1((wd[t] >> (16 * half)) & 0xffffu, rs, rd, pk[t * 2 + half]);
+              }
             }
           }
         }
@@ -1409,23 +1443,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
           if (head_mode) { tc_fence_after(); store_dq(i - 1); tc_fence_before(); }
         }
         {
-          uint32_t r0[16], r1[16];
-          tmem_ld_32x16(tmem + lane_off + kColDP + cg * 32, r0);
-          tmem_ld_32x16(tmem + lane_off + kColDP + cg * 32 + 16, r1);
+          uint32_t r0[16] = {}, r1[16] = {};
+          if (live[0][0]) tmem_ld_32x16(tmem + lane_off + kColDP + cg * 32, r0);
+          if (live[0][1]) tmem_ld_32x16(tmem + lane_off + kColDP + cg * 32 + 16, r1);
           tmem_ld_wait();
           if (!has[1]) { tc_fence_before(); mbar_arrive(&sm.dp_empty); }
-          pass2(cg, 0, dw, r0, pk[0]);
-          pass2(cg, 1, dw, r1, pk[1]);
+          if (live[0][0]) pass2(cg, 0, dw, r0, pk[0]);
+          if (live[0][1]) pass2(cg, 1, dw, r1, pk[1]);
         }
         if (has[1]) {
-          uint32_t r0[16], r1[16];
-          tmem_ld_32x16(tmem + lane_off + kColDP + (cg + 4) * 32, r0);
-          tmem_ld_32x16(tmem + lane_off + kColDP + (cg + 4) * 32 + 16, r1);
+          uint32_t r0[16] = {}, r1[16] = {};
+          if (live[1][0]) tmem_ld_32x16(tmem + lane_off + kColDP + (cg + 4) * 32, r0);
+          if (live[1][1]) tmem_ld_32x16(tmem + lane_off + kColDP + (cg + 4) * 32 + 16, r1);
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(&sm.dp_empty);
-          pass2(cg + 4, 0, dw, r0, pk[2]);
-          pass2(cg + 4, 1, dw, r1, pk[3]);
+          if (live[1][0]) pass2(cg + 4, 0, dw, r0, pk[2]);
+          if (live[1][1]) pass2(cg + 4, 1, dw, r1, pk[3]);
         }
       }
       if (threadIdx.x == 64) TRACE(3, 5 * i + 4);
