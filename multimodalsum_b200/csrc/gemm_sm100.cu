@@ -18,11 +18,13 @@
 // TMEM holds two accumulator stages (2 x BN fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Ragged M/N/K edges rely on TMA: out-of-bounds loads are zero-filled, out-of-bounds stores are clipped.
 //
-// CL = 2 (large problems): the persistent CTAs run as thread-block clusters of two that walk the SAME n-tile on adjacent
-// m-tiles in lock-step.  Each CTA fetches its own A tile and HALF of the shared B tile, which TMA multicasts into both CTAs'
-// shared memory: per k-block a CTA pulls 32 KB instead of 48 KB out of L2 (the 128 x 256 tile at 1 CTA/SM was limited by
-// L2 -> SM operand bandwidth, 96 B/clk/SM; tensor pipe 72 % active in profiles/r01_ncu_gemm_plain_v4_summary.txt).  A stage
-// is recycled only when BOTH CTAs' MMAs have retired it: tcgen05.commit arrives (multicast) on both CTAs' empty barriers.
+// CL = 2 (large problems): the persistent CTAs run as thread-block clusters of two — a CTA PAIR on the two SMs of a TPC — and
+// one tcgen05.mma.cta_group::2 (M = 256, N = 256, issued by the leader CTA only) computes two adjacent m-tiles of the same
+// n-tile.  Each CTA stages its own 128 A rows and HALF of the B tile (128 of the 256 n rows); the tensor cores read the other
+// half out of the peer's shared memory, so per k-block a CTA moves 32 KB instead of 48 KB through L2 -> smem and the smem
+// operand reads per MMA drop by a third (6 stages fit instead of 4).  Both CTAs' TMA loads complete on the LEADER's full
+// barrier; tcgen05.commit.cta_group::2 (multicast) frees the stage in both CTAs and publishes the accumulator halves, which
+// each CTA's epilogue warps read from their own tensor memory; accumulator stages are handed back on the leader's barrier.
 #include "common.cuh"
 #include "../../include/mmsum_b200.h"
 
@@ -40,12 +42,12 @@ static constexpr int kEpiWarps = 8;   // two warps per TMEM lane quarter, each o
 static constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 static constexpr int kEpiBufBytes = 32 * 128;  // 32 rows x 128 B per staging buffer
 
-template <int BN>
+template <int BN, int CL>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CL) * BK * 2;           // CTA pair: this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (CL == 2) ? 6 : ((BN == 256) ? 4 : 6);
   static constexpr int kEpiBytes = kEpiWarps * kEpiBufBytes;     // one staging buffer per epilogue warp
   static constexpr int kBarOffset = kStages * kStageBytes + kEpiBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
@@ -82,7 +84,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                     const __grid_constant__ CUtensorMap tmAux,
                     const GemmKernelArgs g) {
-  using L = GemmSmem<BN>;
+  using L = GemmSmem<BN, CL>;
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window with pointer arithmetic on the __shared__ array (keeps LDS/STS addressing)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -104,13 +106,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < L::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
-      for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * 32); }
+      for (int s = 0; s < L::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      // CTA pair: one arrival per epilogue warp of BOTH CTAs on the leader's barrier; otherwise one per epilogue thread
+      for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], CL == 2 ? 2 * kEpiWarps : kEpiWarps * 32); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (CL == 2) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
+    else         { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -133,6 +136,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sA = smem + stage * L::kStageBytes;
         uint8_t* sB = sA + L::kABytes;
+        if (CL == 2) {
+          // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both stages
+          const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (crank == 0) mbar_expect_tx_w(&full_bar[stage], 2 * L::kStageBytes);
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm_w(sA + j * 8192, &tmA, lbar, m0 + 64 * j, k0);
+          } else if (g.k_split > 0 && k0 >= g.k_split) {
+            tma_load_2d_2sm_w(sA, &tmA2, lbar, k0 - g.k_split, m0);
+          } else {
+            tma_load_2d_2sm_w(sA, &tmA, lbar, k0, m0);
+          }
+          // this CTA's half of the B tile (n rows [crank * BN/2, +BN/2)); the pair's MMA reads the other half from the peer
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm_w(sB + j * 8192, &tmB, lbar, n0 + crank * (BN / 2) + 64 * j, k0);
+          } else {
+            tma_load_2d_2sm_w(sB, &tmB, lbar, k0, n0 + crank * (BN / 2));
+          }
+          if (++stage == L::kStages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         mbar_expect_tx_w(&full_bar[stage], L::kStageBytes);
         if (A_MN) {
 #pragma unroll
@@ -142,18 +167,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else {
           tma_load_2d_w(sA, &tmA, &full_bar[stage], k0, m0);
         }
-        if (CL == 2) {
-          // this CTA's half of the B tile, delivered to both CTAs of the pair (the other half arrives from the peer)
-          if (B_MN) {
-#pragma unroll
-            for (int j = 0; j < BN / 128; ++j) {
-              const int jj = crank * (BN / 128) + j;
-              tma_load_2d_mc_w(sB + jj * 8192, &tmB, &full_bar[stage], n0 + 64 * jj, k0, (uint16_t)3);
-            }
-          } else {
-            tma_load_2d_mc_w(sB + crank * (BN / 2) * 128, &tmB, &full_bar[stage], k0, n0 + crank * (BN / 2), (uint16_t)3);
-          }
-        } else if (B_MN) {
+        if (B_MN) {
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) tma_load_2d_w(sB + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, k0);
         } else {
@@ -163,12 +177,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp runs the loop; lane 0 issues) =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    // ===================== MMA issuer (whole warp runs the loop; lane 0 issues; CTA pair: the leader CTA only) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM * CL, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     const uint32_t smem_base = smem_u32(smem);
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
-    for (int t = unit0; t < total_tiles; t += unit_stride) {
+    for (int t = unit0; t < total_tiles && crank == 0; t += unit_stride) {
       int mu, nt, sp; decode_tile(g, m_units, t, mu, nt, sp);
       const int k_begin = sp * g.k_per_split;
       const int k_end = min(g.K, k_begin + g.k_per_split);
@@ -187,15 +201,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint64_t bd0 = B_MN ? umma_smem_desc_sw128(baddr, 8192, 1024) : umma_smem_desc_sw128(baddr, 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-          umma_bf16_w(d_tmem, ad0 + (uint64_t)((A_MN ? kk * 2048 : kk * 32) >> 4),
-                      bd0 + (uint64_t)((B_MN ? kk * 2048 : kk * 32) >> 4), idesc, accum);
+          if (CL == 2) umma_bf16_2sm_w(d_tmem, ad0 + (uint64_t)((A_MN ? kk * 2048 : kk * 32) >> 4),
+                                       bd0 + (uint64_t)((B_MN ? kk * 2048 : kk * 32) >> 4), idesc, accum);
+          else         umma_bf16_w(d_tmem, ad0 + (uint64_t)((A_MN ? kk * 2048 : kk * 32) >> 4),
+                                   bd0 + (uint64_t)((B_MN ? kk * 2048 : kk * 32) >> 4), idesc, accum);
           accum = 1;
         }
-        // frees the smem stage once these MMAs retire (in BOTH CTAs of a pair: the peer's next multicast writes here too)
-        if (CL == 2) umma_commit_mc_w(&empty_bar[stage], (uint16_t)3); else umma_commit_w(&empty_bar[stage]);
+        // frees the smem stage once these MMAs retire (CTA pair: in BOTH CTAs, each producer refills its own stage)
+        if (CL == 2) umma_commit_2sm_mc_w(&empty_bar[stage], (uint16_t)3); else umma_commit_w(&empty_bar[stage]);
         if (++stage == L::kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit_w(&tfull_bar[as]);       // accumulator complete
+      // accumulator complete (CTA pair: each CTA's epilogue warps wait on their own barrier for their 128 rows)
+      if (CL == 2) umma_commit_2sm_mc_w(&tfull_bar[as], (uint16_t)3); else umma_commit_w(&tfull_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
@@ -341,7 +358,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      if (CL == 2) {   // one arrival per warp on the leader's barrier (its MMA warp owns the accumulator stages of both CTAs)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+      } else {
+        mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -353,7 +375,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CL == 2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -428,7 +450,7 @@ template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& td,
                        const CUtensorMap& taux,
                        const GemmKernelArgs& ka, int grid, cudaStream_t stream) {
-  using L = GemmSmem<BN>;
+  using L = GemmSmem<BN, CL>;
   static std::atomic<unsigned long long> attr_set{0};     // one per template instantiation
   if (int rc = ensure_dyn_smem(gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CL>, L::kTotal, attr_set)) return rc;
   cudaError_t le = launch_pdl_cluster(gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI, CL>, dim3(grid), dim3(kGemmThreads), (size_t)L::kTotal,
@@ -517,10 +539,9 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
     ta2 = ta;
   }
   if (rc) return rc;
-  // CTA pairs with a multicast B tile for problems that fill the machine with 256-wide tiles.  Opt-in (MMSUM_GEMM_CLUSTER=1):
-  // measured on B200 it halves the B-operand L2 reads but moves neither the kernel time nor the tensor-pipe activity
-  // (profiles/r02_gemm_cluster_ab.txt: L2 was never the limiter at 31-52 % of its peak), so the simpler launch is the default.
-  static const bool cluster_off = [] { const char* e = getenv("MMSUM_GEMM_CLUSTER"); return !(e && e[0] == '1'); }();
+  // CTA pairs (cta_group::2) for problems that fill the machine with 256-wide tiles: +11-15 % on the step's large shapes
+  // (profiles/r02_gemm_2sm_ab.txt).  MMSUM_GEMM_CLUSTER=0 switches back to single-CTA tiles for the A/B.
+  static const bool cluster_off = [] { const char* e = getenv("MMSUM_GEMM_CLUSTER"); return e && e[0] == '0'; }();
   const int nsm = num_sms();
   const long long pairs = (long long)((ka.m_tiles + 1) / 2) * ka.n_tiles * ka.splits;
   const int cl = (!cluster_off && bn == 256 && ka.m_tiles >= 2 && pairs * 2 >= nsm && (nsm % 2) == 0) ? 2 : 1;

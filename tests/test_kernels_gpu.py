@@ -91,6 +91,56 @@ def test_gemm_epilogues_and_cat():
     _close(out, torch.cat([A, A2], 1).float() @ B2.float().t() + bias, 1e-2, "cat")
 
 
+@pytest.mark.parametrize("a_t,b_t,f32,acc", [(0, 0, 0, 0), (0, 1, 0, 0), (1, 1, 1, 1), (1, 0, 0, 0), (0, 0, 1, 1)])
+def test_gemm_cta_pair_shapes(a_t, b_t, f32, acc):
+    """Problems large enough for the CTA-pair kernel (tcgen05.mma.cta_group::2, M = 256 per instruction, each CTA staging half
+    of the B tile): an odd number of m-tiles (the last pair has an out-of-range second tile), ragged M / N / K edges, all four
+    operand layouts, bf16 and fp32-accumulating (split-K) outputs."""
+    ops = _ops()
+    torch.manual_seed(2)
+    M, N, K = 2400, 2040, 1000          # 19 x 8 tiles of 128 x 256: 80 pairs >= 74
+    ldk = (K + 7) // 8 * 8
+    A = torch.randn((K, M) if a_t else (M, ldk), device=_dev()).to(torch.bfloat16)
+    B = torch.randn((K, N) if b_t else (N, ldk), device=_dev()).to(torch.bfloat16)
+    if not a_t:
+        A = A[:, :K]
+    if not b_t:
+        B = B[:, :K]
+    out = torch.randn(M, N, device=_dev()) if acc else None
+    base = out.clone() if acc else 0
+    Dm = ops.gemm(A, B, out, a_t=bool(a_t), b_t=bool(b_t), out_dtype=torch.float32 if f32 else torch.bfloat16, accumulate=bool(acc))
+    Af = A.float().t() if a_t else A.float()
+    Bf = B.float().t() if b_t else B.float()
+    _close(Dm, Af @ Bf.t() + base, 1.5e-2 if not f32 else 2e-3, "pair gemm")
+
+
+def test_gemm_cta_pair_epilogues_and_cat():
+    """Fused-activation epilogues and the K-concatenated A operand on the CTA-pair kernel (step-sized M)."""
+    ops = _ops()
+    torch.manual_seed(3)
+    M, N, K = 4736, 1024, 512           # 37 x 4 tiles: 76 pairs
+    A = torch.randn(M, K, device=_dev()).to(torch.bfloat16)
+    B = (torch.randn(N, K, device=_dev()) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device=_dev())
+    aux = torch.empty(M, N, device=_dev(), dtype=torch.bfloat16)
+    out = ops.gemm(A, B, bias=bias, act=ops.ACT_GELU, aux=aux, aux_mode=ops.AUX_STORE_PREACT)
+    pre = A.float() @ B.float().t() + bias
+    _close(aux, pre, 1e-2, "preact")
+    _close(out, F.gelu(pre), 1e-2, "gelu")
+    h = torch.randn(M, N, device=_dev()).to(torch.bfloat16)
+    out = ops.gemm(A, B, act=ops.ACT_GELU, aux=h, aux_mode=ops.AUX_MUL_DACT)
+    hf = h.float().requires_grad_(True)
+    F.gelu(hf).sum().backward()
+    _close(out, (A.float() @ B.float().t()) * hf.grad, 1e-2, "dgelu")
+    Bt = (torch.randn(K, N, device=_dev()) * 0.05).to(torch.bfloat16)
+    out = ops.gemm(A, Bt, b_t=True, act=ops.ACT_GELU, aux=h, aux_mode=ops.AUX_MUL_DACT)
+    _close(out, (A.float() @ Bt.float()) * hf.grad, 1e-2, "dgelu, B MN-major")
+    A2 = torch.randn(M, K, device=_dev()).to(torch.bfloat16)
+    B2 = (torch.randn(N, 2 * K, device=_dev()) * 0.05).to(torch.bfloat16)
+    out = ops.gemm_cat(A, A2, B2, bias=bias)
+    _close(out, torch.cat([A, A2], 1).float() @ B2.float().t() + bias, 1e-2, "cat")
+
+
 # ------------------------------------------------------------------ LayerNorm blocks
 def test_add_ln_fwd_bwd():
     ops = _ops()
@@ -458,6 +508,12 @@ def test_kernels_ignore_stale_onchip_state(variant):
     torch.manual_seed(6)
     A = torch.randn(1000, 520, device=_dev()).to(torch.bfloat16)
     Bm = torch.randn(776, 520, device=_dev()).to(torch.bfloat16)
+    ref = ops.gemm(A, Bm)
+    ops.debug_poison()
+    got = ops.gemm(A, Bm)
+    assert torch.equal(ref, got)
+    A = torch.randn(2400, 1000, device=_dev()).to(torch.bfloat16)      # CTA-pair kernel
+    Bm = torch.randn(2040, 1000, device=_dev()).to(torch.bfloat16)
     ref = ops.gemm(A, Bm)
     ops.debug_poison()
     got = ops.gemm(A, Bm)
