@@ -38,8 +38,9 @@ typedef struct MmsumGemmArgs {
   float alpha;
   const float* bias;  /* fp32 [N] or NULL, added after alpha */
   int32_t act;        /* 0 none, 1 GELU(erf), 2 ReLU */
-  int32_t aux_mode;   /* 0 none, 1 store pre-activation (bf16) to aux, 2 multiply result by act'(aux);
-                         1 and 2 need bf16 output and a row-major A (a_mn_major = 0) */
+  int32_t aux_mode;   /* 0 none, 1 store pre-activation (bf16) to aux, 2 multiply result by act'(aux),
+                         3 store act'(pre-activation) to aux (GELU only), 4 multiply result by aux;
+                         1..4 need bf16 output and a row-major A (a_mn_major = 0) */
   void* aux;          /* bf16 [M,N] */
   int64_t ld_aux;
   const void* A2;     /* optional: A = [A | A2] concatenated along K at k_split (K-major A only), else NULL */

@@ -327,9 +327,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int half = 0; half < 2; ++half) {
             float v[32];
             load_chunk(2 * grp + half, v);
-            if (EPI == 1) pack16(v, prep[EPI == 1 ? half : 0]);     // pre-activation, saved for the backward epilogue
+            if (EPI == 1 && g.aux_mode == 1) pack16(v, prep[EPI == 1 ? half : 0]);     // pre-activation, saved for the backward epilogue
             if (EPI != 2) {
-              if (g.act == 1) {
+              if (EPI == 1 && g.aux_mode == 3) {
+                // GELU and GELU' from one erf / exp evaluation; the DERIVATIVE is saved, so backward is a single multiply
+                float dv[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) gelu_erf_and_grad2(v[i], v[i + 1], dv[i], dv[i + 1]);
+                pack16(dv, prep[EPI == 1 ? half : 0]);
+              } else if (g.act == 1) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) gelu_erf2(v[i], v[i + 1]);
               } else if (g.act == 2) {
@@ -345,7 +351,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 h = unpack_bf16(w[e]);
-                  if (g.act == 1) { gelu_erf_grad_mul2(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1], h.x, h.y); }
+                  if (g.aux_mode == 4) { v[j * 8 + 2 * e] *= h.x; v[j * 8 + 2 * e + 1] *= h.y; }      // aux holds act'(pre-activation)
+                  else if (g.act == 1) { gelu_erf_grad_mul2(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1], h.x, h.y); }
                   else            { v[j * 8 + 2 * e] *= (h.x > 0.f) ? 1.f : 0.f; v[j * 8 + 2 * e + 1] *= (h.y > 0.f) ? 1.f : 0.f; }
                 }
               }
@@ -479,7 +486,8 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
   }
   if (bn != 128 && bn != 256) return MMSUM_ERR_INVALID;
   if (a->aux_mode != 0) {   // fused-activation epilogues exist for row-major A and 256-wide tiles
-    if (a->aux_mode < 0 || a->aux_mode > 2 || a->a_mn_major) return MMSUM_ERR_INVALID;
+    if (a->aux_mode < 0 || a->aux_mode > 4 || a->a_mn_major) return MMSUM_ERR_INVALID;
+    if (a->aux_mode == 3 && a->act != 1) return MMSUM_ERR_INVALID;      // the saved derivative exists for GELU
     bn = 256;
   }
 
@@ -552,7 +560,7 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
   else            rc = make_tmap(&td, a->D, 0, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldd * 2, 64, 32);
   if (rc) return rc;
   CUtensorMap taux = td;   // pre-activation copy (aux_mode 1) leaves through its own map, same tiling as D
-  if (a->aux_mode == 1) {
+  if (a->aux_mode == 1 || a->aux_mode == 3) {
     rc = make_tmap(&taux, a->aux, 0, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ld_aux * 2, 64, 32);
     if (rc) return rc;
   }
@@ -563,7 +571,7 @@ extern "C" int mmsum_gemm_bf16(const MmsumGemmArgs* a, void* stream_v) {
   int grid = total < nsm ? total : nsm;
   if (cl == 2) grid = (int)(pairs * 2 < nsm ? pairs * 2 : nsm);
   const int am = a->a_mn_major ? 1 : 0, bm = a->b_mn_major ? 1 : 0;
-  const int epi = a->aux_mode;
+  const int epi = (a->aux_mode == 3) ? 1 : (a->aux_mode == 4 ? 2 : a->aux_mode);   // 3 / 4 share the kernels of 1 / 2
 #define MMSUM_GEMM_CASE(BN_, AM_, BM_, EPI_, CL_) \
   if (bn == BN_ && am == AM_ && bm == BM_ && epi == EPI_ && cl == CL_) \
     return launch_gemm<BN_, (AM_ != 0), (BM_ != 0), EPI_, CL_>(ta, ta2, tb, td, taux, ka, grid, stream);

@@ -13,7 +13,7 @@ LAUNCHES = 0      # kernels launched through the C-ABI since import (bench.py: g
 KERNEL_TIMER = None
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
-AUX_NONE, AUX_STORE_PREACT, AUX_MUL_DACT = 0, 1, 2
+AUX_NONE, AUX_STORE_PREACT, AUX_MUL_DACT, AUX_STORE_DACT, AUX_MUL = 0, 1, 2, 3, 4
 
 
 def check(rc, what, n_kernels=1):

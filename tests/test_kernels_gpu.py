@@ -85,6 +85,15 @@ def test_gemm_epilogues_and_cat():
     hf = h.float().requires_grad_(True)
     F.gelu(hf).sum().backward()
     _close(out, (A.float() @ B.float().t()) * hf.grad, 1e-2, "dgelu")
+    # the pair the training step uses: the forward epilogue saves GELU'(pre-activation), backward multiplies by it
+    dact = torch.empty(M, N, device=_dev(), dtype=torch.bfloat16)
+    out = ops.gemm(A, B, bias=bias, act=ops.ACT_GELU, aux=dact, aux_mode=ops.AUX_STORE_DACT)
+    pf = pre.clone().requires_grad_(True)
+    F.gelu(pf).sum().backward()
+    _close(out, F.gelu(pre), 1e-2, "gelu (derivative saved)")
+    _close(dact, pf.grad, 1e-2, "saved gelu'")
+    out = ops.gemm(A, B, aux=h, aux_mode=ops.AUX_MUL)
+    _close(out, (A.float() @ B.float().t()) * h.float(), 1e-2, "multiply by aux")
     A2 = torch.randn(M, K, device=_dev()).to(torch.bfloat16)
     B2 = (torch.randn(N, 2 * K, device=_dev()) * 0.05).to(torch.bfloat16)
     out = ops.gemm_cat(A, A2, B2, bias=bias)
