@@ -104,6 +104,18 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return y;
 }
 // Blackwell packed fp32 pairs (FFMA2 / FMUL2): one issue slot for two lanes of the same elementwise chain.
+#ifndef MMSUM_SCALAR_PAIRS
+#define MMSUM_SCALAR_PAIRS 0   // experiment: the same helpers on two scalar FFMA / FMUL / FADD (A/B of the packed instructions)
+#endif
+#if MMSUM_SCALAR_PAIRS
+struct f32x2 { float a, b; };
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 o; o.a = a; o.b = b; return o; }
+__device__ __forceinline__ f32x2 splat2(float a) { return pack2(a, a); }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { a = v.a; b = v.b; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { return pack2(fmaf(a.a, b.a, c.a), fmaf(a.b, b.b, c.b)); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { return pack2(a.a * b.a, a.b * b.b); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { return pack2(a.a + b.a, a.b + b.b); }
+#else
 struct f32x2 { uint64_t r; };
 __device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 o; asm("mov.b64 %0, {%1, %2};" : "=l"(o.r) : "f"(a), "f"(b)); return o; }
 __device__ __forceinline__ f32x2 splat2(float a) { return pack2(a, a); }
@@ -111,6 +123,7 @@ __device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 o; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(o.r) : "l"(a.r), "l"(b.r), "l"(c.r)); return o; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 o; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(o.r) : "l"(a.r), "l"(b.r)); return o; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 o; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(o.r) : "l"(a.r), "l"(b.r)); return o; }
+#endif
 
 // erf(x / sqrt(2)) for a pair; E = exp(-x*x/2)
 __device__ __forceinline__ f32x2 erf_as2(float x0, float x1, f32x2 x, f32x2& E) {
