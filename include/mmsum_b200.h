@@ -80,6 +80,9 @@ typedef struct MmsumAttnArgs {
   void* dKV; int64_t lddkv; int32_t dk_col; int32_t dv_col;    /* bwd out, bf16, same row indexing as KV */
   int32_t n_qseq, H, R, causal, n_mod, E_total;
   float scale;
+  int32_t q_rows;      /* rows of Q / O / dQ per query sequence (the frame stride), 0 = 128; a multiple of 16 <= 128.  Rows beyond
+                          q_rows of a sequence's 128-row query tile belong to the next sequence: they are computed and dropped
+                          (forward / dQ) or masked (dK/dV).  LSE / DELTA keep 128 slots per sequence. */
   MmsumAttnMod mods[3];
 } MmsumAttnArgs;
 int mmsum_attn_fwd(const MmsumAttnArgs* args, void* stream);
@@ -180,6 +183,8 @@ int mmsum_ce_fwd_bwd(void* logits, int64_t ld, int32_t rows, int32_t V, const in
  * (src/multimodal_train.py:154-156), memory key/entity validity, 1/#valid entities, modality presence */
 typedef struct MmsumPrepArgs {
   int32_t B, R, S, F, n_img, img_keys, n_mod, pad_id, bos_id, eos_id;
+  int32_t S_enc;       /* encoder frame: the first S_enc <= S tokens of every review (0 = S); every token beyond it must be pad.
+                          enc_ids / enc_valid / the text region of mem_valid then have B*R*S_enc entries */
   int32_t* enc_ids;    /* [B*R*S] */
   int32_t* dec_ids;    /* [B*R*S] */
   int32_t* labels;     /* [B*R*S] */

@@ -45,13 +45,13 @@ class AttnArgs(C.Structure):
         ("dQ", C.c_void_p), ("lddq", C.c_int64), ("dq_col", C.c_int32),
         ("dKV", C.c_void_p), ("lddkv", C.c_int64), ("dk_col", C.c_int32), ("dv_col", C.c_int32),
         ("n_qseq", C.c_int32), ("H", C.c_int32), ("R", C.c_int32), ("causal", C.c_int32),
-        ("n_mod", C.c_int32), ("E_total", C.c_int32), ("scale", C.c_float),
+        ("n_mod", C.c_int32), ("E_total", C.c_int32), ("scale", C.c_float), ("q_rows", C.c_int32),
         ("mods", AttnMod * 3),
     ]
 
 
 class PrepArgs(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("B", "R", "S", "F", "n_img", "img_keys", "n_mod", "pad_id", "bos_id", "eos_id")] + \
+    _fields_ = [(n, C.c_int32) for n in ("B", "R", "S", "F", "n_img", "img_keys", "n_mod", "pad_id", "bos_id", "eos_id", "S_enc")] + \
                [(n, C.c_void_p) for n in ("enc_ids", "dec_ids", "labels", "enc_valid", "dec_valid", "mem_valid",
                                           "ent_valid", "pres", "rating_diff", "inv_n")]
 

@@ -838,7 +838,8 @@ attn_fwd_tc3_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p
   const int h = head_mode ? 0 : (int)((sidx / p.R) % p.H);
   const int biz = head_mode ? (int)(sidx / p.R) : (int)(sidx / (p.R * p.H));
   const int qseq = biz * p.R + tgt;
-  const int qrow0 = qseq * SQ;
+  const int QS = p.q_rows > 0 ? p.q_rows : SQ;      // query rows of a sequence (frame stride); rows >= QS of the tile are dropped
+  const int qrow0 = qseq * QS;
   auto item_head = [&](int i) { return head_mode ? part * head_mode + i : h; };
 
   if (warp == 0) {
@@ -949,12 +950,14 @@ attn_fwd_tc3_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p
     bf16* Og = reinterpret_cast<bf16*>(p.O);
     auto store_out = [&](int m, int head) {        // acc -> bf16 output row, then reset
       bf16* dst = Og + p.mods[m].o_off + (long long)(qrow0 + row) * p.ldo + head * HD;
+      if (row < QS) {
 #pragma unroll
-      for (int j = 0; j < HD / 8; ++j) {
-        uint4 u;
-        u.x = pack_bf16(acc[j * 8 + 0], acc[j * 8 + 1]); u.y = pack_bf16(acc[j * 8 + 2], acc[j * 8 + 3]);
-        u.z = pack_bf16(acc[j * 8 + 4], acc[j * 8 + 5]); u.w = pack_bf16(acc[j * 8 + 6], acc[j * 8 + 7]);
-        *reinterpret_cast<uint4*>(dst + j * 8) = u;
+        for (int j = 0; j < HD / 8; ++j) {
+          uint4 u;
+          u.x = pack_bf16(acc[j * 8 + 0], acc[j * 8 + 1]); u.y = pack_bf16(acc[j * 8 + 2], acc[j * 8 + 3]);
+          u.z = pack_bf16(acc[j * 8 + 4], acc[j * 8 + 5]); u.w = pack_bf16(acc[j * 8 + 6], acc[j * 8 + 7]);
+          *reinterpret_cast<uint4*>(dst + j * 8) = u;
+        }
       }
 #pragma unroll
       for (int i = 0; i < HD; ++i) acc[i] = 0.f;
@@ -1104,7 +1107,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
   const int h = head_mode ? 0 : (int)((blockIdx.x / p.R) % p.H);
   const int biz = head_mode ? (int)(blockIdx.x / p.R) : (int)(blockIdx.x / (p.R * p.H));
   const int qseq = biz * p.R + tgt;
-  const int qrow0 = qseq * SQ;
+  const int QS = p.q_rows > 0 ? p.q_rows : SQ;      // query rows of a sequence (frame stride); rows >= QS of the tile are dropped
+  const int qrow0 = qseq * QS;
   auto item_head = [&](int i) { return head_mode ? i : h; };
   uint8_t* const q_stage1 = sm.ds + 2 * SQ * 128;
   uint8_t* const da_stage1 = sm.ds + 3 * SQ * 128;
@@ -1254,6 +1258,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
       uint32_t r[16];
       tmem_ld_32x16(tmem + lane_off + kColDQ + cg * 16, r);
       tmem_ld_wait();
+      if (row >= QS) return;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         uint4 u;
@@ -1474,8 +1479,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs
     } else {
       for (int hh = head_mode ? 0 : h; hh < (head_mode ? p.H : h + 1); ++hh) {
         bf16* dQg = reinterpret_cast<bf16*>(p.dQ) + (long long)(qrow0 + row) * p.lddq + p.dq_col + hh * HD + cg * 16;
-        *reinterpret_cast<uint4*>(dQg) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(dQg + 8) = make_uint4(0, 0, 0, 0);
+        if (row < QS) {
+          *reinterpret_cast<uint4*>(dQg) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(dQg + 8) = make_uint4(0, 0, 0, 0);
+        }
       }
     }
   }
@@ -1541,6 +1548,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
   // shared address space (LDS/STS instead of generic LD/ST)
   BwdKVSmem& sm = *reinterpret_cast<BwdKVSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int QS = p.q_rows > 0 ? p.q_rows : SQ;      // query rows of a sequence (frame stride); queries >= QS are masked
   int rem = blockIdx.x % tiles_per_bh;
   const int bh = blockIdx.x / tiles_per_bh;
   // head mode (self-attention): the CTA owns one (sequence, key tile) and walks a group of heads, so the set-up is paid once
@@ -1631,7 +1639,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
         tma_load_2d(sm.v, &kv128, &sm.kv_full, p.v_col + h * HD, kvrow0);
         for (int s = 0; s < n_steps; ++s) {
           const int g = g0 + s, st = g % kKvStages;
-          const int qrow0 = (biz * p.R + step_target(s)) * SQ + (s & 1) * QH;
+          const int qrow0 = (biz * p.R + step_target(s)) * QS + (s & 1) * QH;
           mbar_wait(&sm.qd_empty[st], ((g / kKvStages) & 1) ^ 1);
           mbar_expect_tx(&sm.qd_full[st], 2 * QH * 128);
           tma_load_2d(sm.q[st], &q64, &sm.qd_full[st], p.q_col + h * HD, qrow0);
@@ -1761,6 +1769,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
         const int lo = key0 + row - (s & 1) * QH - cg * 32;
         wd &= (lo <= 0) ? 0xffffffffu : (lo >= 32 ? 0u : ~((1u << lo) - 1u));
       }
+      // queries beyond the sequence's frame (q_rows < 128): their Q / dA rows belong to the next sequence
+      const int qleft = QS - (s & 1) * QH - cg * 32;
+      const bool qpartial = qleft < 32;
+      if (qpartial) wd &= (qleft <= 0) ? 0u : ((1u << qleft) - 1u);
       mbar_wait(&sm.sdp_full, g & 1);
       if (threadIdx.x == 64) TRACE(6, 6 * s + 2);
       tc_fence_after();
@@ -1827,7 +1839,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
       }
       };
       if (__all_sync(0xffffffffu, wd == 0xffffffffu)) body(std::integral_constant<int, 0>{});
-      else if (p.causal) body(std::integral_constant<int, 1>{});
+      else if (p.causal || qpartial) body(std::integral_constant<int, 1>{});
       else body(std::integral_constant<int, 2>{});
       if (threadIdx.x == 64) TRACE(6, 6 * s + 5);
 #if MMSUM_DKV_TS
@@ -1888,6 +1900,7 @@ static int validate_tc(const MmsumAttnArgs* a, bool bwd) {
   }
   if (ents > kMaxEnt || ents > a->E_total || ents > 32) return MMSUM_ERR_INVALID;
   if (a->causal && (a->n_mod != 1 || a->mods[0].Sk != SQ)) return MMSUM_ERR_INVALID;
+  if (a->q_rows != 0 && (a->q_rows < 16 || a->q_rows > SQ || (a->q_rows % 16) || a->causal)) return MMSUM_ERR_INVALID;
   if (bwd) {
     if (!a->DELTA || !a->dQ || !a->dKV) return MMSUM_ERR_INVALID;
     if ((a->lddq % 8) || (a->lddkv % 8) || (a->dq_col % 8) || (a->dk_col % 8) || (a->dv_col % 8)) return MMSUM_ERR_INVALID;
@@ -1897,7 +1910,7 @@ static int validate_tc(const MmsumAttnArgs* a, bool bwd) {
 
 static int build_maps(const MmsumAttnArgs* a, AttnMaps* mp, bool bwd) {
   const int n_biz = a->n_qseq / a->R;
-  const uint64_t qrows = (uint64_t)a->n_qseq * SQ;
+  const uint64_t qrows = (uint64_t)a->n_qseq * (a->q_rows > 0 ? a->q_rows : SQ);   // rows past the last frame: TMA zero fill
   int rc = make_tmap(&mp->q, a->Q, 0, (uint64_t)a->ldq, qrows, (uint64_t)a->ldq * 2, 64, SQ);
   if (rc) return rc;
   for (int m = 0; m < 3; ++m) {
@@ -1972,7 +1985,8 @@ extern "C" int mmsum_attn_fwd(const MmsumAttnArgs* a, void* stream_v) {
   static const bool env_v1 = (getenv("MMSUM_ATTN_FWD_V1") != nullptr);   // A/B switch: the first forward kernel
   static const bool env_v2 = (getenv("MMSUM_ATTN_FWD_V2") != nullptr);   // A/B switch: two coupled groups in one CTA
   const int variant = g_fwd_variant.load();
-  const bool use_v1 = variant ? variant == 1 : env_v1, use_v2 = variant ? variant == 2 : env_v2;
+  const bool short_frames = a->q_rows != 0 && a->q_rows != SQ;     // only the default kernel drops rows beyond q_rows
+  const bool use_v1 = !short_frames && (variant ? variant == 1 : env_v1), use_v2 = !short_frames && (variant ? variant == 2 : env_v2);
   if (!use_v1 && !use_v2) {
     const int smem3 = (int)sizeof(Fwd3Smem) + 1024;
     static std::atomic<unsigned long long> attr3{0};
@@ -2008,7 +2022,7 @@ extern "C" int mmsum_attn_bwd(const MmsumAttnArgs* a, void* stream_v) {
   CUtensorMap kv128, q64, do64;
   if (int rc = make_tmap(&kv128, a->KV, 0, (uint64_t)a->ldkv, kvrows, (uint64_t)a->ldkv * 2, 64, SQ)) return rc;
   {   // 64-query boxes of Q and of the upstream gradient for the dK/dV kernel's steps
-    const uint64_t qrows = (uint64_t)a->n_qseq * SQ;
+    const uint64_t qrows = (uint64_t)a->n_qseq * (a->q_rows > 0 ? a->q_rows : SQ);
     uint64_t orows = 0;
     for (int m = 0; m < a->n_mod; ++m) {
       const uint64_t r = (uint64_t)(a->mods[m].o_off / a->ldo) + qrows;

@@ -635,16 +635,20 @@ __global__ void __launch_bounds__(128) prep_step_kernel(const int64_t* __restric
                                                         const uint8_t* __restrict__ img_mask, MmsumPrepArgs a) {
   const int b = blockIdx.x;
   const int R = a.R, S = a.S;
+  const int SE = a.S_enc > 0 ? a.S_enc : S;      // encoder frame: the first SE tokens of a review (the rest is pad by contract)
   const int n_ent = R + (a.F > 0 ? 1 : 0) + a.n_img;
   for (int i = threadIdx.x; i < R * S; i += blockDim.x) {
     const int r = i / S, t = i - r * S;
     const long long gi = ((long long)b * R + r) * S + t;
     const long long tok = (long long)reviews[gi];
-    a.enc_ids[gi] = (int)tok;
     a.labels[gi] = (int)tok;
-    const uint8_t kv = reviews_mask[gi] != 0 ? 1 : 0;
-    a.enc_valid[gi] = kv;
-    a.mem_valid[gi] = kv;   // text region of the memory comes first
+    if (t < SE) {
+      const long long ge = ((long long)b * R + r) * SE + t;
+      a.enc_ids[ge] = (int)tok;
+      const uint8_t kv = reviews_mask[gi] != 0 ? 1 : 0;
+      a.enc_valid[ge] = kv;
+      a.mem_valid[ge] = kv;   // text region of the memory comes first
+    }
   }
   __shared__ int s_cnt;
   __syncthreads();
@@ -671,7 +675,7 @@ __global__ void __launch_bounds__(128) prep_step_kernel(const int64_t* __restric
     __syncthreads();
   }
   // memory validity: table rows then image keys
-  const long long T_text = (long long)a.B * R * S;
+  const long long T_text = (long long)a.B * R * SE;
   for (int f = threadIdx.x; f < a.F; f += blockDim.x)
     a.mem_valid[T_text + (long long)b * a.F + f] = table_valid[(long long)b * a.F + f];
   const long long T_tab = (long long)a.B * a.F;
@@ -992,6 +996,7 @@ extern "C" int mmsum_prep_step(const int64_t* reviews, const int64_t* reviews_ma
                                const uint8_t* table_valid, const uint8_t* img_mask, const MmsumPrepArgs* a, void* stream) {
   if (!a || !reviews || !reviews_mask || !rating || a->B <= 0 || a->R < 2 || a->S <= 0) return MMSUM_ERR_INVALID;
   if (a->n_mod != 1 && a->n_mod != 3) return MMSUM_ERR_INVALID;
+  if (a->S_enc < 0 || a->S_enc > a->S) return MMSUM_ERR_INVALID;
   if (a->n_mod == 3 && (!table_valid || !img_mask || a->F <= 0 || a->n_img <= 0)) return MMSUM_ERR_INVALID;
   prep_step_kernel<<<a->B, 128, 0, STREAM(stream)>>>(reviews, reviews_mask, rating, table_valid, img_mask, *a);
   MMSUM_CHECK_LAUNCH();

@@ -88,6 +88,24 @@ class _Pool:
                 self.free.append(t)
 
 
+class _PoolRows:
+    """The same free-list handing out the first `rows` rows of its buffers (encoder-sized operands: a GEMM's M is the row count
+    of its tensors)."""
+
+    def __init__(self, base, rows):
+        self.base, self.rows = base, rows
+        self.out = {}
+
+    def get(self):
+        b = self.base.get()
+        v = b[:self.rows]
+        self.out[v.data_ptr()] = b
+        return v
+
+    def put(self, *ts):
+        self.base.put(*[self.out.pop(t.data_ptr(), t) for t in ts if t is not None])
+
+
 class StepEngine:
     def __init__(self, cfg: ModelConfig, device="cuda"):
         if cfg.d_model != 1024 or cfg.head_dim != 64:
@@ -100,9 +118,12 @@ class StepEngine:
         self.numel = 0
         self.bound = False
         self.ws = None
+        self.ws_full = None
         # A/B switches (defaults = the faster variants)
         self.dkv_concat = os.environ.get("MMSUM_DKV_CONCAT", "1") != "0"
         self.gelu_dact = os.environ.get("MMSUM_GELU_DACT", "1") != "0"
+        self.trim_frames = os.environ.get("MMSUM_TRIM_FRAMES", "1") != "0"
+        self._len_cache = None
         self.ws_key = None
         # dropout stream = f(seed, step_count, layer, element): the seed follows torch.manual_seed / torch.initial_seed and
         # differs per data-parallel rank; `seed` and `step_count` are plain attributes so a resume can restore them
@@ -213,18 +234,52 @@ class StepEngine:
         self._w16_fresh = False
 
     # ------------------------------------------------------------------ workspaces
-    def _alloc(self, B, R, S, F, n_img, img_keys):
+    def _frame_view(self, full, S_enc):
+        """Views of the full-size workspace for a step whose encoder runs on S_enc-row frames (see _alloc): every encoder
+        buffer, the memory and its per-layer K|V / gradient buffers cut to the rows this step uses.  The storage never moves,
+        so recorded CUDA graphs of different frames stay valid side by side; the views are built once per frame."""
+        if S_enc == full["S"] or full["Tt"] == 0:
+            return full
+        views = full.setdefault("_views", {})
+        if S_enc in views:
+            return views[S_enc]
+        B, R, F, n_img, ik = full["B"], full["R"], full["F"], full["n_img"], full["img_keys"]
+        Te = B * R * S_enc
+        Tm = Te + B * F + B * n_img * ik
+        w = dict(full)
+        w.update(S_enc=S_enc, Te=Te, Tt=Te, Tm=Tm)
+        cut = lambda t, n: t[:n] if isinstance(t, torch.Tensor) else t
+        w["enc"] = [{k: (v if k == "lse" else cut(v, Te)) for k, v in a.items()} for a in full["enc"]]
+        for k in ("enc_x0", "enc_m0", "enc_r0"):
+            w[k] = full[k][:Te]
+        w["dec"] = [dict(a, kv=a["kv"][:Tm]) for a in full["dec"]]
+        for k in ("MEM", "dkv_all", "dMEM16", "dMEM32", "mem_valid"):
+            if k in full:
+                w[k] = full[k][:Tm]
+        w["pool_e"] = _PoolRows(full["pool"], Te)
+        views[S_enc] = w
+        return w
+
+    def _alloc(self, B, R, S, F, n_img, img_keys, S_enc=None):
         """Workspaces of one step shape.  B businesses, R decoder sequences per business (the leave-one-out targets; 1 in
-        the img / table stages), S = 128; memory rows = [text B*R*S (when the model has a text memory) | table B*F | image]."""
+        the img / table stages), S = 128; memory rows = [text B*R*S_enc (when the model has a text memory) | table B*F | image].
+        S_enc <= S is the ENCODER frame: when no review of the batch is longer than S_enc tokens, the encoder (and the text
+        rows of the memory) run on B*R*S_enc rows — rows beyond a review's last token are pad in every review, are masked as
+        keys everywhere and receive exactly zero gradient, so dropping them changes no result (the decoder keeps its 128-row
+        frames: its pad rows count in the loss, quirk Q2)."""
+        S_enc = S if S_enc is None else S_enc
         key = (B, R, S, F, n_img, img_keys)
         if self.ws_key == key:
-            return self.ws
+            return self._frame_view(self.ws_full, S_enc)
+        self.ws_full = None
+        S_enc_req, S_enc = S_enc, S              # storage for full frames; the step works on views cut to its frame
         self.ws, self.ws_key = None, None       # drop the old workspace before allocating the new one
         cfg, dev = self.cfg, self.device
         D, FF, H = cfg.d_model, cfg.ffn_dim, cfg.heads
         T = B * R * S
         has_text = cfg.text_memory
-        Tt = T if has_text else 0
+        Te = B * R * S_enc                        # encoder rows
+        Tt = Te if has_text else 0
         Tm = Tt + B * F + B * n_img * img_keys
         N = B * R
         Et = (R if has_text else 0) + (1 if F > 0 else 0) + n_img
@@ -233,7 +288,7 @@ class StepEngine:
         f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
         u8 = lambda *s: torch.zeros(s, device=dev, dtype=torch.uint8)
         i32 = lambda *s: torch.zeros(s, device=dev, dtype=torch.int32)
-        w = dict(B=B, R=R, S=S, F=F, n_img=n_img, img_keys=img_keys, T=T, Tt=Tt, Tm=Tm, N=N, Et=Et, nm=nm)
+        w = dict(B=B, R=R, S=S, F=F, n_img=n_img, img_keys=img_keys, T=T, Tt=Tt, Tm=Tm, N=N, Et=Et, nm=nm, S_enc=S_enc, Te=Te)
         w.update(enc_ids=i32(T), dec_ids=i32(T), labels=i32(T), enc_valid=u8(T), dec_valid=u8(T), mem_valid=u8(Tm),
                  ent_valid=u8(B, Et), pres=u8(B, 2), rating_diff=f32(N), inv_n=f32(N, nm))
         w["MEM"] = bf(Tm, D)
@@ -244,12 +299,12 @@ class StepEngine:
         L_e, L_d = (cfg.encoder_layers if has_text else 0), cfg.decoder_layers
         enc = []
         for l in range(L_e):
-            enc.append(dict(x=bf(T, D) if l > 0 else None, qkv=bf(T, 3 * D), ctx=bf(T, D), o=bf(T, D), x1=bf(T, D), h=bf(T, FF),
-                            a=bf(T, FF), f=bf(T, D), lse=f32(N, H, 1, S), m1=f32(T), r1=f32(T), m2=f32(T), r2=f32(T)))
+            enc.append(dict(x=bf(Te, D) if l > 0 else None, qkv=bf(Te, 3 * D), ctx=bf(Te, D), o=bf(Te, D), x1=bf(Te, D), h=bf(Te, FF),
+                            a=bf(Te, FF), f=bf(Te, D), lse=f32(N, H, 1, S), m1=f32(Te), r1=f32(Te), m2=f32(Te), r2=f32(Te)))
         w["enc"] = enc
         if has_text:
-            w["enc_x0"] = bf(T, D)
-            w["enc_m0"], w["enc_r0"] = f32(T), f32(T)
+            w["enc_x0"] = bf(Te, D)
+            w["enc_m0"], w["enc_r0"] = f32(Te), f32(Te)
         dec = []
         for l in range(L_d):
             d = dict(x=bf(T, D), qkv=bf(T, 3 * D), ctx=bf(T, D), o=bf(T, D), x1=bf(T, D), qc=bf(T, D), kv=bf(Tm, 2 * D),
@@ -270,6 +325,7 @@ class StepEngine:
         # backward scratch
         w["pool"] = _Pool(5, (T, D), dev)
         w["pool"].before_put = self._side_join
+        w["pool_e"] = w["pool"]                    # (a frame view hands out row-cut views of the same buffers)
         w["dH"] = bf(T, FF)
         w["dqkv"] = bf(T, 3 * D)
         # cross-attention K|V gradients of ALL decoder layers side by side: the memory gradient is then ONE GEMM over the
@@ -290,19 +346,21 @@ class StepEngine:
             w.update(U=bf(2, T, D), dU=bf(2, T, D), dca=bf(T, 2 * D), dcb=bf(T, 2 * D))
         if F > 0:
             w.update(dtab_h=bf(B * F, D), dtabX=bf(B * F, 2 * D))
-        self.ws, self.ws_key = w, key
-        return w
+        self.ws_full, self.ws_key = w, key
+        return self._frame_view(w, S_enc_req)
 
     # ------------------------------------------------------------------ helpers
     def _sid(self, kind, layer):
         # the step number is added inside the kernels from the device-resident counter `step_dev` (graph-replayable)
         return kind * 64 + layer
 
-    def _self_attn_args(self, w, qkv, out, lse, key_valid, causal, bwd=None):
+    def _self_attn_args(self, w, qkv, out, lse, key_valid, causal, bwd=None, frame=None):
+        """frame: rows per sequence (the encoder's trimmed frame; None = 128)."""
         D, H, S = self.cfg.d_model, self.cfg.heads, w["S"]
+        fr = S if frame is None else frame
         kw = dict(Q=qkv, ldq=3 * D, q_col=0, KV=qkv, ldkv=3 * D, k_col=D, v_col=2 * D, O=out, ldo=D, LSE=lse,
                   key_valid=key_valid, ent_valid=None, inv_n=None, n_qseq=w["N"], H=H, R=1, causal=int(causal), E_total=1,
-                  scale=self.cfg.head_dim ** -0.5, mods=[(0, 0, 1, S, 0, 0)])
+                  scale=self.cfg.head_dim ** -0.5, q_rows=(0 if fr == S else fr), mods=[(0, 0, 1, fr, 0, 0)])
         if bwd is not None:
             dqkv = bwd
             kw.update(DELTA=w["delta"], dQ=dqkv, lddq=3 * D, dq_col=0, dKV=dqkv, lddkv=3 * D, dk_col=D, dv_col=2 * D)
@@ -313,7 +371,7 @@ class StepEngine:
         B, R, F, n_img, ik, Tt = w["B"], w["R"], w["F"], w["n_img"], w["img_keys"], w["Tt"]
         mods, eb = [], 0
         if Tt > 0:
-            mods.append((0, 0, R, S, 1, 0))          # text: leave-one-out over the R reviews of the business
+            mods.append((0, 0, R, w["S_enc"], 1, 0))  # text: leave-one-out over the R reviews of the business (encoder frames)
             eb = R
         if F > 0:
             mods.append((Tt, len(mods) * T * D, 1, F, 0, eb))
@@ -373,7 +431,11 @@ class StepEngine:
         self._graph_entry = None
         if not self.graph_mode or self.grad_ready_hook is not None or self.device.type != "cuda":
             return self.forward(batch, label_smoothing, training)
-        key = (self._batch_key(batch), bool(training), label_smoothing)
+        # the encoder frame is part of the recorded shapes (taken from the batch's length hint, else read back from the mask:
+        # one small host sync per step, which costs a graph-launch latency, not the launch-bound step the graphs remove)
+        S_in = batch.reviews.shape[-1] if batch.reviews is not None else 0
+        frame = self._encoder_frame(batch, S_in) if self.cfg.text_memory else None
+        key = (self._batch_key(batch), bool(training), label_smoothing, frame)
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= 4:
@@ -386,6 +448,7 @@ class StepEngine:
             self._graphs[key] = ent
         for dst, src in zip(ent["static"].tensors(), batch.tensors()):
             dst.copy_(src)
+        ent["static"].max_review_len = frame
         self.refresh_bf16_weights()                       # host-side decision: stays outside the recorded graph
         self._graph_entry = ent
         if not ent["warm"]:                               # first step of a shape: plain launches (one-time attributes, workspaces)
@@ -436,8 +499,10 @@ class StepEngine:
         n_img, img_keys = (batch.img.shape[1], batch.img.shape[2]) if cfg.image else (0, 0)
         if S != 128:
             raise ValueError("the attention kernels are specialised to 128-token frames")
-        w = self._alloc(B, R, S, F, n_img, img_keys)
-        T, Tt, Tm = w["T"], w["Tt"], w["Tm"]
+        S_enc = self._encoder_frame(batch, S) if has_text else S
+        w = self._alloc(B, R, S, F, n_img, img_keys, S_enc)
+        self.ws = w
+        T, Tt, Tm, Te = w["T"], w["Tt"], w["Tm"], w["Te"]
         w["batch"] = batch                 # backward re-reads the bit-code table fields
         self.step_count += 1
         self.step_dev.add_(1)
@@ -468,7 +533,7 @@ class StepEngine:
         if has_text:
             ops.prep_step(batch.reviews, batch.reviews_mask, batch.reviews_rating,
                           w["tab_valid"] if gates else None, img_mask_u8 if gates else None,
-                          B=B, R=R, S=S, F=F, n_img=n_img, img_keys=img_keys, n_mod=3 if gates else 1,
+                          B=B, R=R, S=S, S_enc=S_enc, F=F, n_img=n_img, img_keys=img_keys, n_mod=3 if gates else 1,
                           pad_id=cfg.pad_token_id, bos_id=cfg.bos_token_id, eos_id=cfg.eos_token_id,
                           enc_ids=w["enc_ids"], dec_ids=w["dec_ids"], labels=w["labels"], enc_valid=w["enc_valid"],
                           dec_valid=w["dec_valid"], mem_valid=w["mem_valid"], ent_valid=w["ent_valid"],
@@ -494,14 +559,14 @@ class StepEngine:
             x = w["enc_x0"]
             ops.embed_ln_fwd(w["enc_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"), None, None,
                              self.w32(pre + "layernorm_embedding.weight"), self.w32(pre + "layernorm_embedding.bias"),
-                             x, w["enc_m0"], w["enc_r0"], T, S, pd, seed, self._sid(0, 0), step_dev=self.step_dev)
+                             x, w["enc_m0"], w["enc_r0"], Te, S_enc, pd, seed, self._sid(0, 0), step_dev=self.step_dev)
             L_e = cfg.encoder_layers
             for l in range(L_e):
                 a = w["enc"][l]
                 a["x"] = x
                 lp = pre + "layers.%d." % l
-                out = MEM[:T] if l == L_e - 1 else w["enc"][l + 1]["x"]
-                self._self_block_fwd(w, a, lp, x, w["enc_valid"], False, l, 1)
+                out = MEM[:Te] if l == L_e - 1 else w["enc"][l + 1]["x"]
+                self._self_block_fwd(w, a, lp, x, w["enc_valid"], False, l, 1, frame=S_enc)
                 self._ffn_block_fwd(a, lp, a["x1"], out, "m2", "r2", l, 2)
                 x = out
 
@@ -545,14 +610,33 @@ class StepEngine:
                        lse_rows=w["lse_rows"])
         return w["loss"]
 
+    def _encoder_frame(self, batch, S):
+        """Smallest multiple of 16 that holds every review's last valid token (the encoder frame, see _alloc).  Taken from the
+        batch's host-side hint when there is one; otherwise read back from the mask once per mask tensor (a host sync)."""
+        if not self.trim_frames:
+            return S
+        n = getattr(batch, "max_review_len", None)
+        if n is None:
+            m = batch.reviews_mask
+            key = (m.data_ptr(), m._version, tuple(m.shape))
+            if self._len_cache is not None and self._len_cache[0] == key:
+                n = self._len_cache[1]
+            elif torch.cuda.is_current_stream_capturing():
+                return S
+            else:
+                pos = torch.arange(1, S + 1, device=m.device, dtype=torch.int32)
+                n = int((m.ne(0).to(torch.int32) * pos).max().item())
+                self._len_cache = (key, n)
+        return min(S, max(16, (int(n) + 15) // 16 * 16))
+
     def w32_flb(self):
         return self.final_logits_bias.view(-1) if getattr(self, "final_logits_bias", None) is not None else None
 
-    def _self_block_fwd(self, w, a, lp, x, key_valid, causal, l, kind):
+    def _self_block_fwd(self, w, a, lp, x, key_valid, causal, l, kind, frame=None):
         g = ops.gemm
         s = lp + "self_attn."
         g(x, self.w16(s + "q_proj.weight", s + "v_proj.weight"), a["qkv"], bias=self.w32(s + "q_proj.bias", s + "v_proj.bias"))
-        ops.attn_fwd(self._self_attn_args(w, a["qkv"], a["ctx"], a["lse"], key_valid, causal))
+        ops.attn_fwd(self._self_attn_args(w, a["qkv"], a["ctx"], a["lse"], key_valid, causal, frame=frame))
         g(a["ctx"], self.w16(s + "out_proj.weight"), a["o"], bias=self.w32(s + "out_proj.bias"))
         ops.add_ln_fwd(x, a["o"], self.w32(lp + "self_attn_layer_norm.weight"), self.w32(lp + "self_attn_layer_norm.bias"),
                        a["x1"], a["m1"], a["r1"], self.pd, self.seed, self._sid(kind, l), step_dev=self.step_dev)
@@ -600,9 +684,9 @@ class StepEngine:
             hi = self.offsets[name_last] + (math.prod(self.shapes[name_last]) + ALIGN - 1) // ALIGN * ALIGN
             self.grad_ready_hook(hi)
 
-    def _ffn_block_bwd(self, w, a, lp, d1, d2, xin, mk, rk, l, kind):
+    def _ffn_block_bwd(self, w, a, lp, d1, d2, xin, mk, rk, l, kind, enc=False):
         """Backward of x_out = LN(xin + drop(fc2(gelu(fc1(xin))))).  Returns the two addends of d xin."""
-        pool, pd = w["pool"], self.pd
+        pool, pd = (w["pool_e"] if enc else w["pool"]), self.pd
         dres = pool.get()
         df = pool.get() if pd > 0 else dres
         ops.add_ln_bwd(d1, d2, xin, a["f"], self.w32(lp + "final_layer_norm.weight"), a[mk], a[rk], dres, df,
@@ -611,7 +695,7 @@ class StepEngine:
         pool.put(d1, d2)
         self._bias_grad(df, self.g32(lp + "fc2.bias"))
         self._wgrad(df, a["a"], lp + "fc2.weight")
-        dH = w["dH"]
+        dH = w["dH"][:xin.shape[0]]
         ops.gemm(df, self.w16(lp + "fc2.weight"), dH, b_t=True, act=ops.ACT_GELU, aux=a["h"], aux_mode=ops.AUX_MUL if self.gelu_dact else ops.AUX_MUL_DACT)
         if df is not dres:
             pool.put(df)
@@ -621,9 +705,9 @@ class StepEngine:
         ops.gemm(dH, self.w16(lp + "fc1.weight"), dx, b_t=True)
         return dres, dx
 
-    def _self_block_bwd(self, w, a, lp, d1, d2, key_valid, causal, l, kind):
+    def _self_block_bwd(self, w, a, lp, d1, d2, key_valid, causal, l, kind, enc=False):
         """Backward of x1 = LN(x + drop(out_proj(attn(qkv(x))))).  Returns the two addends of d x."""
-        pool, pd, D = w["pool"], self.pd, self.cfg.d_model
+        pool, pd, D = (w["pool_e"] if enc else w["pool"]), self.pd, self.cfg.d_model
         s = lp + "self_attn."
         dres = pool.get()
         do = pool.get() if pd > 0 else dres
@@ -637,8 +721,8 @@ class StepEngine:
         ops.gemm(do, self.w16(s + "out_proj.weight"), dctx, b_t=True)
         if do is not dres:
             pool.put(do)
-        dqkv = w["dqkv"]
-        ops.attn_bwd(self._self_attn_args(w, a["qkv"], dctx, a["lse"], key_valid, causal, bwd=dqkv))
+        dqkv = w["dqkv"][:a["qkv"].shape[0]]
+        ops.attn_bwd(self._self_attn_args(w, a["qkv"], dctx, a["lse"], key_valid, causal, bwd=dqkv, frame=w["S_enc"] if enc else None))
         pool.put(dctx)
         self._bias_grad(dqkv, self.g32(s + "q_proj.bias", s + "v_proj.bias"))
         self._wgrad(dqkv, a["x"], s + "q_proj.weight", s + "v_proj.weight")
@@ -768,19 +852,20 @@ class StepEngine:
         # ---- encoder layers, last to first (the img / table stages have no text memory: encoder gradients stay zero)
         if Tt > 0:
             pre = bm + "encoder."
+            Te, S_enc, pool = w["Te"], w["S_enc"], w["pool_e"]
             d1 = pool.get()
-            d1.copy_(dMEM[:T])
+            d1.copy_(dMEM[:Te])
             d2 = None
             for l in reversed(range(cfg.encoder_layers)):
                 a = w["enc"][l]
                 lp = pre + "layers.%d." % l
-                d1, d2 = self._ffn_block_bwd(w, a, lp, d1, d2, a["x1"], "m2", "r2", l, 2)
-                d1, d2 = self._self_block_bwd(w, a, lp, d1, d2, w["enc_valid"], False, l, 1)
+                d1, d2 = self._ffn_block_bwd(w, a, lp, d1, d2, a["x1"], "m2", "r2", l, 2, enc=True)
+                d1, d2 = self._self_block_bwd(w, a, lp, d1, d2, w["enc_valid"], False, l, 1, enc=True)
                 self._ready(lp + "self_attn_layer_norm.bias")
             ops.embed_ln_bwd(d1, d2, w["enc_ids"], self.w32(bm + "shared.weight"), self.w32(pre + "embed_positions.weight"), None, None,
                              self.w32(pre + "layernorm_embedding.weight"), w["enc_m0"], w["enc_r0"], self.g32(bm + "shared.weight"),
                              self.g32(pre + "embed_positions.weight"), None, self.g32(pre + "layernorm_embedding.weight"),
-                             self.g32(pre + "layernorm_embedding.bias"), w["dz32"], T, S, cfg.pad_token_id, pd, seed, self._sid(0, 0), step_dev=self.step_dev)
+                             self.g32(pre + "layernorm_embedding.bias"), w["dz32"], Te, S_enc, cfg.pad_token_id, pd, seed, self._sid(0, 0), step_dev=self.step_dev)
             pool.put(d1, d2)
         self._ready(bm + "shared.weight")
         for n, p in self.params.items():

@@ -421,14 +421,16 @@ class MultimodalSum(nn.Module, _EngineRoot):
         self.engine = None
         self._adopt_children()
 
-    def forward(self, reviews, reviews_mask, reviews_rating, field, field_value, img, img_mask, **unused):
+    def forward(self, reviews, reviews_mask, reviews_rating, field, field_value, img, img_mask, max_review_len=None, **unused):
         """-> (loss,)  — same arguments as the reference (src/multimodal_train.py:124-139); `img` holds pooled
-        ResNet-101 stage-3 features [B, max_imgs, 196, 1024] (fp32 or bf16)."""
+        ResNet-101 stage-3 features [B, max_imgs, 196, 1024] (fp32 or bf16).  `max_review_len` (optional, not in the reference):
+        what the collate function knows — no review has a valid token at or beyond that position; the encoder then runs on
+        frames trimmed to it without the engine reading the mask back from the device."""
         eng = self._ensure_engine(reviews.device)
         _check_device(reviews.device, reviews_mask, reviews_rating, field, img, img_mask, *field_value)
         batch = Batch(_ids(reviews), _ids(reviews_mask), reviews_rating.float().contiguous(), _ids(field),
                       [_ids(v) for v in field_value], img if img.dtype == torch.bfloat16 else img.float(),
-                      img_mask.to(torch.bool).contiguous())
+                      img_mask.to(torch.bool).contiguous(), max_review_len=max_review_len)
         loss = _StepFn.apply(eng.anchor, self, batch, self.label_smoothing)
         return (loss,)
 
@@ -466,10 +468,10 @@ class TextSupervised(nn.Module, _EngineRoot):
         self.engine = None
         self._adopt_children()
 
-    def forward(self, reviews, reviews_mask, reviews_rating, **unused):
+    def forward(self, reviews, reviews_mask, reviews_rating, max_review_len=None, **unused):
         eng = self._ensure_engine(reviews.device)
         _check_device(reviews.device, reviews_mask, reviews_rating)
-        batch = Batch(_ids(reviews), _ids(reviews_mask), reviews_rating.float().contiguous())
+        batch = Batch(_ids(reviews), _ids(reviews_mask), reviews_rating.float().contiguous(), max_review_len=max_review_len)
         loss = _StepFn.apply(eng.anchor, self, batch, self.label_smoothing)
         return (loss,)
 

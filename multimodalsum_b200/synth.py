@@ -180,16 +180,27 @@ class Batch:
     img: torch.Tensor = None       # f32 [B, max_imgs, 196, 1024] pooled ResNet-101 stage-3 features
     img_mask: torch.Tensor = None  # bool [B, max_imgs]
     labels: torch.Tensor = None    # i64 [B, S]: decoder targets of the img / table pretraining stages (reviews is None there)
+    max_review_len: int = None     # optional host-side hint: no review has a valid token at position >= max_review_len (the
+                                   # engine trims the encoder frames to it; without the hint it reads the mask back once)
 
     def to(self, device, non_blocking=False):
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
         return Batch(mv(self.reviews), mv(self.reviews_mask), mv(self.reviews_rating), mv(self.field),
-                     [mv(t) for t in self.field_value], mv(self.img), mv(self.img_mask), mv(self.labels))
+                     [mv(t) for t in self.field_value], mv(self.img), mv(self.img_mask), mv(self.labels), self.max_review_len)
 
     def pin(self):
         pv = lambda t: None if t is None else t.pin_memory()
         return Batch(pv(self.reviews), pv(self.reviews_mask), pv(self.reviews_rating), pv(self.field),
-                     [pv(t) for t in self.field_value], pv(self.img), pv(self.img_mask), pv(self.labels))
+                     [pv(t) for t in self.field_value], pv(self.img), pv(self.img_mask), pv(self.labels), self.max_review_len)
+
+    def with_length_hint(self):
+        """Fill `max_review_len` from the mask (a host-side pass when the batch still lives on the CPU: what a collate function
+        knows anyway; a device read-back otherwise)."""
+        if self.reviews_mask is not None:
+            m = self.reviews_mask.ne(0)
+            S = m.shape[-1]
+            self.max_review_len = int((m.to(torch.int32) * torch.arange(1, S + 1, device=m.device, dtype=torch.int32)).max().item())
+        return self
 
     def tensors(self):
         return [t for t in [self.reviews, self.reviews_mask, self.reviews_rating, self.field, self.img, self.img_mask, self.labels]
