@@ -334,6 +334,45 @@ def test_self_attention_fwd_bwd(causal, n_seq):
         _close(dqkv[:, i * D:(i + 1) * D], gref[:, i * D:(i + 1) * D], 2e-2, nm)
 
 
+@pytest.mark.parametrize("n_seq,frame", [(6, 112), (72, 112), (72, 80), (5, 48)])
+def test_self_attention_short_frames(n_seq, frame):
+    """Encoder self-attention on frames of `frame` < 128 rows per sequence (q_rows in the ABI): the 128-row query tile of a
+    sequence then overlaps the next sequence's rows, which must be neither written (forward, dQ) nor allowed to contribute
+    (dK/dV).  Every buffer is pre-filled so that a stray write or a foreign contribution shows."""
+    ops = _ops()
+    torch.manual_seed(9)
+    N, H, hd = n_seq, 16, 64
+    T = N * frame
+    qkv = torch.randn(T, 3 * D, device=_dev()).to(torch.bfloat16)
+    lens = torch.randint(10, frame + 1, (N,), device=_dev())
+    lens[0] = frame
+    valid = torch.arange(frame, device=_dev())[None, :] < lens[:, None]
+    kvalid = valid.reshape(-1).to(torch.uint8)
+    ctx = torch.full((T + 128, D), 7.0, device=_dev(), dtype=torch.bfloat16)            # + guard rows behind the last frame
+    lse = torch.full((N, H, 1, 128), float("nan"), device=_dev())
+    kw = dict(Q=qkv, ldq=3 * D, q_col=0, KV=qkv, ldkv=3 * D, k_col=D, v_col=2 * D, O=ctx, ldo=D, LSE=lse, key_valid=kvalid,
+              ent_valid=None, inv_n=None, n_qseq=N, H=H, R=1, causal=0, E_total=1, scale=hd ** -0.5, q_rows=frame,
+              mods=[(0, 0, 1, frame, 0, 0)])
+    ops.debug_poison()
+    ops.attn_fwd(ops.attn_args(**kw))
+    x = qkv.float().view(N, frame, 3, H, hd).requires_grad_(True)
+    q, k, v = [x[:, :, i].transpose(1, 2) for i in range(3)]
+    ref = _ref_attention(q, k, v, valid, False, hd ** -0.5).transpose(1, 2).reshape(T, D)
+    _close(ctx[:T], ref, 1.5e-2, "short-frame attn fwd")
+    assert (ctx[T:] == 7.0).all()                                                         # nothing written behind the last frame
+    dctx = torch.randn(T, D, device=_dev()).to(torch.bfloat16)
+    ref.backward(dctx.float())
+    dqkv = torch.full((T + 128, 3 * D), 7.0, device=_dev(), dtype=torch.bfloat16)
+    delta = torch.full((N, H, 1, 128), float("nan"), device=_dev())
+    kw.update(O=dctx, DELTA=delta, dQ=dqkv, lddq=3 * D, dq_col=0, dKV=dqkv, lddkv=3 * D, dk_col=D, dv_col=2 * D)
+    ops.debug_poison()
+    ops.attn_bwd(ops.attn_args(**kw))
+    gref = x.grad.reshape(T, 3 * D)
+    for i, nm in enumerate(("dq", "dk", "dv")):
+        _close(dqkv[:T, i * D:(i + 1) * D], gref[:, i * D:(i + 1) * D], 2e-2, "short-frame " + nm)
+    assert (dqkv[T:] == 7.0).all()
+
+
 def test_multi_entity_cross_attention_fwd_bwd():
     """Leave-one-out text entities + a partially masked table + images with null entities / a null-image business,
     against the restated reference semantics (per-entity softmax, masked mean, -2^16 fill)."""

@@ -357,3 +357,42 @@ def test_step_ignores_uninitialised_workspace_memory():
                 if "k_proj." in n:          # small residuals of a large cancellation: 1e-3 run-to-run from the atomics' order
                     continue
                 assert (g0[n] - g1[n]).norm().item() <= 2e-3 * g0[n].norm().item() + 1e-9, (graph, n)
+
+
+def test_trimmed_encoder_frames_change_nothing():
+    """The encoder runs on frames cut to the longest review of the batch (engine._alloc): with dropout off the step must give
+    the loss and the gradients of the untrimmed run (per-row arithmetic is identical; only the row order inside the weight
+    gradients' reductions moves), for review lengths that trim to 80 / 96 / 112 rows and with the length given as a hint or
+    read back from the mask."""
+    from multimodalsum_b200.modules import MultimodalSum, YelpTableEncoder
+    from multimodalsum_b200.synth import make_batch
+    gold = load_golden("small_yelp_gates_open")
+    cfg = gold["cfg"]
+    cfg.dropout = 0.0
+
+    def run(trim, b, hint):
+        torch.manual_seed(0)
+        model = MultimodalSum(TableEncoder=YelpTableEncoder, config=cfg, label_smoothing=0.1)
+        model.load_state_dict(gold["sd"], strict=False)
+        model = model.cuda().train()
+        eng = model._ensure_engine(torch.device("cuda"))
+        eng.trim_frames = trim
+        loss = model(b.reviews, b.reviews_mask, b.reviews_rating, b.field, b.field_value, b.img, b.img_mask,
+                     max_review_len=(b.max_review_len if hint else None))[0]
+        model.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss.item(), {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}, eng.ws["S_enc"]
+
+    for hi, frame in ((70, 80), (90, 96), (100, 112), (128, 128)):
+        b = make_batch(cfg, 3, seed=80 + hi, n_reviews=4, max_imgs=3, len_range=(20, hi)).with_length_hint().to("cuda")
+        l0, g0, f0 = run(False, b, False)
+        assert f0 == 128
+        for hint in (False, True):
+            l1, g1, f1 = run(True, b, hint)
+            assert f1 <= frame and f1 % 16 == 0, (f1, frame)
+            assert abs(l0 - l1) <= 1e-6 * abs(l0), (hi, hint, l0, l1)
+            for n in g0:
+                if "k_proj." in n:
+                    continue
+                assert (g0[n] - g1[n]).norm().item() <= 2e-3 * g0[n].norm().item() + 1e-9, (hi, hint, n)
