@@ -637,11 +637,15 @@ __global__ void __launch_bounds__(128) prep_step_kernel(const int64_t* __restric
   const int R = a.R, S = a.S;
   const int SE = a.S_enc > 0 ? a.S_enc : S;      // encoder frame: the first SE tokens of a review (the rest is pad by contract)
   const int n_ent = R + (a.F > 0 ? 1 : 0) + a.n_img;
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
   for (int i = threadIdx.x; i < R * S; i += blockDim.x) {
     const int r = i / S, t = i - r * S;
     const long long gi = ((long long)b * R + r) * S + t;
     const long long tok = (long long)reviews[gi];
     a.labels[gi] = (int)tok;
+    if (t >= SE && reviews_mask[gi] != 0) s_bad = 1;   // a valid token beyond the encoder frame: the caller's length hint was wrong
     if (t < SE) {
       const long long ge = ((long long)b * R + r) * SE + t;
       a.enc_ids[ge] = (int)tok;
@@ -708,7 +712,8 @@ __global__ void __launch_bounds__(128) prep_step_kernel(const int64_t* __restric
     for (int r = 0; r < R; ++r) {
       const long long q = (long long)b * R + r;
       const float ri = rating[q];
-      a.rating_diff[q] = ri - (rsum - ri) / (float)(R - 1);
+      // (a violated frame contract must not pass silently: the NaN reaches the decoder embedding and the loss)
+      a.rating_diff[q] = s_bad ? __int_as_float(0x7fc00000) : ri - (rsum - ri) / (float)(R - 1);
       const int self_valid = a.ent_valid[(long long)b * n_ent + r];
       const int nt = text_cnt - self_valid;
       a.inv_n[q * a.n_mod + 0] = nt > 0 ? 1.f / (float)nt : 0.f;

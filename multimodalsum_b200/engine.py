@@ -15,6 +15,7 @@ torch is used for memory (arenas, workspaces), streams and torch.distributed onl
 """
 import math
 import os
+import weakref
 
 import torch
 
@@ -618,15 +619,16 @@ class StepEngine:
         n = getattr(batch, "max_review_len", None)
         if n is None:
             m = batch.reviews_mask
-            key = (m.data_ptr(), m._version, tuple(m.shape))
-            if self._len_cache is not None and self._len_cache[0] == key:
-                n = self._len_cache[1]
+            # cached only for the SAME tensor object at the same version (an address can be recycled by a new batch)
+            c = self._len_cache
+            if c is not None and c[0]() is m and c[1] == m._version:
+                n = c[2]
             elif torch.cuda.is_current_stream_capturing():
                 return S
             else:
                 pos = torch.arange(1, S + 1, device=m.device, dtype=torch.int32)
                 n = int((m.ne(0).to(torch.int32) * pos).max().item())
-                self._len_cache = (key, n)
+                self._len_cache = (weakref.ref(m), m._version, n)
         return min(S, max(16, (int(n) + 15) // 16 * 16))
 
     def w32_flb(self):

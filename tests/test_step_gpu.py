@@ -396,3 +396,10 @@ def test_trimmed_encoder_frames_change_nothing():
                 if "k_proj." in n:
                     continue
                 assert (g0[n] - g1[n]).norm().item() <= 2e-3 * g0[n].norm().item() + 1e-9, (hi, hint, n)
+    # a length hint that cuts valid tokens off must not pass silently: the loss turns NaN
+    b = make_batch(cfg, 3, seed=99, n_reviews=4, max_imgs=3, len_range=(60, 100)).to("cuda")
+    model = MultimodalSum(TableEncoder=YelpTableEncoder, config=cfg, label_smoothing=0.1)
+    model.load_state_dict(gold["sd"], strict=False)
+    model = model.cuda().train()
+    loss = model(b.reviews, b.reviews_mask, b.reviews_rating, b.field, b.field_value, b.img, b.img_mask, max_review_len=32)[0]
+    assert torch.isnan(loss).item()
