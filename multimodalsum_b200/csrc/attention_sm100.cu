@@ -35,6 +35,9 @@
 #ifndef MMSUM_TAIL16
 #define MMSUM_TAIL16 1     // forward v3 / dQ: the last 16 score columns of an entity with n16 % 32 == 16 are not processed as a
 #endif                     // full 32-column chunk (no exp2 / TMEM traffic for columns that do not exist)
+#ifndef MMSUM_FWD_ONEPASS
+#define MMSUM_FWD_ONEPASS 1 // forward v3: one pass over the scores with a lazily raised reference instead of a row-max pass first
+#endif
 #ifndef MMSUM_DKV_TS
 #define MMSUM_DKV_TS 1     // dK/dV kernel: P^T / dS^T stay in tensor memory as the A operands of the dV / dK products
 #endif
@@ -981,6 +984,80 @@ attn_fwd_tc3_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p
       const int nfull = nchunk;
       const bool tail = false;
 #endif
+#if MMSUM_FWD_ONEPASS
+      // One pass: every 32-column chunk is read from tensor memory ONCE.  P = exp2(s*sc - ref) where ref is an integer reference
+      // in the scaled log2 domain that starts at ceil(max of the first chunk) and is raised only when a later chunk exceeds it
+      // by more than kSlack — then the bf16 P columns already written and the row sum are rescaled by the exact power of two
+      // 2^(ref_old - ref_new).  The softmax is invariant to the reference (P keeps its relative precision in bf16, the sum is
+      // fp32, the normalisation divides it out), so this equals the max-first form up to rounding; with real logits the raise
+      // never triggers after the first chunk (it needs a score 22 nats above everything seen before) and costs one vote.
+      constexpr float kSlack = 32.f;
+      float ref = -INFINITY;
+      f32x2 l2[2] = {splat2(0.f), splat2(0.f)};
+      const f32x2 sc2 = splat2(sc);
+      auto one_part = [&](auto ntag, int c) {
+        constexpr int NC = decltype(ntag)::value;
+        uint32_t wd = sm.kmask[i][c];
+        if (p.causal) wd = causal_word(wd, row, c);
+        constexpr uint32_t kAll = NC == 32 ? 0xffffffffu : 0xffffu;
+        wd &= kAll;
+        uint32_t r[NC], pk[NC / 2];
+        if constexpr (NC == 32) tmem_ld_32x32(scol + c * 32, r); else tmem_ld_32x16(scol + c * 32, r);
+        tmem_ld_wait();
+        const bool full = __all_sync(0xffffffffu, wd == kAll);
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < NC; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < NC; ++j) mx4[j & 3] = ((wd >> j) & 1u) ? fmaxf(mx4[j & 3], __uint_as_float(r[j])) : mx4[j & 3];
+        }
+        const float cms = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sc;     // -inf when the row has no valid column here
+        const bool raise = cms > ref + kSlack;                                           // (ref = -inf: any finite value raises)
+        if (__any_sync(0xffffffffu, raise)) {
+          const float nref = raise ? ceilf(cms) : ref;
+          if (c > 0) {       // rescale what this row has produced so far; rows that do not raise use the factor 1
+            const float f = raise ? ex2(ref - nref) : 1.f;                               // exact power of two (0 when ref = -inf)
+            const f32x2 f2 = splat2(f);
+            for (int cc = 0; cc < c; ++cc) {
+              uint32_t q[16];
+              tmem_ld_32x16(scol + cc * 16, q);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 v = unpack_bf16(q[j]);
+                q[j] = pack_bf16(v.x * f, v.y * f);
+              }
+              tmem_st_32x16(scol + cc * 16, q);
+            }
+            l2[0] = mul2(l2[0], f2);
+            l2[1] = mul2(l2[1], f2);
+          }
+          ref = nref;
+        }
+        const f32x2 nref2 = splat2(-ref);
+        auto body = [&](auto tag) {
+          constexpr bool kFull = decltype(tag)::value;
+#pragma unroll
+          for (int j = 0; j < NC; j += 2) {
+            float a0, a1;
+            unpack2(fma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), sc2, nref2), a0, a1);
+            float e0 = ex2(a0), e1 = ex2(a1);
+            if constexpr (!kFull) { e0 = ((wd >> j) & 1u) ? e0 : 0.f; e1 = ((wd >> (j + 1)) & 1u) ? e1 : 0.f; }
+            l2[(j >> 1) & 1] = add2(l2[(j >> 1) & 1], pack2(e0, e1));
+            pk[j >> 1] = pack_bf16(e0, e1);
+          }
+        };
+        if (full) body(std::true_type{}); else body(std::false_type{});
+        // columns [16c, 16c + NC/2) lie inside score chunks this thread has consumed
+        if constexpr (NC == 32) tmem_st_32x16(scol + c * 16, pk); else tmem_st_32x8(scol + c * 16, pk);
+      };
+#pragma unroll 1
+      for (int c = 0; c < nfull; ++c) one_part(std::integral_constant<int, 32>{}, c);
+      if (tail) one_part(std::integral_constant<int, 16>{}, nfull);
+      const float msc = (ref == -INFINITY) ? 0.f : ref;
+#else
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       auto max_part = [&](auto ntag, int c) {
         constexpr int NC = decltype(ntag)::value;
@@ -1035,6 +1112,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p
 #pragma unroll 1
       for (int c = 0; c < nfull; ++c) exp_part(std::integral_constant<int, 32>{}, c);
       if (tail) exp_part(std::integral_constant<int, 16>{}, nfull);
+#endif
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&sm.p_full);

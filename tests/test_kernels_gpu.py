@@ -373,6 +373,48 @@ def test_self_attention_short_frames(n_seq, frame):
     assert (dqkv[T:] == 7.0).all()
 
 
+@pytest.mark.parametrize("n_seq", [6, 72])
+def test_attention_scores_growing_along_the_keys(n_seq):
+    """The forward kernel reads every score chunk once and keeps a reference that is raised lazily (csrc/attention_sm100.cu,
+    MMSUM_FWD_ONEPASS): keys whose scores grow by hundreds of nats from chunk to chunk force the raise-and-rescale path on most
+    rows (and no raise on the rows whose scores shrink instead).  Output, log-sum-exp (through the backward pass) and
+    gradients must still match the max-first softmax of the reference."""
+    ops = _ops()
+    torch.manual_seed(12)
+    N, H, S, hd = n_seq, 16, 128, 64
+    T = N * S
+    qkv = torch.randn(T, 3 * D, device=_dev())
+    ramp = torch.linspace(1.0, 40.0, S, device=_dev()).repeat(N)[:, None]          # key norm grows 40x along the sequence
+    u = torch.randn(1, H, 1, hd, device=_dev()).expand(N, H, S, hd).transpose(1, 2).reshape(T, D)
+    qkv[:, D:2 * D] = u * ramp                                                         # k_j = ramp_j * u: scores = ramp_j * (q . u)
+    qkv = qkv.to(torch.bfloat16)
+    lens = torch.randint(100, S + 1, (N,), device=_dev())
+    valid = torch.arange(S, device=_dev())[None, :] < lens[:, None]
+    kvalid = valid.reshape(-1).to(torch.uint8)
+    ctx = torch.empty(T, D, device=_dev(), dtype=torch.bfloat16)
+    lse = torch.empty(N, H, 1, S, device=_dev())
+    kw = dict(Q=qkv, ldq=3 * D, q_col=0, KV=qkv, ldkv=3 * D, k_col=D, v_col=2 * D, O=ctx, ldo=D, LSE=lse, key_valid=kvalid,
+              ent_valid=None, inv_n=None, n_qseq=N, H=H, R=1, causal=0, E_total=1, scale=hd ** -0.5, mods=[(0, 0, 1, S, 0, 0)])
+    ops.attn_fwd(ops.attn_args(**kw))
+    x = qkv.float().view(N, S, 3, H, hd).requires_grad_(True)
+    q, k, v = [x[:, :, i].transpose(1, 2) for i in range(3)]
+    w = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    assert (w.amax(-1) - w[..., :32].amax(-1)).max().item() > 100.0                    # the raise path is really exercised
+    ref = _ref_attention(q, k, v, valid, False, hd ** -0.5).transpose(1, 2).reshape(T, D)
+    assert torch.isfinite(ctx.float()).all()
+    _close(ctx, ref, 1.5e-2, "attn fwd, growing scores")
+    lse_ref = torch.logsumexp(w.masked_fill(~valid[:, None, None, :], float("-inf")), -1) * 1.4426950408889634   # log2 domain
+    assert (lse[:, :, 0] - lse_ref).abs().max().item() <= 2e-2 + 1e-3 * lse_ref.abs().max().item()
+    dctx = torch.randn(T, D, device=_dev()).to(torch.bfloat16)
+    ref.backward(dctx.float())
+    dqkv = torch.zeros(T, 3 * D, device=_dev(), dtype=torch.bfloat16)
+    delta = torch.empty(N, H, 1, S, device=_dev())
+    kw.update(O=dctx, DELTA=delta, dQ=dqkv, lddq=3 * D, dq_col=0, dKV=dqkv, lddkv=3 * D, dk_col=D, dv_col=2 * D)
+    ops.attn_bwd(ops.attn_args(**kw))
+    gref = x.grad.reshape(T, 3 * D)
+    _close(dqkv[:, 2 * D:], gref[:, 2 * D:], 3e-2, "dv, growing scores")
+
+
 def test_multi_entity_cross_attention_fwd_bwd():
     """Leave-one-out text entities + a partially masked table + images with null entities / a null-image business,
     against the restated reference semantics (per-entity softmax, masked mean, -2^16 fill)."""
