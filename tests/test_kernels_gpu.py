@@ -725,7 +725,9 @@ def test_gate_fwd_bwd():
     _close(do3, exp, 2e-2, "gate dO3")
 
 
-# ------------------------------------------------------------------ integer bookkeeping + table front end (bit-exact)
+# ------------------------------------------------------------------ integer bookkeeping + table front end
+# (ids, masks, validity: bit-exact; the bf16 sum-pooled table features: equal up to the summation order of the fp32 pool, i.e.
+#  the rare element whose fp32 sum sits on a bf16 rounding boundary may differ by one ulp)
 @pytest.mark.parametrize("dataset", ["yelp", "amazon"])
 def test_prep_and_table_exact(dataset):
     ops = _ops()
@@ -765,7 +767,10 @@ def test_prep_and_table_exact(dataset):
         OR._lin = orig
     assert torch.equal(tv.bool(), valid)
     ref = captured["x"].reshape(B * F_, 2 * D)
-    assert torch.equal(X, ref.to(torch.bfloat16)) or (X.float() - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+    refb = ref.to(torch.bfloat16)
+    neq = X != refb
+    assert neq.float().mean().item() <= 2e-3, neq.float().mean().item()                       # rounding-boundary ties only
+    assert ((X.float() - refb.float()).abs() <= refb.float().abs() * 2.0 ** -7 + 1e-30).all()     # ... and at most one ulp apart
 
     T = B * R * S
     Tm = T + B * F_ + B * n_img * ik
@@ -789,3 +794,17 @@ def test_prep_and_table_exact(dataset):
     assert torch.equal(outs["mem_valid"][T:T + B * F_].bool(), valid.reshape(-1))
     assert torch.equal(outs["mem_valid"][T + B * F_:].view(B, n_img, ik)[:, :, 0].bool(), batch.img_mask)
     assert torch.equal(outs["pres"][:, 1].bool(), batch.img_mask.any(1))
+    # trimmed encoder frame (S_enc): the encoder-side arrays hold the first S_enc tokens of every review, everything else is unchanged
+    S_enc = min(S, (int(batch.reviews_mask.sum(-1).max().item()) + 15) // 16 * 16)
+    o2 = dict(enc_ids=i32(T), dec_ids=i32(T), labels=i32(T), enc_valid=u8(T), dec_valid=u8(T), mem_valid=u8(Tm),
+              ent_valid=u8(B, Et), pres=u8(B, 2), rating_diff=torch.zeros(B * R, device=dev), inv_n=torch.zeros(B * R, 3, device=dev))
+    ops.prep_step(batch.reviews, batch.reviews_mask, batch.reviews_rating, tv, batch.img_mask.view(torch.uint8),
+                  B=B, R=R, S=S, S_enc=S_enc, F=F_, n_img=n_img, img_keys=ik, n_mod=3, pad_id=1, bos_id=0, eos_id=2, **o2)
+    Te = B * R * S_enc
+    assert torch.equal(o2["enc_ids"][:Te].long(), batch.reviews[:, :, :S_enc].reshape(-1))
+    assert torch.equal(o2["enc_valid"][:Te].bool(), batch.reviews_mask[:, :, :S_enc].reshape(-1).bool())
+    assert torch.equal(o2["mem_valid"][:Te].bool(), batch.reviews_mask[:, :, :S_enc].reshape(-1).bool())
+    assert torch.equal(o2["mem_valid"][Te:Te + B * F_].bool(), valid.reshape(-1))
+    assert torch.equal(o2["mem_valid"][Te + B * F_:Te + B * F_ + B * n_img * ik], outs["mem_valid"][T + B * F_:])
+    for k in ("dec_ids", "labels", "dec_valid", "ent_valid", "pres", "rating_diff", "inv_n"):
+        assert torch.equal(o2[k], outs[k]), k
