@@ -127,8 +127,12 @@ def test_generation_at_config5_shape():
     out2 = gen.generate(*args, num_beams=beams, max_length=12, no_repeat_ngram_size=3, early_stopping=True)
     assert torch.equal(out, out2)                   # second call: same plan, graph replayed from the first token on
     ref_out = gen.generate(*args, num_beams=beams, max_length=12, no_repeat_ngram_size=3, early_stopping=True, use_cache=False)
-    same = (out.shape == ref_out.shape) and float((out == ref_out).float().mean()) or 0.0
-    assert same > 0.9, same                         # two bf16 kernel families: near-tied candidates may swap in a few businesses
+    # two bf16 kernel families: near-tied candidates may swap in a few businesses — which can also move the longest summary,
+    # i.e. the padded width of the returned tensor, by a token; compare on the common width, pad on the right
+    W = max(out.shape[1], ref_out.shape[1])
+    padw = lambda t: torch.nn.functional.pad(t, (0, W - t.shape[1]), value=cfg.pad_token_id)
+    same = float((padw(out) == padw(ref_out)).float().mean())
+    assert same > 0.9, (same, tuple(out.shape), tuple(ref_out.shape))
     assert out.shape[0] == B and out.shape[1] <= 12 and (out[:, 0] == cfg.eos_token_id).all() and (out[:, 1] == cfg.bos_token_id).all()
 
 
