@@ -125,13 +125,20 @@ def test_generation_at_config5_shape():
     out = gen.generate(*args, num_beams=beams, max_length=12, no_repeat_ngram_size=3, early_stopping=True)
     assert gen.last_used_graph                      # decoder step + beam update of a token replayed from one CUDA graph
     out2 = gen.generate(*args, num_beams=beams, max_length=12, no_repeat_ngram_size=3, early_stopping=True)
-    assert torch.equal(out, out2)                   # second call: same plan, graph replayed from the first token on
     ref_out = gen.generate(*args, num_beams=beams, max_length=12, no_repeat_ngram_size=3, early_stopping=True, use_cache=False)
-    # two bf16 kernel families: near-tied candidates may swap in a few businesses — which can also move the longest summary,
-    # i.e. the padded width of the returned tensor, by a token; compare on the common width, pad on the right
-    W = max(out.shape[1], ref_out.shape[1])
-    padw = lambda t: torch.nn.functional.pad(t, (0, W - t.shape[1]), value=cfg.pad_token_id)
-    same = float((padw(out) == padw(ref_out)).float().mean())
+
+    def agreement(a, b):     # on the common width, padded on the right (a swapped near-tie can move the longest summary by a token)
+        W = max(a.shape[1], b.shape[1])
+        padw = lambda t: torch.nn.functional.pad(t, (0, W - t.shape[1]), value=cfg.pad_token_id)
+        return float((padw(a) == padw(b)).float().mean())
+
+    # second call: same plan, graph replayed from the first token on.  The decode cross-attention adds the entity outputs of a
+    # business into its accumulator with shared-memory atomics in the order the entities finish (dynamic entity scheduling,
+    # csrc/decode_sm100.cu), so two runs agree to fp32 rounding, not bit for bit: with random-init weights a near-tied
+    # candidate swaps in roughly one run out of ten, in one business (equality was asserted here first and failed at that rate).
+    assert agreement(out, out2) >= 0.98, agreement(out, out2)
+    # two bf16 kernel families (cached decode vs prefix recompute): near-tied candidates may swap in a few businesses
+    same = agreement(out, ref_out)
     assert same > 0.9, (same, tuple(out.shape), tuple(ref_out.shape))
     assert out.shape[0] == B and out.shape[1] <= 12 and (out[:, 0] == cfg.eos_token_id).all() and (out[:, 1] == cfg.bos_token_id).all()
 
