@@ -46,6 +46,7 @@ struct DecSmem {
   DecItem items[kDecMaxEnt];
   int n_items;
   int next_item;
+  int turn;                              // ordered accumulation: index of the entity whose output is added next
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t (&r)[4]) {
@@ -90,7 +91,7 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, ok);
     if (ok) sm.items[__popc(bal & ((1u << lane) - 1u))] = it;
-    if (lane == 0) { sm.n_items = __popc(bal); sm.next_item = 0; }
+    if (lane == 0) { sm.n_items = __popc(bal); sm.next_item = 0; sm.turn = 0; }
   }
   for (int i = threadIdx.x; i < 3 * kDecMaxBeams * DHD; i += blockDim.x) (&sm.oacc[0][0][0])[i] = 0.f;
   if (threadIdx.x == 32) {
@@ -124,7 +125,30 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
   float oc[8][4];
 #pragma unroll
   for (int nd = 0; nd < 8; ++nd) { oc[nd][0] = 0.f; oc[nd][1] = 0.f; oc[nd][2] = 0.f; oc[nd][3] = 0.f; }
+#ifndef MMSUM_DECODE_ORDERED
+#define MMSUM_DECODE_ORDERED 1     // entity outputs are added to the CTA accumulator in ENTITY ORDER (bit-reproducible results)
+#endif
   int cur_mod = -1;
+  // ordered variant: the warp that finished entity i waits until entity i-1 has been added, then adds its own output with plain
+  // read-modify-writes (it holds the turn) and passes the turn on.  Entities are pulled in increasing order, so they also finish
+  // roughly in order and the wait is short; the sum order no longer depends on which warp got which entity or on timing.
+  auto add_in_order = [&](int i, int m) {
+    if (lane == 0) { while (*reinterpret_cast<volatile int*>(&sm.turn) != i) { } }
+    __syncwarp();
+    __threadfence_block();
+    if (g < R) {
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        sm.oacc[m][g][nd * 8 + 2 * t] += oc[nd][0];
+        sm.oacc[m][g][nd * 8 + 2 * t + 1] += oc[nd][1];
+      }
+    }
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) { oc[nd][0] = 0.f; oc[nd][1] = 0.f; oc[nd][2] = 0.f; oc[nd][3] = 0.f; }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile int*>(&sm.turn) = i + 1;
+  };
   auto flush = [&](int m) {          // fold this warp's partial output of modality m into the CTA accumulator
     if (m >= 0 && g < R) {
 #pragma unroll
@@ -145,7 +169,9 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
     if (i >= n_items) break;
     const DecItem it = sm.items[i];
     if (lane == 0) load_tile(it, p.k_col);
+#if !MMSUM_DECODE_ORDERED
     if (it.mod != cur_mod) { flush(cur_mod); cur_mod = it.mod; }
+#endif
     const int nkeys = it.nkeys;
     const int nblk = (nkeys + 15) >> 4;
     // validity words of the entity's keys (bit j of word c: key 32c + j may be attended)
@@ -248,8 +274,13 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
       }
     }
     __syncwarp();          // the stage may be overwritten by the next entity's keys
+#if MMSUM_DECODE_ORDERED
+    add_in_order(i, it.mod);
+#endif
   }
+#if !MMSUM_DECODE_ORDERED
   flush(cur_mod);
+#endif
   __syncthreads();
   // ---- modality outputs: [n_mod][hypothesis][head slice] (a modality without a valid entity yields zeros)
   bf16* Og = reinterpret_cast<bf16*>(p.O);

@@ -132,11 +132,10 @@ def test_generation_at_config5_shape():
         padw = lambda t: torch.nn.functional.pad(t, (0, W - t.shape[1]), value=cfg.pad_token_id)
         return float((padw(a) == padw(b)).float().mean())
 
-    # second call: same plan, graph replayed from the first token on.  The decode cross-attention adds the entity outputs of a
-    # business into its accumulator with shared-memory atomics in the order the entities finish (dynamic entity scheduling,
-    # csrc/decode_sm100.cu), so two runs agree to fp32 rounding, not bit for bit: with random-init weights a near-tied
-    # candidate swaps in roughly one run out of ten, in one business (equality was asserted here first and failed at that rate).
-    assert agreement(out, out2) >= 0.98, agreement(out, out2)
+    # second call: same plan, graph replayed from the first token on — bit-identical (the decode cross-attention adds the entity
+    # outputs of a business in entity order; when it used shared-memory atomics in completion order, a near-tied candidate
+    # swapped in about one run out of ten and this equality failed at that rate)
+    assert torch.equal(out, out2)
     # two bf16 kernel families (cached decode vs prefix recompute): near-tied candidates may swap in a few businesses
     same = agreement(out, ref_out)
     assert same > 0.9, (same, tuple(out.shape), tuple(ref_out.shape))
