@@ -971,7 +971,6 @@ attn_fwd_tc3_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p
     for (int i = 0; i < n_items; ++i) {
       const EntItem it = sm.items[i];
       const int head = item_head(i);
-      const int nchunk = (it.n16 + 31) >> 5;
       const float inv_n = p.inv_n ? p.inv_n[(long long)qseq * p.n_mod + it.mod] : 1.f;
       if (!head_mode) { while (cur_mod < it.mod) { store_out(cur_mod, h); ++cur_mod; } }
       mbar_wait(&sm.s_full, i & 1);
@@ -981,7 +980,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ AttnMaps maps, const MmsumAttnArgs p
       const int nfull = it.n16 >> 5;                 // 32-column chunks; an odd 16-column tail is handled on its own
       const bool tail = (it.n16 & 16) != 0;
 #else
-      const int nfull = nchunk;
+      const int nfull = (it.n16 + 31) >> 5;
       const bool tail = false;
 #endif
 #if MMSUM_FWD_ONEPASS
@@ -1658,7 +1657,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap q64, const __grid_con
     kvrow0 = (int)(md.kv_row_base + ((long long)biz * md.E + e) * (md.ent_stride > 0 ? md.ent_stride : md.Sk)) + key0;
   }
   const int e_hi = min(e + 1, md.E - 1);                       // second entity of a packed tile (== e when there is none)
-  const int ge = md.ent_base + e;
   auto ent_valid_at = [&](int ee) { return (p.ent_valid == nullptr) || (p.ent_valid[(long long)biz * p.E_total + md.ent_base + ee] != 0); };
   const bool ok_lo = ent_valid_at(e), ok_hi = packed && (key0 + SQ > md.Sk) && (e + 1 < md.E) && ent_valid_at(e + 1);
   const bool ent_ok = ok_lo || ok_hi;

@@ -128,7 +128,6 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
 #ifndef MMSUM_DECODE_ORDERED
 #define MMSUM_DECODE_ORDERED 1     // entity outputs are added to the CTA accumulator in ENTITY ORDER (bit-reproducible results)
 #endif
-  int cur_mod = -1;
   // ordered variant: the warp that finished entity i waits until entity i-1 has been added, then adds its own output with plain
   // read-modify-writes (it holds the turn) and passes the turn on.  Entities are pulled in increasing order, so they also finish
   // roughly in order and the wait is short; the sum order no longer depends on which warp got which entity or on timing.
@@ -149,6 +148,8 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
     __syncwarp();
     if (lane == 0) *reinterpret_cast<volatile int*>(&sm.turn) = i + 1;
   };
+#if !MMSUM_DECODE_ORDERED
+  int cur_mod = -1;
   auto flush = [&](int m) {          // fold this warp's partial output of modality m into the CTA accumulator
     if (m >= 0 && g < R) {
 #pragma unroll
@@ -160,6 +161,7 @@ attn_decode_cross_kernel(const __grid_constant__ DecMaps maps, const MmsumAttnAr
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd) { oc[nd][0] = 0.f; oc[nd][1] = 0.f; oc[nd][2] = 0.f; oc[nd][3] = 0.f; }
   };
+#endif
 
   uint32_t phase = 0;
   for (;;) {
