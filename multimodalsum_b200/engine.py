@@ -623,7 +623,7 @@ class StepEngine:
             c = self._len_cache
             if c is not None and c[0]() is m and c[1] == m._version:
                 n = c[2]
-            elif torch.cuda.is_current_stream_capturing():
+            elif m.is_cuda and torch.cuda.is_current_stream_capturing():
                 return S
             else:
                 pos = torch.arange(1, S + 1, device=m.device, dtype=torch.int32)

@@ -105,3 +105,56 @@ def test_synthetic_batch_shapes_and_invariants():
     assert ((b.reviews == 1) == (b.reviews_mask == 0)).all()
     b2 = make_batch(ModelConfig(dataset="amazon"), 2, seed=3)
     assert b2.img.shape == (2, 1, 196, 1024) and b2.field.shape == (6, 1) and b2.field_value[4].shape == (2, 3, 8, 12)
+
+
+def test_encoder_frame_views_and_length_cache():
+    """Host logic of the trimmed encoder frames (engine._encoder_frame / _alloc / _frame_view), on CPU tensors: the frame is
+    the next multiple of 16 above the longest review (hint, read-back, cache keyed on the tensor's identity and version), the
+    workspace is allocated once for full frames and a step works on views of the same storage, and the encoder-sized scratch
+    pool hands out row-cut views of the shared buffers."""
+    import torch
+    from multimodalsum_b200.engine import StepEngine
+    from multimodalsum_b200.synth import ModelConfig, make_batch
+    cfg = ModelConfig(dataset="yelp", encoder_layers=1, decoder_layers=2, ffn_dim=64, vocab_size=512, max_position_embeddings=128)
+    eng = StepEngine(cfg, device="cpu")
+    b = make_batch(cfg, 2, seed=3, n_reviews=3, max_imgs=2, len_range=(20, 70))
+    longest = int(b.reviews_mask.sum(-1).max())
+    frame = (longest + 15) // 16 * 16
+    assert eng._encoder_frame(b, 128) == frame                       # read back from the mask
+    assert eng._len_cache[0]() is b.reviews_mask and eng._len_cache[2] == longest
+    b.reviews_mask[0, 0, 100] = 1                                    # in-place change bumps the version: the cache must miss
+    assert eng._encoder_frame(b, 128) == 112
+    b.reviews_mask[0, 0, 100] = 0
+    other = b.reviews_mask.clone()                                   # a different tensor object never hits the cache
+    b2 = make_batch(cfg, 2, seed=3, n_reviews=3, max_imgs=2, len_range=(20, 70))
+    b2.reviews_mask = other
+    assert eng._encoder_frame(b2, 128) == frame
+    assert b.with_length_hint().max_review_len == longest
+    b.max_review_len = 17
+    assert eng._encoder_frame(b, 128) == 32                          # the hint wins (a wrong one fails loudly on the device)
+    b.max_review_len = 1
+    assert eng._encoder_frame(b, 128) == 16
+    eng.trim_frames = False
+    assert eng._encoder_frame(b, 128) == 128
+    eng.trim_frames = True
+
+    B, R, S, F, n_img, ik = 2, 3, 128, 47, 2, 196
+    w = eng._alloc(B, R, S, F, n_img, ik, 80)
+    full = eng.ws_full
+    assert (w["S_enc"], w["Te"], w["Tt"]) == (80, B * R * 80, B * R * 80)
+    assert w["Tm"] == B * R * 80 + B * F + B * n_img * ik and w["T"] == B * R * S
+    assert w["MEM"].shape[0] == w["Tm"] and w["MEM"].data_ptr() == full["MEM"].data_ptr()
+    assert w["enc"][0]["qkv"].shape == (w["Te"], 3 * cfg.d_model) and w["enc"][0]["qkv"].data_ptr() == full["enc"][0]["qkv"].data_ptr()
+    assert w["enc"][0]["lse"] is full["enc"][0]["lse"]
+    assert w["dec"][0]["kv"].shape[0] == w["Tm"] and w["dec"][0]["x"] is full["dec"][0]["x"]
+    assert w["dkv_all"].shape == (w["Tm"], cfg.decoder_layers * 2 * cfg.d_model)
+    assert eng._alloc(B, R, S, F, n_img, ik, 80) is w                # cached view, nothing reallocated
+    assert eng._alloc(B, R, S, F, n_img, ik, 128) is full
+    assert eng._alloc(B, R, S, F, n_img, ik, 96)["MEM"].data_ptr() == full["MEM"].data_ptr()
+    pool = w["pool_e"]
+    x = pool.get()
+    y = pool.get()
+    assert x.shape == (w["Te"], cfg.d_model) and x.data_ptr() != y.data_ptr()
+    n_free = len(full["pool"].free)
+    pool.put(x, y)
+    assert len(full["pool"].free) == n_free + 2 and all(t.shape[0] == B * R * S for t in full["pool"].free)
