@@ -428,6 +428,8 @@ class MultimodalSum(nn.Module, _EngineRoot):
         frames trimmed to it without the engine reading the mask back from the device."""
         eng = self._ensure_engine(reviews.device)
         _check_device(reviews.device, reviews_mask, reviews_rating, field, img, img_mask, *field_value)
+        if max_review_len is None:
+            max_review_len = getattr(reviews_mask, "max_review_len", None)      # attached by prefetch.*_data_prefetcher
         batch = Batch(_ids(reviews), _ids(reviews_mask), reviews_rating.float().contiguous(), _ids(field),
                       [_ids(v) for v in field_value], img if img.dtype == torch.bfloat16 else img.float(),
                       img_mask.to(torch.bool).contiguous(), max_review_len=max_review_len)
@@ -471,6 +473,8 @@ class TextSupervised(nn.Module, _EngineRoot):
     def forward(self, reviews, reviews_mask, reviews_rating, max_review_len=None, **unused):
         eng = self._ensure_engine(reviews.device)
         _check_device(reviews.device, reviews_mask, reviews_rating)
+        if max_review_len is None:
+            max_review_len = getattr(reviews_mask, "max_review_len", None)      # attached by prefetch.text_data_prefetcher
         batch = Batch(_ids(reviews), _ids(reviews_mask), reviews_rating.float().contiguous(), max_review_len=max_review_len)
         loss = _StepFn.apply(eng.anchor, self, batch, self.label_smoothing)
         return (loss,)
