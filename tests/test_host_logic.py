@@ -158,3 +158,41 @@ def test_encoder_frame_views_and_length_cache():
     n_free = len(full["pool"].free)
     pool.put(x, y)
     assert len(full["pool"].free) == n_free + 2 and all(t.shape[0] == B * R * S for t in full["pool"].free)
+
+
+def test_bench_reference_arm_prints_the_contract_line(monkeypatch, capsys):
+    """`bench.py --impl reference` (the driver's reference arm): ONE JSON line with the b200 arm's metric / unit / workload, the
+    extra keys of the tier contract (impl, cpu_baseline, e2e with zero copy bytes); under torchrun only rank 0 works (the other
+    ranks exit 0 without output).  The timing loop itself (a 40-second full-size CPU step) is stubbed here."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    sys.path.insert(0, root)
+    import bench
+    seen = {}
+
+    def fake_steps(steps, warmup, budget_s, dataset="yelp"):
+        seen.update(steps=steps, warmup=warmup, budget_s=budget_s, dataset=dataset)
+        return dict(value=0.25, ms_per_step=4000.0, steps=steps, warmup=warmup, cores=8, kind="reference", sample="1 business per step (stub)")
+
+    monkeypatch.setattr(bench, "cpu_reference_steps", fake_steps)
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "4", "--steps", "2", "--warmup", "1"])
+    bench.main()
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert seen == dict(steps=2, warmup=1, budget_s=240.0, dataset="yelp")
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "businesses/s" and d["n_gpus"] == 4
+    assert d["higher_is_better"] is True and d["value"] == 0.25 and d["steps"] == 2 and d["warmup"] == 1 and d["scaling"] == "weak"
+    assert d["cpu_baseline"] == {"value": 0.25, "unit": "businesses/s", "cores": 8, "kind": "reference", "sample": "1 business per step (stub)"}
+    assert d["e2e"] == {"value": 0.25, "unit": "businesses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    # same workload description as the b200 arm (the driver compares the two lines' configs)
+    args = bench.parse()
+    assert d["config"]["workload"] == bench.train_config(args, 1)["workload"] and d["config"]["workload"].startswith("BASELINE configs[1]")
