@@ -225,6 +225,14 @@ def _dist_env():
     return world, rank, local_rank
 
 
+def _build_record():
+    """Which library ran: the record build() wrote next to libmmsum_b200.so and whether it matches the sources of this tree."""
+    from multimodalsum_b200 import _lib
+    b = _lib.build_info()
+    return {"library": os.path.relpath(b["path"], ROOT), "nvcc": b.get("nvcc"), "arch": b.get("arch"),
+            "source_digest": (b.get("source_digest") or "")[:16], "matches_sources": b["matches_sources"]}
+
+
 class KernelTimer:
     """ops.KERNEL_TIMER hook: brackets every C-ABI call of the instrumented steps with CUDA events on the launching stream."""
 
@@ -442,6 +450,7 @@ def run_train(args):
                      "frac": gemm.get("frac"), "traffic": traffic.get("gemm"),
                      "peak_source": peaks["source"] + " (sustained bf16)", "gemm_share_of_step": gemm.get("share_of_step")},
         "roofline_kernels": rk,
+        "build": _build_record(),
     }
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_steps(3, 1, 60.0, args.workload)

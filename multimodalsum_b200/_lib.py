@@ -70,6 +70,12 @@ def lib():
             raise MmsumError(
                 "libmmsum_b200.so is not built (%s). Run `python -m multimodalsum_b200.build` "
                 "(needs nvcc); there is no fallback path." % LIB_PATH)
+        if not os.environ.get("MMSUM_LIB_PATH") and os.environ.get("MMSUM_ALLOW_STALE_LIB") != "1":
+            from . import build as _build
+            if _build.is_current() is False:       # None = no build record next to the library: nothing to compare
+                raise MmsumError(
+                    "libmmsum_b200.so was built from different sources than the ones in %s (csrc/, include/ or the compiler "
+                    "flags changed since). Re-run `python -m multimodalsum_b200.build`." % _HERE)
         _lib = C.CDLL(LIB_PATH)
         for name in EXPORTS:
             fn = getattr(_lib, name)  # AttributeError if the symbol is missing
@@ -86,6 +92,15 @@ EXPORTS = [
     "mmsum_table_fwd", "mmsum_table_bits_bwd", "mmsum_grad_sumsq", "mmsum_adamw_step",
     "mmsum_embed_ln_decode", "mmsum_attn_decode_cross", "mmsum_attn_decode_self", "mmsum_beam_topk", "mmsum_beam_update",
 ]
+
+
+def build_info():
+    """The record build() wrote next to the library (compiler, flags, source digest) + whether it matches this tree."""
+    from . import build as _build
+    info = dict(_build.read_build_info() or {})
+    info["matches_sources"] = _build.is_current()
+    info["path"] = LIB_PATH
+    return info
 
 
 def check(rc, what):

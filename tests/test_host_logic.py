@@ -196,3 +196,22 @@ def test_bench_reference_arm_prints_the_contract_line(monkeypatch, capsys):
     # same workload description as the b200 arm (the driver compares the two lines' configs)
     args = bench.parse()
     assert d["config"]["workload"] == bench.train_config(args, 1)["workload"] and d["config"]["workload"].startswith("BASELINE configs[1]")
+
+
+def test_library_is_tied_to_the_sources_it_was_built_from(monkeypatch):
+    """build() leaves a record (source digest, nvcc, flags) next to the library; loading a library whose record does not match
+    csrc/ + include/ raises instead of running stale kernels (file mtimes do not survive the snapshot to the GPU box)."""
+    from multimodalsum_b200 import build as B
+    info = _lib.build_info()
+    if B.read_build_info() is None:
+        pytest.skip("library shipped without a build record")
+    assert info["matches_sources"] is True and info["source_digest"] == B.source_digest()
+    assert "arch=compute_100a,code=sm_100a" in info["flags"] and "-lineinfo" in info["flags"] and info["arch"] == "sm_100a"
+    assert B.build(force=False) == B.LIB                          # current: nothing is recompiled
+    monkeypatch.setattr(B, "source_digest", lambda: "0" * 64)     # as if a .cu file had been edited after the build
+    assert B.is_current() is False
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(_lib.MmsumError, match="built from different sources"):
+        _lib.lib()
+    monkeypatch.setenv("MMSUM_ALLOW_STALE_LIB", "1")              # explicit override (A/B tooling)
+    assert _lib.lib() is not None
