@@ -88,6 +88,26 @@ class GradAllReducer:
         self.lo = 0
 
 
+class DistributedDataParallel(torch.nn.Module):
+    """`DDP(model, delay_allreduce=True)` as src/multimodal_train.py:474 writes it (apex.parallel.DistributedDataParallel): the
+    wrapped model under `.module`, forward delegated, rank 0's parameters broadcast at construction (apex does the same), and the
+    gradient exchange attached — here the bucketed, overlapped `GradAllReducer` instead of apex's one flat all-reduce after
+    backward.  The module must already live on its CUDA device (`model.cuda()` comes first in the reference too)."""
+
+    def __init__(self, module, delay_allreduce=True, process_group=None, bucket_mb=64, wire_dtype=None):
+        super().__init__()
+        self.module = module
+        dev = next(module.parameters()).device
+        eng = module._ensure_engine(dev)
+        if dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            dist.broadcast(eng.W32, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+            eng.mark_weights_dirty()
+        self.reducer = GradAllReducer(eng, process_group=process_group, bucket_mb=bucket_mb, wire_dtype=wire_dtype)
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+
 def reduce_tensor(tensor, world_size):
     """src/utils.py:8-12 — average a scalar over ranks for logging."""
     rt = tensor.clone()

@@ -5,13 +5,21 @@
                                       clip_grad_norm_, AdamW.step, scheduler.step
   save_checkpoint                     src/train_utils.py:79-97       pytorch_model.bin (+ training_state.bin), `save_option`
                                       'whole' | 'text' | 'img' | 'table' selects the sub-module whose state_dict is written
+  set_environments                    src/train_utils.py:12-31       checkpoint dir + training_args.bin, NCCL process group
+  make_loops -> (train, validate)     src/multimodal_train.py:346-408 the epoch bodies with the reference's signatures (the
+                                      module globals `args` / `field` they read are bound here), on prefetch.*_data_prefetcher
+  train_model                         src/train_utils.py:65-97       epochs, sampler epochs, validation, early stopping, files
+  AverageMeter                        src/utils.py:40-56
 The files interchange with the reference: `state_dict` keys / shapes are the reference's, the optimizer state
 uses transformers-AdamW names.
 """
+import datetime
 import os
+import time
 
 import torch
 
+from .dp import reduce_tensor
 from .optim import FusedAdamW, LinearWarmupSchedule, get_optimizer, get_scheduler  # noqa: F401
 
 
@@ -45,3 +53,128 @@ def save_checkpoint(model, optimizer, scheduler, epoch, ckpt_dir, save_option="w
              "scheduler": scheduler.state_dict() if scheduler is not None else None}
     torch.save(state, os.path.join(ckpt_dir, "training_state.bin"))
     return ckpt_dir
+
+
+class AverageMeter:
+    """src/utils.py:40-56."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.val = self.avg = self.sum = self.count = 0
+
+    def update(self, val, n=1):
+        self.val = val
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / self.count
+
+
+def set_environments(args):
+    """src/train_utils.py:12-31: rank 0 creates `args.ckpt` and writes training_args.bin; under torchrun (WORLD_SIZE > 1) the
+    process binds its GPU and joins the NCCL group (one process per GPU).  LOCAL_RANK from the environment wins over
+    `args.local_rank` (torchrun no longer passes --local_rank)."""
+    args.local_rank = int(os.environ.get("LOCAL_RANK", getattr(args, "local_rank", 0)))
+    if args.local_rank == 0:
+        os.makedirs(args.ckpt, exist_ok=True)
+        torch.save(vars(args), "%s/training_args.bin" % args.ckpt)
+    args.distributed = int(os.environ.get("WORLD_SIZE", "1")) > 1
+    args.gpu = 0
+    args.world_size = 1
+    if args.distributed:
+        args.gpu = args.local_rank
+        torch.cuda.set_device(args.gpu)
+        if not torch.distributed.is_initialized():
+            torch.distributed.init_process_group(backend="nccl", init_method="env://", device_id=torch.device("cuda", args.gpu))
+        args.world_size = torch.distributed.get_world_size()
+        print("GPU {}/{}".format(args.gpu, args.world_size))
+    return args
+
+
+def make_loops(args, field, log=print):
+    """-> (train, validate) with the signatures of src/multimodal_train.py:346 / :381, to be handed to `train_model`.
+
+    `args` needs: dataset ('yelp' | 'amazon'), max_grad_norm, log_interval, distributed, world_size, local_rank.  `field` is the
+    table's field-name ids already on the GPU (src/multimodal_train.py:469-470).  Statement order is the reference's; batches
+    come through `prefetch.yelp_/amazon_data_prefetcher`; with a FusedAdamW built with `max_grad_norm` the clip is part of the
+    update kernel, otherwise `clip_grad_norm_` runs as in :361-362."""
+    from . import prefetch
+
+    def _prefetcher(loader):
+        if args.dataset == "yelp":
+            return prefetch.yelp_data_prefetcher(loader)
+        if args.dataset == "amazon":
+            return prefetch.amazon_data_prefetcher(loader)
+        raise ValueError("args.dataset must be 'yelp' or 'amazon'")
+
+    def train(start_time, train_dataloader, model, optimizer, scheduler, e, t_epoch):
+        model.train()
+        prefetcher = _prefetcher(train_dataloader)
+        reviews, reviews_mask, reviews_rating, field_value, img, img_mask = prefetcher.next()
+        i = 0
+        fused_clip = isinstance(optimizer, FusedAdamW) and optimizer.max_grad_norm is not None
+        while reviews is not None:
+            loss = model(reviews, reviews_mask, reviews_rating, field, field_value, img, img_mask)[0]
+
+            optimizer.zero_grad()
+            loss.backward()
+            if args.max_grad_norm is not None and not fused_clip:
+                torch.nn.utils.clip_grad_norm_(model.parameters(), args.max_grad_norm)
+            optimizer.step()
+            scheduler.step()
+
+            if args.log_interval and i % args.log_interval == 0:
+                reduced_loss = reduce_tensor(loss.data, args.world_size) if args.distributed else loss.data
+                torch.cuda.synchronize()
+                if args.local_rank == 0:
+                    timedelta = str(datetime.timedelta(seconds=int(time.time() - start_time)))
+                    log("{} epoch {} batch id {}/{} loss {}".format(timedelta, e + 1, i + 1, t_epoch, reduced_loss.item()))
+
+            reviews, reviews_mask, reviews_rating, field_value, img, img_mask = prefetcher.next()
+            i += 1
+        return i
+
+    def validate(val_dataloader, model, e):
+        model.eval()
+        losses = AverageMeter()
+        prefetcher = _prefetcher(val_dataloader)
+        reviews, reviews_mask, reviews_rating, field_value, img, img_mask = prefetcher.next()
+        while reviews is not None:
+            with torch.no_grad():
+                loss = model(reviews, reviews_mask, reviews_rating, field, field_value, img, img_mask)[0]
+            reduced_loss = reduce_tensor(loss.data, args.world_size) if args.distributed else loss.data
+            losses.update(reduced_loss.item(), reviews.size(0))
+            reviews, reviews_mask, reviews_rating, field_value, img, img_mask = prefetcher.next()
+        torch.cuda.synchronize()
+        if args.local_rank == 0:
+            log("{} epoch valid loss {}".format(e + 1, losses.avg))
+        return losses.avg
+
+    return train, validate
+
+
+def train_model(args, model, train_sampler, train_dataloader, val_dataloader, train, validate, optimizer, scheduler, t_epoch,
+                save_option="whole", log=print):
+    """src/train_utils.py:65-97: per epoch — sampler / dataset epoch bookkeeping, `train`, `validate`, and on rank 0 the
+    checkpoint files when the validation loss is the best so far (`args.early_stopping`) or always (otherwise).  Returns the
+    list of validation losses (rank 0's view)."""
+    start_time = time.time()
+    val_loss_list = []
+    for e in range(args.num_epochs):
+        log("Epoch {}".format(e + 1))
+        if args.distributed and train_sampler is not None:
+            train_sampler.set_epoch(e)
+        if e != 0 and hasattr(getattr(train_dataloader, "dataset", None), "set_epoch"):
+            train_dataloader.dataset.set_epoch()
+
+        train(start_time, train_dataloader, model, optimizer, scheduler, e, t_epoch)
+        val_loss = validate(val_dataloader, model, e)
+
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        if args.local_rank == 0:
+            val_loss_list.append(val_loss)
+            if (not args.early_stopping) or val_loss <= min(val_loss_list):
+                save_checkpoint(model, optimizer, scheduler, e, args.ckpt, save_option)
+    return val_loss_list

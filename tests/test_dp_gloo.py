@@ -43,6 +43,27 @@ def _worker(rank, world, port, q):
     ok = torch.allclose(eng.G32, (g0 + g1) / 2, atol=1e-6)
     # small ranges are merged into >= bucket-size all-reduces; the tail is always flushed
     ok = ok and red.n_buckets == 3 and red.lo == 0 and not red.works
+    # DDP(model, delay_allreduce=True) of src/multimodal_train.py:474: rank 0's parameters reach every rank, the reducer is hooked
+    from multimodalsum_b200.dp import DistributedDataParallel as DDP
+
+    class _Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(4))
+            self.eng = types.SimpleNamespace(W32=torch.full((64,), float(rank + 1)), G32=torch.zeros(64), numel=64, device=torch.device("cpu"),
+                                             grad_ready_hook=None, dirty=0)
+            self.eng.mark_weights_dirty = lambda: setattr(self.eng, "dirty", self.eng.dirty + 1)
+
+        def _ensure_engine(self, device):
+            return self.eng
+
+        def forward(self, x, scale=1.0):
+            return (x * scale,)
+
+    m = _Model()
+    ddp = DDP(m, delay_allreduce=True)
+    ok = ok and ddp.module is m and bool((m.eng.W32 == 1.0).all()) and m.eng.dirty == 1 and m.eng.grad_ready_hook is not None
+    ok = ok and ddp(torch.ones(1), scale=3.0)[0].item() == 3.0 and list(ddp.state_dict()) == ["module.w"]
     r = reduce_tensor(torch.tensor(float(rank + 1)), world)
     ok = ok and abs(r.item() - 1.5) < 1e-6
     q.put((rank, bool(ok), red.n_buckets))
