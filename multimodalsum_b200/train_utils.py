@@ -7,7 +7,9 @@
                                       'whole' | 'text' | 'img' | 'table' selects the sub-module whose state_dict is written
   set_environments                    src/train_utils.py:12-31       checkpoint dir + training_args.bin, NCCL process group
   make_loops -> (train, validate)     src/multimodal_train.py:346-408 the epoch bodies with the reference's signatures (the
-                                      module globals `args` / `field` they read are bound here), on prefetch.*_data_prefetcher
+                                      module globals `args` / `field` they read are bound here), on prefetch.*_data_prefetcher;
+                                      `stage=` 'text' | 'img' | 'table' gives the loops of src/text_pretrain.py:151-207,
+                                      src/img_pretrain.py:178-238, src/table_pretrain.py:242-303
   train_model                         src/train_utils.py:65-97       epochs, sampler epochs, validation, early stopping, files
   AverageMeter                        src/utils.py:40-56
 The files interchange with the reference: `state_dict` keys / shapes are the reference's, the optimizer state
@@ -92,61 +94,86 @@ def set_environments(args):
     return args
 
 
-def make_loops(args, field, log=print):
-    """-> (train, validate) with the signatures of src/multimodal_train.py:346 / :381, to be handed to `train_model`.
+def _stage_table(args, field, stage):
+    """Per training stage: the prefetcher, how a staged tuple becomes the model call, the batch size `validate` weights by, and
+    the parameters `clip_grad_norm_` sees (all for the multimodal / text stages; the trained head only for the img / table
+    pretraining stages, src/img_pretrain.py:190-194, src/table_pretrain.py:259-263)."""
+    from . import prefetch
+    by_dataset = lambda y, a: {"yelp": y, "amazon": a}.get(args.dataset)       # noqa: E731
+    unwrap = lambda m: getattr(m, "module", m)                                  # noqa: E731
+    if stage == "multimodal":        # src/multimodal_train.py:346-408
+        return dict(prefetcher=by_dataset(prefetch.yelp_data_prefetcher, prefetch.amazon_data_prefetcher),
+                    call=lambda m, t: m(t[0], t[1], t[2], field, t[3], t[4], t[5]), first=lambda t: t[0],
+                    clip=lambda m: m.parameters())
+    if stage == "text":              # src/text_pretrain.py:151-207
+        return dict(prefetcher=prefetch.text_data_prefetcher, call=lambda m, t: m(t[0], t[1], t[2]), first=lambda t: t[0],
+                    clip=lambda m: m.parameters())
+    if stage == "img":               # src/img_pretrain.py:178-238
+        return dict(prefetcher=prefetch.img_data_prefetcher, call=lambda m, t: m(t[0], t[1], labels=t[2]), first=lambda t: t[0],
+                    clip=lambda m: [p for n, p in unwrap(m).named_parameters() if n.startswith("img_encoder")])
+    if stage == "table":             # src/table_pretrain.py:242-303
+        return dict(prefetcher=by_dataset(prefetch.yelp_table_data_prefetcher, prefetch.amazon_table_data_prefetcher),
+                    call=lambda m, t: m(field, t[0], labels=t[1]), first=lambda t: t[0][0],
+                    clip=lambda m: [p for n, p in unwrap(m).table_encoder.named_parameters() if not n.startswith("bart")])
+    raise ValueError("stage must be 'multimodal', 'text', 'img' or 'table'")
+
+
+def make_loops(args, field=None, log=print, stage="multimodal", device=None):
+    """-> (train, validate) with the signatures of src/multimodal_train.py:346 / :381 (and of the three pretraining scripts'
+    loops, `stage=`), to be handed to `train_model`.
 
     `args` needs: dataset ('yelp' | 'amazon'), max_grad_norm, log_interval, distributed, world_size, local_rank.  `field` is the
-    table's field-name ids already on the GPU (src/multimodal_train.py:469-470).  Statement order is the reference's; batches
-    come through `prefetch.yelp_/amazon_data_prefetcher`; with a FusedAdamW built with `max_grad_norm` the clip is part of the
-    update kernel, otherwise `clip_grad_norm_` runs as in :361-362."""
-    from . import prefetch
-
-    def _prefetcher(loader):
-        if args.dataset == "yelp":
-            return prefetch.yelp_data_prefetcher(loader)
-        if args.dataset == "amazon":
-            return prefetch.amazon_data_prefetcher(loader)
+    table's field-name ids already on the GPU (src/multimodal_train.py:469-470; unused by the text / img stages).  Statement
+    order is the reference's; batches come through the staging prefetchers (prefetch.py); with a FusedAdamW built with
+    `max_grad_norm` the clip is part of the update kernel, otherwise `clip_grad_norm_` runs as in the reference."""
+    st = _stage_table(args, field, stage)
+    if st["prefetcher"] is None:
         raise ValueError("args.dataset must be 'yelp' or 'amazon'")
+    on_cuda = device is None or torch.device(device).type == "cuda"
+
+    def _sync():
+        if on_cuda:
+            torch.cuda.synchronize()
 
     def train(start_time, train_dataloader, model, optimizer, scheduler, e, t_epoch):
         model.train()
-        prefetcher = _prefetcher(train_dataloader)
-        reviews, reviews_mask, reviews_rating, field_value, img, img_mask = prefetcher.next()
+        prefetcher = st["prefetcher"](train_dataloader, device=device)
+        batch = prefetcher.next()
         i = 0
         fused_clip = isinstance(optimizer, FusedAdamW) and optimizer.max_grad_norm is not None
-        while reviews is not None:
-            loss = model(reviews, reviews_mask, reviews_rating, field, field_value, img, img_mask)[0]
+        while st["first"](batch) is not None:
+            loss = st["call"](model, batch)[0]
 
             optimizer.zero_grad()
             loss.backward()
             if args.max_grad_norm is not None and not fused_clip:
-                torch.nn.utils.clip_grad_norm_(model.parameters(), args.max_grad_norm)
+                torch.nn.utils.clip_grad_norm_(st["clip"](model), args.max_grad_norm)
             optimizer.step()
             scheduler.step()
 
             if args.log_interval and i % args.log_interval == 0:
                 reduced_loss = reduce_tensor(loss.data, args.world_size) if args.distributed else loss.data
-                torch.cuda.synchronize()
+                _sync()
                 if args.local_rank == 0:
                     timedelta = str(datetime.timedelta(seconds=int(time.time() - start_time)))
                     log("{} epoch {} batch id {}/{} loss {}".format(timedelta, e + 1, i + 1, t_epoch, reduced_loss.item()))
 
-            reviews, reviews_mask, reviews_rating, field_value, img, img_mask = prefetcher.next()
+            batch = prefetcher.next()
             i += 1
         return i
 
     def validate(val_dataloader, model, e):
         model.eval()
         losses = AverageMeter()
-        prefetcher = _prefetcher(val_dataloader)
-        reviews, reviews_mask, reviews_rating, field_value, img, img_mask = prefetcher.next()
-        while reviews is not None:
+        prefetcher = st["prefetcher"](val_dataloader, device=device)
+        batch = prefetcher.next()
+        while st["first"](batch) is not None:
             with torch.no_grad():
-                loss = model(reviews, reviews_mask, reviews_rating, field, field_value, img, img_mask)[0]
+                loss = st["call"](model, batch)[0]
             reduced_loss = reduce_tensor(loss.data, args.world_size) if args.distributed else loss.data
-            losses.update(reduced_loss.item(), reviews.size(0))
-            reviews, reviews_mask, reviews_rating, field_value, img, img_mask = prefetcher.next()
-        torch.cuda.synchronize()
+            losses.update(reduced_loss.item(), st["first"](batch).size(0))
+            batch = prefetcher.next()
+        _sync()
         if args.local_rank == 0:
             log("{} epoch valid loss {}".format(e + 1, losses.avg))
         return losses.avg

@@ -101,6 +101,83 @@ def test_average_meter():
     assert m.val == 5.0 and m.count == 6 and m.sum == 18.0 and m.avg == 3.0
 
 
+class _StubModel(torch.nn.Module):
+    """Stands in for the four stage modules on the CPU: records how it was called, returns a loss that depends on one tensor of
+    the batch and on its parameters (so backward / clip / step do something)."""
+
+    def __init__(self, pick):
+        super().__init__()
+        self.img_encoder = torch.nn.Linear(1, 1, bias=False)
+        self.table_encoder = torch.nn.Module()
+        self.table_encoder.fc = torch.nn.Linear(1, 1, bias=False)
+        self.table_encoder.bart_embedding = torch.nn.Linear(1, 1, bias=False)
+        self.other = torch.nn.Parameter(torch.ones(1))
+        with torch.no_grad():
+            for p in self.parameters():
+                p.fill_(1.0)
+        self.pick, self.calls = pick, []
+
+    def forward(self, *a, **k):
+        self.calls.append((self.training, torch.is_grad_enabled(), len(a), sorted(k)))
+        x = self.pick(a, k).float().mean()
+        w = self.img_encoder.weight.sum() + self.table_encoder.fc.weight.sum() + self.table_encoder.bart_embedding.weight.sum() + self.other.sum()
+        return (x * w * 100.0,)
+
+
+@pytest.mark.parametrize("stage", ["multimodal", "text", "img", "table"])
+def test_stage_loops_call_the_model_as_the_reference_scripts_do(stage):
+    """make_loops(stage=...) on CPU tensors (device='cpu' prefetchers, stub model): the positional / keyword layout of each
+    script's model call, clip_grad_norm_ restricted to the trained head in the img / table stages, size-weighted validation."""
+    cfg = ModelConfig(dataset="yelp", **SMALL)
+    bs = [make_batch(cfg, n, seed=s, n_reviews=2, max_imgs=2) for s, n in ((1, 2), (2, 2), (3, 1))]
+    g = torch.Generator().manual_seed(0)
+    labels = [torch.randint(3, 50, (b.reviews.shape[0], 16), generator=g) for b in bs]
+    field = bs[0].field
+    if stage == "multimodal":
+        loader = [_tuple(b) for b in bs]
+        pick, want_call = (lambda a, k: a[5]), (7, [])                                     # img
+        expect = [b.img.float().mean().item() for b in bs]
+    elif stage == "text":
+        loader = [(b.reviews, b.reviews_mask, b.reviews_rating) for b in bs]
+        pick, want_call = (lambda a, k: a[2]), (3, [])                                     # reviews_rating
+        expect = [b.reviews_rating.mean().item() for b in bs]
+    elif stage == "img":
+        loader = [(b.img[:, 0], b.img_mask, l) for b, l in zip(bs, labels)]
+        pick, want_call = (lambda a, k: k["labels"]), (2, ["labels"])
+        expect = [l.float().mean().item() for l in labels]
+    else:
+        loader = [(*b.field_value, l) for b, l in zip(bs, labels)]
+        pick, want_call = (lambda a, k: k["labels"] + 0 * a[0].sum() + 0 * a[1][5].sum()), (2, ["labels"])   # (field, field_value, labels=)
+        expect = [l.float().mean().item() for l in labels]
+    args = types.SimpleNamespace(dataset="yelp", max_grad_norm=1, log_interval=1, distributed=False, world_size=1, local_rank=0)
+    model = _StubModel(pick)
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)                                       # lr 0: the loss stays a function of the batch only
+    sch = torch.optim.lr_scheduler.LambdaLR(opt, lambda step: 1.0)
+    logs = []
+    train, validate = TU.make_loops(args, field, log=logs.append, stage=stage, device="cpu")
+    assert train(0.0, loader, model, opt, sch, 0, 3) == 3
+    assert [c[2:] for c in model.calls] == [want_call] * 3 and all(c[0] and c[1] for c in model.calls)
+    got = [float(l.rsplit(" ", 1)[1]) for l in logs]
+    assert got == pytest.approx([x * 4 * 100.0 for x in expect], rel=1e-5)
+    # gradient clipping: the whole model in the multimodal / text stages, only the trained head in the pretraining stages
+    gn = {n: p.grad.abs().item() for n, p in [("img", model.img_encoder.weight), ("fc", model.table_encoder.fc.weight),
+                                                ("bart", model.table_encoder.bart_embedding.weight), ("other", model.other)]}
+    raw = abs(expect[-1]) * 100.0
+    if stage in ("multimodal", "text"):
+        assert all(v == pytest.approx(0.5, rel=1e-4) for v in gn.values())                 # 4 equal gradients clipped to total norm 1
+    elif stage == "img":
+        assert gn["img"] == pytest.approx(1.0, rel=1e-4) and gn["fc"] == pytest.approx(raw, rel=1e-4) and gn["other"] == pytest.approx(raw, rel=1e-4)
+    else:
+        assert gn["fc"] == pytest.approx(1.0, rel=1e-4) and gn["bart"] == pytest.approx(raw, rel=1e-4) and gn["img"] == pytest.approx(raw, rel=1e-4)
+    model.calls.clear()
+    avg = validate(loader, model, 0)
+    assert all((not c[0]) and (not c[1]) for c in model.calls) and len(model.calls) == 3   # eval mode, under no_grad
+    sizes = [2, 2, 1]
+    assert avg == pytest.approx(sum(x * 400.0 * n for x, n in zip(expect, sizes)) / 5, rel=1e-5)
+    with pytest.raises(ValueError):
+        TU.make_loops(args, field, stage="bogus")
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _tuple(b):
     return (b.reviews, b.reviews_mask, b.reviews_rating, *b.field_value, b.img, b.img_mask)
