@@ -5,6 +5,7 @@
                                       clip_grad_norm_, AdamW.step, scheduler.step
   save_checkpoint                     src/train_utils.py:79-97       pytorch_model.bin (+ training_state.bin), `save_option`
                                       'whole' | 'text' | 'img' | 'table' selects the sub-module whose state_dict is written
+  load_checkpoint                     (no reference counterpart)     resume: weights, optimizer moments, schedule position
   set_environments                    src/train_utils.py:12-31       checkpoint dir + training_args.bin, NCCL process group
   make_loops -> (train, validate)     src/multimodal_train.py:346-408 the epoch bodies with the reference's signatures (the
                                       module globals `args` / `field` they read are bound here), on prefetch.*_data_prefetcher;
@@ -55,6 +56,33 @@ def save_checkpoint(model, optimizer, scheduler, epoch, ckpt_dir, save_option="w
              "scheduler": scheduler.state_dict() if scheduler is not None else None}
     torch.save(state, os.path.join(ckpt_dir, "training_state.bin"))
     return ckpt_dir
+
+
+def load_checkpoint(model, optimizer, scheduler, ckpt_dir, save_option="whole", map_location="cpu"):
+    """Resume from the files `save_checkpoint` (or the reference, src/train_utils.py:96-97) wrote — the reference itself never
+    reads `training_state.bin` back, so this is an addition: weights into the (sub-)module `save_option` names,
+    optimizer moments / step and the schedule position restored, the next epoch index returned.  The engine's bf16 compute copy
+    follows at the next forward (parameter versions change)."""
+    target = getattr(model, "module", model)
+    if save_option == "text":
+        target = target.bart_model
+    elif save_option == "img":
+        target = target.img_encoder
+    elif save_option == "table":
+        target = target.table_encoder
+    sd = torch.load(os.path.join(ckpt_dir, "pytorch_model.bin"), map_location=map_location)
+    missing = target.load_state_dict(sd, strict=False)      # missing keys are tolerated as in the stage hand-offs (:116-122)
+    if missing.unexpected_keys:
+        raise KeyError("unexpected keys in %s/pytorch_model.bin: %s" % (ckpt_dir, missing.unexpected_keys[:4]))
+    eng = getattr(getattr(model, "module", model), "engine", None)
+    if eng is not None:
+        eng.mark_weights_dirty()
+    state = torch.load(os.path.join(ckpt_dir, "training_state.bin"), map_location=map_location)
+    if optimizer is not None and state.get("optimizer") is not None:
+        optimizer.load_state_dict(state["optimizer"])
+    if scheduler is not None and state.get("scheduler") is not None:
+        scheduler.load_state_dict(state["scheduler"])
+    return int(state["epoch"]) + 1
 
 
 class AverageMeter:

@@ -101,6 +101,44 @@ def test_average_meter():
     assert m.val == 5.0 and m.count == 6 and m.sum == 18.0 and m.avg == 3.0
 
 
+def test_checkpoint_resume_round_trip(tmp_path):
+    """save_checkpoint -> load_checkpoint: weights, optimizer moments and the schedule position come back; the next epoch index is
+    returned; files with foreign keys are refused."""
+    from multimodalsum_b200.optim import LinearWarmupSchedule
+
+    def make():
+        torch.manual_seed(0)
+        m = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.Linear(4, 2))
+        o = torch.optim.AdamW(m.parameters(), lr=1e-2)
+        return m, o, LinearWarmupSchedule(o, 2, 10)
+
+    m, o, sch = make()
+    for _ in range(3):
+        o.zero_grad()
+        m(torch.ones(1, 4)).sum().backward()
+        o.step()
+        sch.step()
+    TU.save_checkpoint(m, o, sch, 1, str(tmp_path / "c"))
+    m2, o2, s2 = make()
+    assert TU.load_checkpoint(m2, o2, s2, str(tmp_path / "c")) == 2
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    assert s2.last_epoch == 3 and o2.param_groups[0]["lr"] == o.param_groups[0]["lr"]
+    k = next(iter(o.state))
+    k2 = next(iter(o2.state))
+    assert torch.equal(o.state[k]["exp_avg"], o2.state[k2]["exp_avg"]) and o2.state[k2]["step"] == o.state[k]["step"]
+    for mm, oo, ss in ((m, o, sch), (m2, o2, s2)):                  # both continue identically
+        oo.zero_grad()
+        mm(torch.ones(1, 4)).sum().backward()
+        oo.step()
+        ss.step()
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    sd = torch.load(tmp_path / "c" / "pytorch_model.bin")
+    sd["bogus.weight"] = torch.zeros(1)
+    torch.save(sd, tmp_path / "c" / "pytorch_model.bin")
+    with pytest.raises(KeyError, match="unexpected keys"):
+        TU.load_checkpoint(m2, o2, s2, str(tmp_path / "c"))
+
+
 class _StubModel(torch.nn.Module):
     """Stands in for the four stage modules on the CPU: records how it was called, returns a loss that depends on one tensor of
     the batch and on its parameters (so backward / clip / step do something)."""
