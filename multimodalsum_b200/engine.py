@@ -178,7 +178,7 @@ class StepEngine:
                 p.data = v
                 self.params[n] = p
         self.anchor = torch.zeros(1, device=dev, requires_grad=True)
-        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)     # dropout step counter, incremented by every forward
+        self.step_dev = torch.full((1,), self.step_count, device=dev, dtype=torch.int32)   # dropout step counter, incremented by every forward
         self.bound = True
         self._w16_fresh = False
 
@@ -212,6 +212,19 @@ class StepEngine:
         except Exception:
             rank = 0
         return (torch.initial_seed() ^ (0x5EED + rank * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
+
+    def rng_state(self):
+        """What the dropout masks of the next step depend on besides the layer / element index: saved by
+        train_utils.save_checkpoint, so a resumed run draws the masks the uninterrupted run would have drawn."""
+        return {"seed": int(self.seed), "step_count": int(self.step_count)}
+
+    def set_rng_state(self, state):
+        self.seed = int(state["seed"]) & 0xFFFFFFFFFFFFFFFF
+        self.step_count = int(state["step_count"])
+        if getattr(self, "step_dev", None) is not None:
+            self.step_dev.fill_(self.step_count)
+        self._graphs.clear()                      # recorded graphs baked the old seed into their kernel arguments
+        self._graph_entry = None
 
     def _param_versions(self):
         return sum(p._version for p in self.params.values())

@@ -54,6 +54,9 @@ def save_checkpoint(model, optimizer, scheduler, epoch, ckpt_dir, save_option="w
     torch.save(sd, os.path.join(ckpt_dir, "pytorch_model.bin"))
     state = {"epoch": epoch, "optimizer": optimizer.state_dict() if optimizer is not None else None,
              "scheduler": scheduler.state_dict() if scheduler is not None else None}
+    eng = getattr(getattr(model, "module", model), "engine", None)
+    if eng is not None:
+        state["engine"] = eng.rng_state()        # dropout seed + step counter (a key the reference never reads)
     torch.save(state, os.path.join(ckpt_dir, "training_state.bin"))
     return ckpt_dir
 
@@ -82,6 +85,8 @@ def load_checkpoint(model, optimizer, scheduler, ckpt_dir, save_option="whole", 
         optimizer.load_state_dict(state["optimizer"])
     if scheduler is not None and state.get("scheduler") is not None:
         scheduler.load_state_dict(state["scheduler"])
+    if eng is not None and state.get("engine") is not None:
+        eng.set_rng_state(state["engine"])       # the resumed run draws the dropout masks the uninterrupted run would have
     return int(state["epoch"]) + 1
 
 

@@ -215,3 +215,27 @@ def test_library_is_tied_to_the_sources_it_was_built_from(monkeypatch):
         _lib.lib()
     monkeypatch.setenv("MMSUM_ALLOW_STALE_LIB", "1")              # explicit override (A/B tooling)
     assert _lib.lib() is not None
+
+
+def test_engine_rng_state_round_trip_cpu():
+    """Dropout stream state (seed, step counter) is checkpointable: set before or after the arenas are bound, the device-side step
+    counter follows; the default seed follows torch.manual_seed and differs per data-parallel rank."""
+    from multimodalsum_b200.modules import MultimodalSum, YelpTableEncoder
+    cfg = ModelConfig(dataset="yelp", encoder_layers=1, decoder_layers=1, ffn_dim=64, vocab_size=300, max_position_embeddings=128)
+    torch.manual_seed(11)
+    a = StepEngine(cfg, device="cpu")
+    torch.manual_seed(12)
+    b = StepEngine(cfg, device="cpu")
+    assert a.seed != b.seed and a.rng_state() == {"seed": a.seed, "step_count": 0}
+    os.environ["RANK"] = "3"
+    try:
+        torch.manual_seed(11)
+        assert StepEngine(cfg, device="cpu").seed != a.seed          # same torch seed, another rank: other masks
+    finally:
+        del os.environ["RANK"]
+    a.set_rng_state({"seed": 2 ** 63 + 5, "step_count": 7})           # before bind(): the counter is created from it
+    model = MultimodalSum(TableEncoder=YelpTableEncoder, config=cfg)
+    a.bind(model.named_parameters())
+    assert a.rng_state() == {"seed": 2 ** 63 + 5, "step_count": 7} and int(a.step_dev.item()) == 7
+    a.set_rng_state({"seed": 9, "step_count": 21})                    # after bind(): the device counter is rewritten
+    assert int(a.step_dev.item()) == 21 and a.seed == 9 and a._graphs == {}
