@@ -148,10 +148,16 @@ class StagedPrefetcher:
             slot.hint = int((m.ne(0).to(torch.int32) * torch.arange(1, S + 1, dtype=torch.int32)).max().item()) if m.numel() else 0
         if self.cuda and slot.ready is not None and slot.pinned:
             slot.ready.synchronize()            # the pinned mirrors are rewritten by the host below: their last H2D copy is done
+        n_alloc = self.allocations
         for name, t in host.items():            # (re)allocation happens on the caller's stream, outside the copy-stream scope
             self._slot_tensor(slot, name, t)
             slot.rows[name] = t.shape[0] if t.dim() > 0 else None
             host[name] = self._stage_host(slot, name, t)
+        if self.cuda and self.allocations != n_alloc:
+            # a new block may be recycled memory whose last use is still queued on the caller's stream (the caching allocator
+            # orders re-use only within the allocating stream): the copy stream must not write into it before that work is done.
+            # Happens for the first n_stage batches (and on a shape change), never in steady state.
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with (torch.cuda.stream(self.stream) if self.cuda else contextlib.nullcontext()):
             if self.cuda and slot.free is not None:
                 self.stream.wait_event(slot.free)
