@@ -11,6 +11,7 @@
                                       module globals `args` / `field` they read are bound here), on prefetch.*_data_prefetcher;
                                       `stage=` 'text' | 'img' | 'table' gives the loops of src/text_pretrain.py:151-207,
                                       src/img_pretrain.py:178-238, src/table_pretrain.py:242-303
+  make_test_loop -> test              src/test.py:137-165            generation over a loader (get_multimodal_outputs + generate)
   train_model                         src/train_utils.py:65-97       epochs, sampler epochs, validation, early stopping, files
   AverageMeter                        src/utils.py:40-56
 The files interchange with the reference: `state_dict` keys / shapes are the reference's, the optimizer state
@@ -212,6 +213,45 @@ def make_loops(args, field=None, log=print, stage="multimodal", device=None):
         return losses.avg
 
     return train, validate
+
+
+def make_test_loop(args, field, log=print, device=None):
+    """-> `test(test_dataloader, model, tokenizer)` of src/test.py:137-165: beam-search summaries for every business of the loader.
+    `args` needs dataset, num_beams, length_penalty, max_length.  The body is the reference's: memories from
+    `model.get_multimodal_outputs`, zero `rating_diff`, `model.bart_model.generate(..., no_repeat_ngram_size=3,
+    early_stopping=True)`; `tokenizer` may be None (token-id lists are returned undecoded)."""
+    from . import prefetch
+    Prefetcher = {"yelp": prefetch.yelp_data_prefetcher, "amazon": prefetch.amazon_data_prefetcher}.get(args.dataset)
+    if Prefetcher is None:
+        raise ValueError("args.dataset must be 'yelp' or 'amazon'")
+
+    def test(test_dataloader, model, tokenizer):
+        model.eval()
+        prefetcher = Prefetcher(test_dataloader, device=device)
+        reviews, reviews_mask, reviews_rating, field_value, img, img_mask = prefetcher.next()
+        i = 0
+        generated_list = []
+        while reviews is not None:
+            try:
+                log("%d / %d" % (i + 1, len(test_dataloader)))
+            except TypeError:                      # a loader without a length
+                log("%d" % (i + 1))
+            with torch.no_grad():
+                _, text_hiddens, text_attention_mask, table_hiddens, table_attention_mask, img_hiddens, img_attention_mask = \
+                    model.get_multimodal_outputs(reviews, reviews_mask, field, field_value, img, img_mask)
+                rating_diff = torch.zeros([text_hiddens.size(0), 1], device=text_hiddens.device)
+                generated = model.bart_model.generate(text_hiddens, text_attention_mask, table_hiddens, table_attention_mask,
+                                                      img_hiddens, img_attention_mask, rating_diff=rating_diff,
+                                                      num_beams=args.num_beams, length_penalty=args.length_penalty,
+                                                      max_length=args.max_length, no_repeat_ngram_size=3, early_stopping=True)
+            generated_list.extend(generated)
+            reviews, reviews_mask, reviews_rating, field_value, img, img_mask = prefetcher.next()
+            i += 1
+        if tokenizer is not None:
+            generated_list = [tokenizer.decode(g, skip_special_tokens=True, clean_up_tokenization_spaces=False) for g in generated_list]
+        return generated_list
+
+    return test
 
 
 def train_model(args, model, train_sampler, train_dataloader, val_dataloader, train, validate, optimizer, scheduler, t_epoch,

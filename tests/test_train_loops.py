@@ -216,6 +216,38 @@ def test_stage_loops_call_the_model_as_the_reference_scripts_do(stage):
         TU.make_loops(args, field, stage="bogus")
 
 
+def test_generation_loop_of_test_py_on_stubs():
+    """make_test_loop: the body of src/test.py:137-165 — one get_multimodal_outputs + generate per batch with the reference's
+    arguments, summaries of all businesses in loader order, decoded when a tokenizer is given."""
+    cfg = ModelConfig(dataset="yelp", **SMALL)
+    bs = [make_batch(cfg, n, seed=s, n_reviews=2, max_imgs=2) for s, n in ((1, 2), (2, 1))]
+    seen = []
+
+    class _Bart:
+        def generate(self, th, tm, tbh, tbm, ih, im, **kw):
+            seen.append((tuple(th.shape), kw["rating_diff"].shape, {k: v for k, v in kw.items() if k != "rating_diff"}, torch.is_grad_enabled()))
+            return torch.arange(th.size(0) * 3).reshape(th.size(0), 3) + 10 * len(seen)
+
+    class _Model(torch.nn.Module):
+        bart_model = _Bart()
+
+        def get_multimodal_outputs(self, reviews, reviews_mask, field, field_value, img, img_mask):
+            assert field.shape == (47, 6) and len(field_value) == 6 and not self.training
+            B = reviews.size(0)
+            return (reviews.size(1), torch.zeros(B, 2, 128, 4), reviews_mask, torch.zeros(B, 1, 47, 4), torch.ones(B, 1, 47),
+                    torch.zeros(B, 2, 196, 4), torch.ones(B, 2, 196))
+
+    args = types.SimpleNamespace(dataset="yelp", num_beams=4, length_penalty=1.0, max_length=128)
+    logs = []
+    test = TU.make_test_loop(args, bs[0].field, log=logs.append, device="cpu")
+    out = test([_tuple(b) for b in bs], _Model(), None)
+    assert [o.tolist() for o in out] == [[10, 11, 12], [13, 14, 15], [20, 21, 22]] and logs == ["1 / 2", "2 / 2"]
+    want_kw = dict(num_beams=4, length_penalty=1.0, max_length=128, no_repeat_ngram_size=3, early_stopping=True)
+    assert seen == [((2, 2, 128, 4), torch.Size([2, 1]), want_kw, False), ((1, 2, 128, 4), torch.Size([1, 1]), want_kw, False)]
+    tok = types.SimpleNamespace(decode=lambda g, skip_special_tokens, clean_up_tokenization_spaces: " ".join(str(int(x)) for x in g))
+    assert test([_tuple(bs[1])], _Model(), tok) == ["30 31 32"]
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _tuple(b):
     return (b.reviews, b.reviews_mask, b.reviews_rating, *b.field_value, b.img, b.img_mask)
