@@ -239,3 +239,30 @@ def test_engine_rng_state_round_trip_cpu():
     assert a.rng_state() == {"seed": 2 ** 63 + 5, "step_count": 7} and int(a.step_dev.item()) == 7
     a.set_rng_state({"seed": 9, "step_count": 21})                    # after bind(): the device counter is rewritten
     assert int(a.step_dev.item()) == 21 and a.seed == 9 and a._graphs == {}
+
+
+def test_c_abi_rejects_invalid_arguments_on_the_host():
+    """Error behaviour of the boundary (include/mmsum_b200.h): invalid arguments are detected on the host BEFORE any launch and come
+    back as a negative status (-1 invalid argument, -2 driver / tensor-map failure) — no exception, no crash, no device needed;
+    the Python side turns any non-zero status into MmsumError."""
+    import ctypes as C
+    L = _lib.lib()
+    i64, i32 = C.c_int64, C.c_int32
+    assert L.mmsum_gemm_bf16(None, None) == -1
+    assert L.mmsum_gemm_bf16(C.byref(_lib.GemmArgs()), None) == -1                              # null operands
+    ok = dict(A=4096, B=4096, D=4096, lda=64, ldb=64, ldd=64, M=128, N=128, K=64)
+    for bad in (dict(M=0), dict(K=-3), dict(accumulate=1), dict(aux_mode=1), dict(block_n=96), dict(splits=2),
+                dict(out_f32=1, act=1), dict(A=4097)):                                         # misaligned pointer: TMA needs 16 B
+        assert L.mmsum_gemm_bf16(C.byref(_lib.GemmArgs(**dict(ok, **bad))), None) < 0, bad
+    for fn in (L.mmsum_attn_fwd, L.mmsum_attn_bwd, L.mmsum_attn_decode_cross):
+        assert fn(None, None) == -1 and fn(C.byref(_lib.AttnArgs()), None) == -1
+    a = _lib.AttnArgs(Q=4096, KV=4096, O=4096, LSE=4096, ldq=1024, ldkv=1024, ldo=1024, n_qseq=1, H=16, R=1, n_mod=5)
+    assert L.mmsum_attn_fwd(C.byref(a), None) == -1                                             # at most 3 memory modalities
+    assert L.mmsum_table_fwd(None, None) == -1 and L.mmsum_table_fwd(C.byref(_lib.TableArgs(dataset=7, B=1)), None) == -1
+    assert L.mmsum_cast_f32_bf16(None, None, i64(16), None) == -1
+    assert L.mmsum_cast_f32_bf16(C.c_void_p(4096), C.c_void_p(4096), i64(-1), None) == -1
+    assert L.mmsum_colsum(None, i64(8), i32(4), i32(8), None, None) == -1
+    assert L.mmsum_grad_sumsq(None, i64(4), None, i32(4), None, None) == -1
+    with pytest.raises(_lib.MmsumError, match="rc=-1"):
+        _lib.check(-1, "mmsum_gemm_bf16")
+    _lib.check(0, "mmsum_gemm_bf16")
