@@ -259,8 +259,8 @@ class KernelTimer:
 
 
 TENSOR_KINDS = ("gemm", "attn_cross_fwd", "attn_cross_bwd", "attn_self_fwd", "attn_self_bwd")
-KERNEL_OF = {"gemm": "gemm_tcgen05_kernel", "attn_cross_fwd": "attn_fwd_tc2_kernel (multi-entity cross-attention)",
-             "attn_cross_bwd": "attn_bwd_dq_tc_kernel + attn_bwd_dkv_tc_kernel (cross)", "attn_self_fwd": "attn_fwd_tc2_kernel (self)",
+KERNEL_OF = {"gemm": "gemm_tcgen05_kernel", "attn_cross_fwd": "attn_fwd_tc3_kernel (multi-entity cross-attention)",
+             "attn_cross_bwd": "attn_bwd_dq_tc_kernel + attn_bwd_dkv_tc_kernel (cross)", "attn_self_fwd": "attn_fwd_tc3_kernel (self)",
              "attn_self_bwd": "attn_bwd_dq_tc_kernel + attn_bwd_dkv_tc_kernel (self)", "add_ln_fwd": "add_ln_fwd_kernel",
              "add_ln_bwd": "add_ln_bwd_kernel", "embed_ln_fwd": "embed_ln_fwd_kernel", "ce_fwd": "ce_fwd_bwd_kernel (loss pass)",
              "ce_bwd": "ce_fwd_bwd_kernel (gradient pass)", "colsum": "colsum_kernel", "gate": "gate_fwd/bwd kernels"}

@@ -266,3 +266,24 @@ def test_c_abi_rejects_invalid_arguments_on_the_host():
     with pytest.raises(_lib.MmsumError, match="rc=-1"):
         _lib.check(-1, "mmsum_gemm_bf16")
     _lib.check(0, "mmsum_gemm_bf16")
+
+
+def test_bench_roofline_arithmetic():
+    """bench.roofline_kernels: achieved = algorithmic work / summed event time; tensor kernels against the sustained bf16 peak in
+    TFLOP/s, the others against the HBM peak in GB/s; shares are of the step time; ncu DRAM traffic attached where captured."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    peaks = dict(hbm_gbs=6500.0, tf_burst=1600.0, tf_sustained=1400.0, source="measured")
+    agg = {"gemm": [984, 2 * 58.0e12, 2 * 46.0], "add_ln_fwd": [120, 120 * 113.2e6, 120 * 0.0283], "idle": [1, 0.0, 0.0]}
+    rk = bench.roofline_kernels(agg, 2, peaks, 93.5, {"gemm": {"dram_bytes": 1.0}})
+    assert set(rk) == {"gemm", "add_ln_fwd"}                                   # kinds without time are dropped
+    g, l = rk["gemm"], rk["add_ln_fwd"]
+    assert g["bound"] == "tensor" and g["unit"] == "TFLOP/s" and g["peak"] == 1400.0 and g["launches_per_step"] == 492
+    assert g["achieved"] == pytest.approx(58.0e12 / 46.0e-3 / 1e12) and g["frac"] == pytest.approx(g["achieved"] / 1400.0)
+    assert g["share_of_step"] == pytest.approx(46.0 / 93.5) and g["traffic"] == {"dram_bytes": 1.0} and g["kernel"] == "gemm_tcgen05_kernel"
+    assert l["bound"] == "hbm" and l["unit"] == "GB/s" and l["peak"] == 6500.0 and l["avg_us"] == pytest.approx(28.3)
+    assert l["achieved"] == pytest.approx(113.2e6 / 28.3e-6 / 1e9) and "traffic" not in l
+    p = bench.load_peaks()
+    assert p["tf_sustained"] <= p["tf_burst"] and p["hbm_gbs"] > 1000 and p["source"] in ("measured", "fallback")
