@@ -447,7 +447,9 @@ def run_train(args):
         "roofline": {"kernel": "gemm_tcgen05_kernel (all %d GEMM launches of a step, timed in %d instrumented steps after the timed region)"
                                % (int(gemm.get("launches_per_step", 0)), n_inst),
                      "bound": "tensor", "achieved": gemm.get("achieved"), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": gemm.get("frac"), "traffic": traffic.get("gemm"),
+                     "frac": gemm.get("frac"),
+                     # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (committed capture, profiles/r02_traffic.json)
+                     "traffic": (traffic.get("gemm") or {}).get("dram_bytes_per_launch"), "traffic_detail": traffic.get("gemm"),
                      "peak_source": peaks["source"] + " (sustained bf16)", "gemm_share_of_step": gemm.get("share_of_step")},
         "roofline_kernels": rk,
         "build": _build_record(),
