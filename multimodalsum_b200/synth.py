@@ -275,3 +275,31 @@ def make_batch(cfg: ModelConfig, B, seed=1, n_reviews=9, seq_len=128, fixed_len=
         k = torch.full((B,), n_valid_imgs, dtype=torch.long)
     batch.img_mask = torch.arange(mi).unsqueeze(0) < k.unsqueeze(1)
     return batch
+
+
+class SyntheticDataset(torch.utils.data.Dataset):
+    """Map-style dataset with the item layout of the reference's `MultimodalDataset.__getitem__` (src/multimodal_train.py:63-86):
+    one business per item — (reviews [R,S], reviews_mask, reviews_rating [R], <six table fields>, img [max_imgs,196,1024],
+    img_mask [max_imgs]) — so that `DataLoader(..., pin_memory=True)` collates the 11-tuple the prefetchers expect, and `.field`
+    [47,6] / [6,1] as `data_train.field` (:59-62).  Items are generated from `seed + idx` on demand (deterministic, no storage);
+    image entries are pooled ResNet-101 stage-3 features, not pixels (the trunk is outside this path)."""
+
+    def __init__(self, cfg: ModelConfig, n_businesses, seed=0, **batch_kw):
+        if cfg.dataset not in ("yelp", "amazon"):
+            raise ValueError("SyntheticDataset mirrors the multimodal stage: cfg.dataset must be 'yelp' or 'amazon'")
+        self.cfg, self.n, self.seed, self.kw = cfg, int(n_businesses), int(seed), batch_kw
+        self.field = make_batch(cfg, 1, seed=seed, **batch_kw).field
+        self.epoch = 0
+
+    def __len__(self):
+        return self.n
+
+    def set_epoch(self):
+        """The reference re-draws its leave-one-out sampling between epochs (src/train_utils.py:72-73); here: new synthetic items."""
+        self.epoch += 1
+
+    def __getitem__(self, idx):
+        if not 0 <= idx < self.n:
+            raise IndexError(idx)
+        b = make_batch(self.cfg, 1, seed=self.seed + 1 + idx + self.epoch * self.n, **self.kw)
+        return (b.reviews[0], b.reviews_mask[0], b.reviews_rating[0], *[v[0] for v in b.field_value], b.img[0], b.img_mask[0])

@@ -206,3 +206,31 @@ def test_reference_training_loop_body_through_the_prefetcher_gpu():
         reviews, reviews_mask, reviews_rating, field_value, img, img_mask = prefetcher.next()
     assert got == want                                           # same kernels, same inputs, dropout 0: bit-equal losses
     assert model.engine._len_cache is None                       # the hint was used: the mask was never read back
+
+
+def test_synthetic_dataset_through_dataloader_and_prefetcher_cpu():
+    """The reference's data path end to end on the host: Dataset.__getitem__ (one business, src/multimodal_train.py:63-86) ->
+    DataLoader collate (drop_last=False) -> prefetcher.next() tuples of the shapes MultimodalSum.forward takes."""
+    from torch.utils.data import DataLoader
+    from multimodalsum_b200.synth import SyntheticDataset
+    for dataset, n_tab, n_img in (("yelp", 47, 10), ("amazon", 6, 1)):
+        cfg = ModelConfig(dataset=dataset, **SMALL)
+        data = SyntheticDataset(cfg, 5, seed=3, n_reviews=3, fixed_len=40)
+        assert len(data) == 5 and data.field.shape[0] == n_tab and len(data[0]) == 11
+        assert all(torch.equal(a, b) for a, b in zip(data[2], data[2]))                 # deterministic items
+        first = data[0][0].clone()
+        loader = DataLoader(data, batch_size=2, shuffle=False, num_workers=0, drop_last=False)
+        cls = PF.yelp_data_prefetcher if dataset == "yelp" else PF.amazon_data_prefetcher
+        sizes = []
+        for reviews, reviews_mask, reviews_rating, field_value, img, img_mask in cls(loader, device="cpu"):
+            B = reviews.shape[0]
+            sizes.append(B)
+            assert reviews.shape == (B, 3, 128) and reviews_mask.shape == (B, 3, 128) and reviews_rating.shape == (B, 3)
+            assert img.shape == (B, n_img, 196, 1024) and img_mask.shape == (B, n_img) and img_mask.dtype == torch.bool
+            assert len(field_value) == 6 and all(v.shape[0] == B and v.dtype == torch.int64 for v in field_value)
+            assert reviews_mask.max_review_len == 40
+        assert sizes == [2, 2, 1]
+        data.set_epoch()
+        assert not torch.equal(data[0][0], first)                                       # a new epoch draws new items
+        with pytest.raises(IndexError):
+            data[5]

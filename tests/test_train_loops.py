@@ -314,3 +314,20 @@ def test_epoch_bodies_match_a_hand_written_loop_gpu(tmp_path):
     missing = re.load_state_dict(torch.load(tmp_path / "ckpt" / "pytorch_model.bin"), strict=False)
     assert not missing.unexpected_keys
     assert torch.load(tmp_path / "ckpt" / "training_state.bin")["epoch"] == 0
+
+
+def test_train_synthetic_script_keeps_the_reference_flags():
+    """tools/train_synthetic.py (main() of src/multimodal_train.py on the drop-in): the reference's flags and defaults (:411-439)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "train_synthetic.py")
+    spec = importlib.util.spec_from_file_location("train_synthetic", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    a = mod.parse([])
+    assert (a.dataset, a.batch_size, a.num_epochs, a.warmup_ratio, a.max_grad_norm, a.learning_rate, a.label_smoothing,
+            a.early_stopping, a.workers, a.local_rank) == ("yelp", 1, 5, 0.05, 1, 1e-5, 0.1, False, 4, 0)
+    b = mod.parse(["--dataset", "amazon", "--early_stopping", "true", "--batch_size", "16"])
+    assert b.dataset == "amazon" and b.early_stopping is True and b.batch_size == 16
+    with pytest.raises(SystemExit):
+        mod.parse(["--early_stopping", "maybe"])
