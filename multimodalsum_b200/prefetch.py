@@ -181,8 +181,10 @@ class StagedPrefetcher:
         return v
 
     def next(self):
-        """The staged batch as the reference's tuple (views of the slot, valid until `n_stage - 1` further `next()` calls), or all
-        None at the end of the loader; the following batch starts copying before this returns."""
+        """The staged batch as the reference's tuple (views of a slot), or all None at the end of the loader; the following batch
+        starts copying before this returns.  Contract (the reference loop's own pattern): all GPU work that reads a batch is
+        enqueued before `next()` is called again — the slot is re-used `n_stage - 1` calls later and its rewrite waits only for
+        work enqueued up to the call that followed its own."""
         cur = torch.cuda.current_stream(self.device) if self.cuda else None
         if self.cuda and self.last_served is not None:
             # everything enqueued so far used the previous batch at the latest: its slot is free once that work is done

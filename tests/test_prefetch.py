@@ -38,7 +38,7 @@ def _check_stream(pf_cls, batches, to_tuple, device, transform=lambda t: t, n_st
     served = []
     out = pf.next()
     while (out[0][0] if isinstance(out[0], list) else out[0]) is not None:
-        served.append(_snapshot(out))                            # a served batch lives n_stage - 1 further calls: copy it out
+        served.append(_snapshot(out))                            # a slot is re-used n_stage - 1 calls later: copy the batch out
         out = pf.next()
     assert all(x is None for g in out for x in (g if isinstance(g, list) else [g]))       # end of loader: every element None
     assert len(served) == len(batches)
@@ -67,7 +67,7 @@ def test_multimodal_prefetcher_tuples_and_contents_cpu(dataset):
     assert pf.h2d_bytes == sum(b.nbytes() - b.field.numel() * 8 for b in batches)
 
 
-def test_slot_reuse_keeps_served_batches_intact_for_n_stage_minus_one_calls():
+def test_slot_reuse_distance():
     cfg = ModelConfig(dataset="yelp", **SMALL)
     batches = _loader(cfg, [2] * 6)
     pf = PF.yelp_data_prefetcher([_yelp_tuple(b) for b in batches], device="cpu", n_stage=3)
@@ -77,7 +77,7 @@ def test_slot_reuse_keeps_served_batches_intact_for_n_stage_minus_one_calls():
     assert all(torch.equal(a, b) for a, b in zip(_flat(first), keep))
     assert first[0].data_ptr() != second[0].data_ptr()
     pf.next()                                                    # stages batch 3 into the first slot again
-    assert torch.equal(first[0], batches[3].reviews)             # documented: a served batch is valid for n_stage - 1 more calls
+    assert torch.equal(first[0], batches[3].reviews)             # documented: the slot is re-used n_stage - 1 calls later
     # a fresh tensor object per batch carries the hint (the slot tensor itself is never annotated)
     assert not hasattr(pf.slots[0].dev["reviews_mask"], "max_review_len")
 
